@@ -1,0 +1,127 @@
+"""The oracle against the reference-generated golden vectors (CPU only).
+
+Every fixture under tests/golden/ was produced by the unmodified reference
+classes (tests/golden/make_golden.py).  The oracle must reproduce all of them
+before it is allowed to judge the CUDA path.
+"""
+import numpy as np
+import pytest
+
+from oracle import bruteforce_oracle as orc
+from conftest import golden_names, load_golden
+
+PRODUCT_CASES = [n for n in golden_names() if not n.startswith("solver_")]
+SOLVER_CASES = [n for n in golden_names() if n.startswith("solver_")]
+
+
+def _product(g, **kw):
+    return orc.kernel_product(
+        g["kernel"],
+        g["source_points"],
+        None if g["same_points"] else g["target_points"],
+        g["source_signal"],
+        normalize_rows=g["normalize_rows"],
+        density_estimation=g["density_estimation"],
+        **kw,
+    )
+
+
+@pytest.mark.parametrize("name", PRODUCT_CASES)
+def test_oracle_matches_reference_float64(name):
+    g = load_golden(name)
+    out = _product(g)
+    assert out.dtype == np.float64 and out.shape == g["truth"].shape
+    assert orc.rel_l2(out, g["truth"]) <= 1e-12
+
+
+@pytest.mark.parametrize("name", PRODUCT_CASES)
+@pytest.mark.parametrize("variant,kw,tol", [
+    ("ref_f32_fast", dict(precision="float32", fast_sqdists=True), 2e-5),
+    ("ref_f32_slow", dict(precision="float32", fast_sqdists=False), 2e-6),
+    ("ref_f64_fast", dict(precision="float64", fast_sqdists=True), 1e-11),
+])
+def test_oracle_matches_reference_variants(name, variant, kw, tol):
+    g = load_golden(name)
+    if variant not in g:
+        pytest.skip("variant not stored for this case")
+    # float32 BLAS blocking differs from the reference's single GEMM, so only
+    # agreement at the float32 rounding level can be asked for
+    assert orc.rel_l2(_product(g, **kw), g[variant]) <= tol
+
+
+def test_groundtruth_call_equals_runner_call():
+    """datasets.py:187-189 calls prepare_data without flags; runner.py:78-83 passes
+    them.  Both are stored; on the difference path they agree bit for bit."""
+    g = load_golden("product_gaussian_cube_d3")
+    assert np.array_equal(g["truth"], g["truth_groundtruth_call"])
+
+
+@pytest.mark.parametrize("name", PRODUCT_CASES)
+def test_oracle_row_subset(name):
+    g = load_golden(name)
+    rows = np.array([0, 3, g["truth"].shape[0] // 2, g["truth"].shape[0] - 1])
+    out = _product(g, rows=rows)
+    assert orc.rel_l2(out, g["truth"][rows]) <= 1e-12
+
+
+@pytest.mark.parametrize("name", PRODUCT_CASES)
+def test_oracle_row_blocking_is_irrelevant(name):
+    g = load_golden(name)
+    assert orc.rel_l2(_product(g, row_block=7), g["truth"]) <= 1e-12
+
+
+def test_inverse_distance_zeroing_rule():
+    """Flat indices that are multiples of M+1 are zeroed (bruteforce.py:12-14):
+    with N > M+1 that is more than the diagonal."""
+    g = load_golden("product_invdist_tall_d3")
+    K = orc.dense_kernel_matrix("inverse-distance", g["source_points"], g["target_points"])
+    N, M = K.shape
+    zeros = {(i, j) for i, j in zip(*np.nonzero(K == 0))}
+    expect = {(f // M, f % M) for f in range(0, N * M, M + 1)}
+    assert zeros == expect and len(expect) > min(N, M)
+
+
+def test_known_answers():
+    # coincident points -> k = 1; |x-y|^2 = 1 -> e^-1 (gaussian and absolute-exponential)
+    y = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0]])
+    b = np.array([[1.0], [0.0]])
+    for kernel in ("gaussian", "absolute-exponential"):
+        out = orc.kernel_product(kernel, y, None, b)
+        assert np.allclose(out[:, 0], [1.0, np.exp(-1.0)], rtol=1e-15)
+    # attention output of a constant signal is that constant
+    g = load_golden("attention_gaussian_d64_e8")
+    c = np.full((g["source_points"].shape[0], 2), 3.25)
+    out = orc.kernel_product("gaussian", g["source_points"], g["target_points"], c, normalize_rows=True)
+    assert np.allclose(out, 3.25, rtol=1e-13)
+    # symmetry <u, K v> = <K u, v> when x == y
+    g = load_golden("product_gaussian_cube_d3")
+    rng = np.random.RandomState(0)
+    u, v = rng.randn(600, 1), rng.randn(600, 1)
+    Ku = orc.kernel_product("gaussian", g["source_points"], None, u)
+    Kv = orc.kernel_product("gaussian", g["source_points"], None, v)
+    assert abs((u * Kv).sum() - (Ku * v).sum()) <= 1e-10 * abs((u * Kv).sum())
+
+
+def test_unsupported_kernel():
+    with pytest.raises(NotImplementedError):
+        orc.kernel_product("laplace", np.zeros((2, 3)), None, np.zeros((2, 1)))
+
+
+@pytest.mark.parametrize("name", SOLVER_CASES)
+def test_solver_oracle(name):
+    g = load_golden(name)
+    lam = float(g["lam"])
+    # the reference's lstsq on the un-regularised system: reproduce its residual
+    # (its solution is ill-posed: cond(K) ~ 1e20)
+    x_ref = g["ref_lstsq_unregularised"]
+    x_orc = orc.kernel_solve_lstsq(g["kernel"], g["source_points"], g["rhs_unregularised"])
+    res_ref = orc.rel_l2(orc.regularised_matvec(g["kernel"], g["source_points"], x_ref, 0.0), g["rhs_unregularised"])
+    res_orc = orc.rel_l2(orc.regularised_matvec(g["kernel"], g["source_points"], x_orc, 0.0), g["rhs_unregularised"])
+    assert res_ref <= 1e-9 and res_orc <= 1e-9
+    # the regularised SPD system the CG solver is scored on
+    x_spd = orc.kernel_solve_spd(g["kernel"], g["source_points"], g["rhs"], lam)
+    assert orc.rel_l2(x_spd, g["spd_solution"]) <= 1e-10
+    assert orc.rel_l2(orc.regularised_matvec(g["kernel"], g["source_points"], x_spd, lam), g["rhs"]) <= 1e-12
+    # rhs = K b + lam b  =>  the SPD solution is the generator's signal
+    cond_limited = 1e-6 if lam >= 1 else 1e-3
+    assert orc.rel_l2(x_spd, g["source_signal"]) <= cond_limited
