@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Headline benchmark: Gaussian kernel product K.b, N = M = 1M, D = 3, E = 1 (BASELINE.json config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A step is one pass of the hot path over the whole synthetic problem: a_i = sum_j exp(-|x_i-y_j|^2) b_j
+for all N targets.  With N > 1 GPUs the target rows are sharded (strong scaling: the problem is
+fixed), sources are replicated, no collective sits on the data path.  Rank 0 prints ONE JSON line.
+
+  value     Gpairs/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       same metric through the plugin call sequence (runner.py:73-143) with HOST float64
+            arrays: cast + H2D of points and signal, query, D2H of the result inside the timer
+  roofline  the dominant kernel against the FP32/MUFU pipe roofline of SURVEY.md section 8(d):
+            16 pairs/clk/SM x SMs x clocks.max.sm (this path is compute bound: its compulsory
+            HBM traffic is 32 MB per 10^12 pairs)
+  cpu_baseline / --impl reference
+            the reference algorithm (NumPy port in oracle/, the reference itself is pure Python
+            and does not travel to the GPU box) on a bounded row sample, all host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "gaussian_kernel_product_gpairs_per_s"
+UNIT = "Gpairs/s"
+PAIRS_PER_CLK_PER_SM = 16.0  # MUFU lanes per SM per clock == issue bound of the 8-slot pair
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000, help="N = M (default: the BASELINE config, 1M)")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = sized for ~15 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(n, n_gpus):
+    return {
+        "workload": f"C2: gaussian kernel product N=M={n}, D=3, E=1 (datasets.uniform_cube semantics)",
+        "kernel": "gaussian",
+        "N": n,
+        "M": n,
+        "D": 3,
+        "E": 1,
+        "sharding": f"target rows over {n_gpus} GPU(s), sources replicated, no collective",
+        "l2": "flushed between timed steps (256 MiB write)",
+    }
+
+
+def read_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+
+
+def cpu_reference_sample(ds, rows, precision="float32", fast_sqdists=True):
+    """The reference algorithm (bruteforce.py:25-58 + :153) on `rows` target rows x all sources,
+    in its fastest configuration (float32, BLAS squared distances).  Returns seconds."""
+    from oracle import bruteforce_oracle as orc
+
+    t0 = time.perf_counter()
+    orc.kernel_product(ds.kernel, ds.source_points, None, ds.source_signal, precision=precision,
+                       fast_sqdists=fast_sqdists, rows=rows, row_block=64)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(ds, n_rows):
+    rows = np.random.RandomState(1).choice(ds.N, n_rows, replace=False)
+    rows.sort()
+    secs = cpu_reference_sample(ds, rows)
+    pairs = float(n_rows) * ds.M
+    return {
+        "value": pairs / secs / 1e9,
+        "unit": UNIT,
+        "cores": os.cpu_count(),
+        "kind": "port",
+        "sample": f"{n_rows} target rows x {ds.M} sources ({pairs:.2e} pairs, {secs:.1f} s), NumPy port of "
+                  f"bruteforce.py float32 fast_sqdists=True: OpenBLAS GEMM on all cores, exp/broadcast ufuncs single-threaded",
+    }
+
+
+def pick_cpu_rows(ds, requested):
+    if requested:
+        return requested
+    # ~1.5e8 pairs/s measured for this variant in the survey; aim at ~15 s
+    return int(max(64, min(ds.N, 2.0e9 // ds.M)))
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU algorithm on a bounded sample per step (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from kernel_matrix_benchmarks_b200 import datasets
+
+    ds = datasets.config_c2(args.n)
+    n_rows = pick_cpu_rows(ds, args.cpu_rows)
+    rows = np.sort(np.random.RandomState(1).choice(ds.N, n_rows, replace=False))
+    for _ in range(args.warmup):
+        cpu_reference_sample(ds, rows[: max(8, n_rows // 16)])
+    secs = [cpu_reference_sample(ds, rows) for _ in range(args.steps)]
+    ms = 1e3 * sum(secs) / len(secs)
+    pairs = float(n_rows) * ds.M
+    value = pairs / (ms * 1e-3) / 1e9
+    sample = (f"each step = {n_rows} target rows x {ds.M} sources ({pairs:.2e} pairs) of the C2 workload; "
+              "NumPy port of bruteforce.py (float32, fast_sqdists=True), OpenBLAS on all cores")
+    print(json.dumps({
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.n, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        clocks, powers, reasons, sm_max = [], [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                clocks.append(float(f[1]))
+                sm_max = float(f[2])
+                powers.append(float(f[3]))
+                for name, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if clocks:
+            # "under load": samples at or above the median power
+            med_p = float(np.median(powers))
+            loaded = [c for c, p in zip(clocks, powers) if p >= med_p] or clocks
+            out.update(sm_mhz=float(np.median(loaded)), sm_max_mhz=sm_max, reasons=sorted(reasons), samples=len(clocks),
+                       power_w_max=max(powers))
+        return out
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from kernel_matrix_benchmarks_b200 import datasets, product
+    from kernel_matrix_benchmarks_b200.algorithms.b200 import B200Product
+    from kernel_matrix_benchmarks_b200.solver import shard_bounds
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ds = datasets.config_c2(args.n)  # same seeded arrays on every rank
+    N, M = ds.N, ds.M
+    lo, hi, _ = shard_bounds(N, rank, world)
+    pairs_total = float(N) * float(M)
+
+    # ---- device-resident arm ---------------------------------------------------------------
+    y = torch.from_numpy(ds.source_points.astype(np.float32)).to(dev)
+    b = torch.from_numpy(ds.source_signal.astype(np.float32)).to(dev)
+    x = y[lo:hi]
+    out = torch.empty((hi - lo, 1), dtype=torch.float32, device=dev)
+    ws = product.Workspace()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        product.kernel_product(x, y, b, kernel="gaussian", path="direct", row_offset=lo, out=out, workspace=ws)
+
+    product.set_profiling(True)
+    for _ in range(args.warmup):
+        step()
+    launches_per_step = product.last_launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    for e0, e1 in ev:
+        flush.fill_(1)  # evict L2 between timed steps (outside the event bracket)
+        e0.record()
+        step()
+        e1.record()
+        kernel_ms.append(product.last_main_kernel_ms())
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = sum(a.elapsed_time(b_) for a, b_ in ev) / args.steps
+    step_ms = max_over_ranks(step_ms)
+    main_ms = max_over_ranks(sum(kernel_ms) / len(kernel_ms))
+    value = pairs_total / (step_ms * 1e-3) / 1e9
+
+    # ---- end-to-end arm: plugin API, host float64 arrays in, host float64 result out ------------
+    e2e = None
+    if not args.no_e2e:
+        xs_host = ds.source_points[lo:hi]
+
+        def e2e_step():
+            algo = B200Product(kernel="gaussian", dimension=3, normalize_rows=False, precision="float32", path="direct",
+                               device=local_rank)
+            if world == 1:
+                algo.prepare_data(source_points=ds.source_points, target_points=ds.source_points, same_points=True)
+            else:
+                algo.prepare_data(source_points=ds.source_points, target_points=xs_host, same_points=False)
+            algo.fit()
+            algo.prepare_query(source_signal=ds.source_signal)
+            algo.query()
+            res = algo.get_result()
+            algo.done()
+            return res
+
+        for _ in range(max(1, min(2, args.warmup))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        e2e_ms = max_over_ranks(1e3 * dt / args.steps)
+        n_x = 0 if world == 1 else (hi - lo) * 3
+        e2e = {
+            "value": pairs_total / (e2e_ms * 1e-3) / 1e9,
+            "unit": UNIT,
+            "ms_per_step": e2e_ms,
+            "h2d_bytes_per_step": int(4 * (n_x + M * 3 + M * 1)),
+            "d2h_bytes_per_step": int(4 * (hi - lo)),
+            "api": "B200Product.prepare_data/fit/prepare_query/query/get_result, host float64 in/out",
+        }
+        assert res.shape == (hi - lo, 1)
+
+    if rank == 0:
+        peaks, peaks_src = read_peaks()
+        info = product.device_info(local_rank)
+        sm_max = float(clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or info["clock_khz"] / 1e3)
+        peak = PAIRS_PER_CLK_PER_SM * info["sm_count"] * sm_max * 1e6 / 1e9  # Gpairs/s per GPU
+        pairs_per_launch = float(hi - lo) * M  # rank 0's shard (the largest)
+        achieved = pairs_per_launch / (main_ms * 1e-3) / 1e9
+        roofline = {
+            "bound": "fp32_mufu",
+            "achieved": achieved,
+            "peak": peak,
+            "unit": UNIT,
+            "frac": achieved / peak,
+            "traffic": None,
+            "kernel": "kprod_direct_kernel<D=3,E=1,R=8,gaussian>",
+            "kernel_ms": main_ms,
+            "peak_basis": f"16 pairs/clk/SM x {info['sm_count']} SMs x {sm_max:.0f} MHz (clocks.max.sm); "
+                          f"MEASURED_PEAKS.json {peaks_src}: hbm {peaks.get('hbm_gbs')} GB/s not binding "
+                          f"(algorithmic HBM bytes/launch = {4 * ((hi - lo) * 3 + M * 4 + (hi - lo))})",
+            "frac_at_sampled_clock": (achieved / (PAIRS_PER_CLK_PER_SM * info["sm_count"] * clocks["sm_mhz"] * 1e-3)
+                                      if clocks.get("sm_mhz") else None),
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.n, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(ds, pick_cpu_rows(ds, args.cpu_rows))
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

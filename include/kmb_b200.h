@@ -1,0 +1,138 @@
+/* kmb_b200.h -- C ABI of libkmb_b200.so: the B200 (sm_100a) kernel-matrix hot path.
+ *
+ * The reference (kernel-matrix-benchmarks) is pure Python: its hot path is
+ * kernel_matrix_benchmarks/algorithms/bruteforce.py, called through the plugin
+ * interface of algorithms/base.py.  It has no FFI of its own, so this header
+ * declares what a ctypes binding for that path binds (INTEGRATION.md shows the
+ * stub); each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a KMB_ERR_* code otherwise; the
+ *     message for the calling thread is kmb_last_error().  No exceptions, no
+ *     torch types, no hidden allocation: all device buffers (inputs, outputs,
+ *     workspace) belong to the caller.
+ *   - "device pointer" arguments are fp32, row-major, contiguous, 16-byte
+ *     aligned, resident on the current CUDA device; `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream).  Calls are asynchronous
+ *     on `stream` unless stated otherwise.
+ *   - sizes are int64_t; D (point dimension) and E (signal dimension) are int.
+ *   - not thread-safe per stream/workspace (the reference's caller,
+ *     runner.py:70-176, is single-threaded).
+ */
+#ifndef KMB_B200_H
+#define KMB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMB_ABI_VERSION 1
+
+/* error codes */
+enum {
+    KMB_OK = 0,
+    KMB_ERR_INVALID = 1,     /* bad argument (NULL pointer, negative size, ...) */
+    KMB_ERR_UNSUPPORTED = 2, /* kernel / path / shape not implemented -> NotImplementedError in Python,
+                                as bruteforce.py:82-85 does for unknown kernels */
+    KMB_ERR_WORKSPACE = 3,   /* workspace too small */
+    KMB_ERR_CUDA = 4         /* a CUDA runtime call failed; message carries cudaGetErrorString */
+};
+
+/* kernel functions: bruteforce.py:18-22 */
+enum {
+    KMB_KERNEL_GAUSSIAN = 0,             /* exp(-|x-y|^2)              :20 */
+    KMB_KERNEL_ABSOLUTE_EXPONENTIAL = 1, /* exp(-|x-y|)                :21 */
+    KMB_KERNEL_INVERSE_DISTANCE = 2      /* 1/|x-y|, flat indices k(M+1) zeroed  :8-15 */
+};
+
+/* query modes: BruteForceProductBLAS.query, bruteforce.py:130-153 */
+enum {
+    KMB_FLAG_NORMALIZE_ROWS = 1, /* attention: (K @ [b,1])[:, :-1] / [:, -1:]     :139-145 */
+    KMB_FLAG_DENSITY = 2         /* b == 1, E == 1: K.sum(-1)                      :150    */
+};
+
+/* evaluation paths */
+enum {
+    KMB_PATH_AUTO = 0,
+    KMB_PATH_DIRECT_F32 = 1,  /* sum of squared differences (bruteforce.py:53-54) in FP32 FMAs, D <= 16 */
+    KMB_PATH_TENSOR_3XTF32 = 2 /* |x|^2+|y|^2-2x.y (bruteforce.py:36-49) on tcgen05, 3xTF32 split, D >= 32 */
+};
+
+typedef struct {
+    int sm_count;
+    int cc_major, cc_minor;
+    int clock_khz;           /* cudaDevAttrClockRate */
+    int l2_bytes;
+    int smem_per_block_optin;
+    size_t total_mem;
+} kmb_device_info;
+
+int kmb_abi_version(void);
+const char* kmb_last_error(void);
+int kmb_get_device_info(int device, kmb_device_info* info);
+
+/* Workspace (bytes) kmb_product_f32 needs for this shape; *bytes is a multiple of 256. */
+int kmb_product_workspace_bytes(int64_t n_targets, int64_t n_sources, int D, int E, int kernel_id,
+                                int flags, int path, size_t* bytes);
+
+/* out[i, :] = sum_j k(x_i, y_j) b[j, :]   (K is never materialised)
+ *
+ * Replaces kernel_matrix(...) + the matrix product of
+ * BruteForceProductBLAS.fit/query (bruteforce.py:25-58, 113-120, 130-153).
+ *
+ *   x   (n_targets, D)  target points  (device)   -- may alias y (same_points)
+ *   y   (n_sources, D)  source points  (device)
+ *   b   (n_sources, E)  source signal  (device); NULL with KMB_FLAG_DENSITY (then E must be 1)
+ *   out (n_targets, E)  result         (device)
+ *   row_offset: global index of x's first row in the full target set.  Only
+ *     the inverse-distance kernel looks at it (its zeroing rule depends on the
+ *     global flat index, bruteforce.py:12-14); pass 0 unless rows are sharded.
+ *   KMB_FLAG_NORMALIZE_ROWS | KMB_FLAG_DENSITY fills out with ones (bruteforce.py:134-138).
+ */
+int kmb_product_f32(const float* x, const float* y, const float* b, float* out, int64_t n_targets,
+                    int64_t n_sources, int D, int E, int kernel_id, int flags, int path,
+                    int64_t row_offset, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of this library's kernels the last kmb_product_f32 / kmb_cg_* call on this
+ * thread launched (bench.py's gpu_launches). */
+int kmb_last_launch_count(void);
+
+/* Measurement hooks (bench.py's roofline leg).  With profiling enabled on this thread,
+ * kmb_product_f32 records a CUDA event on `stream` immediately before and after its dominant
+ * kernel (the last pass's main kernel, not the source packing); kmb_last_main_kernel_ms waits
+ * for the second event and returns the elapsed device time. */
+int kmb_set_profiling(int enabled);
+int kmb_last_main_kernel_ms(float* ms);
+
+/* ---- conjugate gradients on (K + lambda I) b = a: fused vector steps -------------------
+ * The reference solves K b = a densely (BruteForceSolverLAPACK.query, bruteforce.py:205-207);
+ * at N = 10^6 the build iterates with the product above as its matvec.  All vectors are
+ * (n_local, E) row shards; scalars live on the device as E floats per quantity so the
+ * loop needs no host synchronisation.  *_local outputs are this shard's partial sums: the
+ * caller all-reduces them across ranks when rows are sharded.  Reductions are deterministic
+ * (fixed block order).  `scratch`: kmb_cg_scratch_bytes() bytes, zeroed once by the caller,
+ * 256-byte aligned, reusable across calls on one stream.  E <= 16 per call.
+ */
+size_t kmb_cg_scratch_bytes(void);
+
+/* x = 0, r = a, p_shard = a, rs_local[e] = sum_i r[i,e]^2 */
+int kmb_cg_init_f32(const float* a, float* x, float* r, float* p_shard, float* rs_local,
+                    int64_t n_local, int E, void* scratch, void* stream);
+/* Ap += lambda * p ; pAp_local[e] = sum_i p[i,e] * Ap[i,e] */
+int kmb_cg_shift_dot_f32(float* Ap, const float* p_shard, float lambda, float* pAp_local,
+                         int64_t n_local, int E, void* scratch, void* stream);
+/* alpha = rs/pAp ; x += alpha p ; r -= alpha Ap ; rs_new_local[e] = sum_i r[i,e]^2 */
+int kmb_cg_update_f32(float* x, float* r, const float* p_shard, const float* Ap, const float* rs,
+                      const float* pAp, float* rs_new_local, int64_t n_local, int E, void* scratch,
+                      void* stream);
+/* beta = rs_new/rs ; p = r + beta p */
+int kmb_cg_direction_f32(float* p_shard, const float* r, const float* rs_new, const float* rs,
+                         int64_t n_local, int E, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMB_B200_H */

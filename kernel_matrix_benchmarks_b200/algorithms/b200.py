@@ -1,0 +1,233 @@
+"""B200 plugins for kernel-matrix-benchmarks: drop-ins for the brute-force path.
+
+``B200Product`` stands where ``BruteForceProductBLAS`` stands
+(/root/reference/kernel_matrix_benchmarks/algorithms/bruteforce.py:61-153) and
+``B200Solver`` where ``BruteForceSolverLAPACK`` stands (:156-207): same
+constructor keywords, same prepare_data / fit / prepare_query / query /
+get_result sequence driven by ``runner.run`` (runner.py:70-176), same error
+behaviour (``NotImplementedError`` for an unknown kernel, :82-85).  Registered in
+``algos.yaml`` with ``hardware: GPU``.
+
+What differs is *where* the work happens: the reference builds the dense kernel
+matrix in ``fit()`` and multiplies in ``query()``; here the matrix is never
+built, ``fit()`` only sizes device buffers and all arithmetic happens inside
+``query()`` in hand-written sm_100a kernels (libkmb_b200.so).  Compare the two
+on total time (build + query), the harness's default x-axis.
+
+The timer around fit()/query() is host wall-clock (runner.py:97-99, 138-140), so
+both end with a device synchronise.  There is no CPU fallback: constructing
+either class without the CUDA library or a GPU raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..product import Workspace, device_info, kernel_product, last_launch_count
+from ..solver import CudaShardOps, LocalComm, cg_solve
+from .base import BaseProduct, BaseSolver
+
+
+def _check_precision(precision, who):
+    """The reference accepts a numpy dtype or its name (algos.yaml:156-162 passes strings)."""
+    dt = np.dtype(precision)
+    if dt != np.float32:
+        raise NotImplementedError(f"{who} computes in float32 only (got precision={precision}).")
+    return dt
+
+
+def _to_device(array, device):
+    """float64 host array (owned by the runner, never mutated) -> float32 device tensor."""
+    host = torch.from_numpy(np.ascontiguousarray(array, dtype=np.float32))
+    if host.dim() == 1:
+        host = host[:, None]
+    return host.pin_memory().to(device, non_blocking=True)
+
+
+class _GpuTimer:
+    def __init__(self):
+        self.start, self.stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def __enter__(self):
+        self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop.record()
+
+    def ms(self):
+        self.stop.synchronize()
+        return self.start.elapsed_time(self.stop)
+
+
+class B200Product(BaseProduct):
+    """On-the-fly kernel product / density / attention on one B200."""
+
+    def __init__(self, *, kernel, dimension, normalize_rows=False, precision="float32", path="auto", device=0):
+        super().__init__(kernel=kernel, dimension=dimension, normalize_rows=normalize_rows, precision=precision)
+        if kernel not in _lib.KERNEL_IDS:
+            raise NotImplementedError(f"B200Product doesn't support kernel {kernel}.")
+        if path not in _lib.PATH_IDS:
+            raise ValueError(f"unknown path {path!r} (expected one of {sorted(_lib.PATH_IDS)})")
+        _check_precision(precision, "B200Product")
+        _lib.load()  # fail here, loudly, if the CUDA library is absent
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200Product needs a CUDA device; there is no CPU fallback.")
+        self.path = path
+        self.device = torch.device("cuda", int(device))
+        self.name = f"B200Product({np.dtype(precision).name}, path={path})"
+        self.workspace = Workspace()
+        self.query_ms = None
+        self.launches = 0
+        self.res = None
+
+    def prepare_data(self, *, source_points, target_points, same_points=False, density_estimation=False):
+        """Untimed host->device copy (base.py:64-67), cast to float32 as bruteforce.py:100-106 casts."""
+        self.source_points = _to_device(source_points, self.device)
+        self.same_points = bool(same_points)
+        self.target_points = self.source_points if self.same_points else _to_device(target_points, self.device)
+        self.density_estimation = bool(density_estimation)
+        torch.cuda.synchronize(self.device)
+
+    def fit(self):
+        """Timed.  Nothing to precompute: K is never materialised (bruteforce.py:113-120 builds it here)."""
+        N = self.target_points.shape[0]
+        self._out_rows = N
+        torch.cuda.synchronize(self.device)
+
+    def prepare_query(self, *, source_signal):
+        """Untimed host->device copy of the signal (bruteforce.py:122-128)."""
+        self.source_signal = None if self.density_estimation else _to_device(source_signal, self.device)
+        torch.cuda.synchronize(self.device)
+
+    def query(self):
+        """Timed: the whole product, ending with a device synchronise."""
+        with torch.cuda.device(self.device):
+            with _GpuTimer() as t:
+                self.res_device = kernel_product(
+                    self.target_points,
+                    self.source_points,
+                    self.source_signal,
+                    kernel=self.kernel,
+                    normalize_rows=bool(self.normalize_rows),
+                    density_estimation=self.density_estimation,
+                    path=self.path,
+                    workspace=self.workspace,
+                )
+            self.launches = last_launch_count()
+            torch.cuda.synchronize(self.device)
+        self.query_ms = t.ms()
+
+    def get_result(self):
+        """Untimed device->host copy; float64 contiguous as base.py:116."""
+        self.res = self.res_device.cpu().numpy()
+        return np.ascontiguousarray(self.res, dtype=np.float64)
+
+    def get_additional(self):
+        """Extra attrs stored with the result (runner.py:162 -> results.py:116-117)."""
+        if self.query_ms is None:
+            return {}
+        pairs = float(self.target_points.shape[0]) * float(self.source_points.shape[0])
+        return {
+            "gpu_query_ms": float(self.query_ms),
+            "gpairs_per_s": pairs / (self.query_ms * 1e-3) / 1e9,
+            "gpu_launches": int(self.launches),
+            "path": self.path,
+        }
+
+    def get_memory_usage(self):
+        """Host RSS as the reference reports, plus device bytes in kB."""
+        return super().get_memory_usage() + torch.cuda.memory_allocated(self.device) / 1024
+
+    def done(self):
+        for k in ("source_points", "target_points", "source_signal", "res_device"):
+            self.__dict__.pop(k, None)
+        self.workspace = Workspace()
+
+    def __del__(self):  # runner.py keeps only the fastest-fit instance; the others are just dropped
+        try:
+            self.done()
+        except Exception:
+            pass
+
+
+class B200Solver(BaseSolver):
+    """Kernel solve (K + lam I) b = a by conjugate gradients on the on-the-fly product.
+
+    ``lam = 0`` is the reference's system K b = a (bruteforce.py:205-207); for the
+    Gaussian kernel that matrix is singular to working precision (cond ~ 1e20), so
+    the BASELINE solve config uses lam = 1 and scores the residual.
+    """
+
+    def __init__(self, *, kernel, dimension, normalize_rows=False, precision="float32", lam=0.0, rtol=1e-6,
+                 max_iter=500, path="auto", device=0):
+        super().__init__(kernel=kernel, dimension=dimension, normalize_rows=normalize_rows, precision=precision)
+        if kernel not in _lib.KERNEL_IDS:
+            raise NotImplementedError(f"B200Solver doesn't support kernel {kernel}.")
+        _check_precision(precision, "B200Solver")
+        _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200Solver needs a CUDA device; there is no CPU fallback.")
+        self.lam, self.rtol, self.max_iter, self.path = float(lam), float(rtol), int(max_iter), path
+        self.device = torch.device("cuda", int(device))
+        self.name = f"B200Solver({np.dtype(precision).name}, lam={lam:g}, rtol={rtol:g})"
+        self.info = None
+        self.res = None
+
+    def set_query_arguments(self, **kwargs):
+        """``query-args`` of algos.yaml (runner.py:123): rtol / max_iter / lam can be swept without refitting."""
+        for k in ("rtol", "lam"):
+            if k in kwargs:
+                setattr(self, k, float(kwargs[k]))
+        if "max_iter" in kwargs:
+            self.max_iter = int(kwargs["max_iter"])
+
+    def prepare_data(self, *, source_points):
+        self.source_points = _to_device(source_points, self.device)
+        torch.cuda.synchronize(self.device)
+
+    def fit(self):
+        n = self.source_points.shape[0]
+        self.ops = CudaShardOps(self.source_points, self.kernel, 0, n, path=self.path)
+        torch.cuda.synchronize(self.device)
+
+    def prepare_query(self, *, target_signal):
+        self.target_signal = _to_device(target_signal, self.device)
+        torch.cuda.synchronize(self.device)
+
+    def query(self):
+        with torch.cuda.device(self.device):
+            with _GpuTimer() as t:
+                self.info = cg_solve(self.ops, LocalComm(), self.target_signal, self.source_points.shape[0],
+                                     lam=self.lam, rtol=self.rtol, max_iter=self.max_iter)
+            torch.cuda.synchronize(self.device)
+        self.query_ms = t.ms()
+
+    def get_result(self):
+        self.res = self.info.x.cpu().numpy()
+        return np.ascontiguousarray(self.res, dtype=np.float64)
+
+    def get_additional(self):
+        if self.info is None:
+            return {}
+        return {
+            "gpu_query_ms": float(self.query_ms),
+            "cg_iterations": int(self.info.iterations),
+            "cg_rel_residual": float(self.info.rel_residual),
+            "cg_converged": bool(self.info.converged),
+            "gpu_launches": int(self.ops.launches),
+        }
+
+    def get_memory_usage(self):
+        return super().get_memory_usage() + torch.cuda.memory_allocated(self.device) / 1024
+
+    def done(self):
+        for k in ("source_points", "target_signal", "ops"):
+            self.__dict__.pop(k, None)
+
+    def __del__(self):
+        try:
+            self.done()
+        except Exception:
+            pass

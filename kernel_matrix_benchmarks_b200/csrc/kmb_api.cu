@@ -1,0 +1,269 @@
+// C ABI of libkmb_b200.so (see include/kmb_b200.h): argument checking, path selection,
+// workspace carving and kernel launches.  No allocation, no synchronisation.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "kprod_direct.cuh"
+
+namespace kmb {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+// optional CUDA-event bracket around the dominant (main) kernel of the last product call
+static thread_local bool g_profile = false;
+static thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static thread_local bool g_ev_valid = false;
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+void count_launch(int n) { g_launches += n; }
+
+#define KMB_DECLARE_TABLE(NAME)      \
+    extern const DirectEntry NAME[]; \
+    extern const int NAME##_count;
+KMB_DECLARE_TABLE(kDirect_gauss_n0)
+KMB_DECLARE_TABLE(kDirect_gauss_n1)
+KMB_DECLARE_TABLE(kDirect_absexp_n0)
+KMB_DECLARE_TABLE(kDirect_absexp_n1)
+KMB_DECLARE_TABLE(kDirect_invdist_n0)
+KMB_DECLARE_TABLE(kDirect_invdist_n1)
+
+static const DirectEntry* find_direct(int D, int e_chunk, int kid, bool norm) {
+    const DirectEntry* tab = nullptr;
+    int n = 0;
+#define KMB_PICK(K, NAME0, NAME1)            \
+    if (kid == K) {                          \
+        tab = norm ? NAME1 : NAME0;          \
+        n = norm ? NAME1##_count : NAME0##_count; \
+    }
+    KMB_PICK(KMB_KERNEL_GAUSSIAN, kDirect_gauss_n0, kDirect_gauss_n1)
+    KMB_PICK(KMB_KERNEL_ABSOLUTE_EXPONENTIAL, kDirect_absexp_n0, kDirect_absexp_n1)
+    KMB_PICK(KMB_KERNEL_INVERSE_DISTANCE, kDirect_invdist_n0, kDirect_invdist_n1)
+#undef KMB_PICK
+    const DirectEntry* best = nullptr;
+    for (int i = 0; i < n; ++i) {
+        const DirectEntry& e = tab[i];
+        if (e.DP < D || e.EP < e_chunk) continue;
+        if (!best || e.DP < best->DP || (e.DP == best->DP && e.EP < best->EP)) best = &e;
+    }
+    return best;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// coordinate scale folded into x and y so the exponential is a bare ex2
+static float coord_scale(int kid) {
+    if (kid == KMB_KERNEL_GAUSSIAN) return 1.2011224087864498f;             // sqrt(log2 e)
+    if (kid == KMB_KERNEL_ABSOLUTE_EXPONENTIAL) return 1.4426950408889634f; // log2 e
+    return 1.0f;
+}
+
+struct DirectPlan {
+    const DirectEntry* ent;
+    int e_chunk, n_passes;
+    long long n_tiles, nsb, M_pad;
+    int grid_max;
+    size_t rec_bytes, partial_bytes, counter_bytes, total_bytes;
+};
+
+static int device_sm_count(int* sms) {
+    static int cached_dev = -1, cached = 0;
+    int dev = 0;
+    KMB_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev != cached_dev) {
+        KMB_CUDA_CHECK(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
+        cached_dev = dev;
+    }
+    *sms = cached;
+    return KMB_OK;
+}
+
+static int plan_direct(int64_t N, int64_t M, int D, int E, int kid, int flags, DirectPlan* pl) {
+    const bool norm = flags & KMB_FLAG_NORMALIZE_ROWS;
+    if (D > 16) return set_error(KMB_ERR_UNSUPPORTED, "direct FP32 path supports D <= 16 (got D=%d)", D);
+    pl->e_chunk = E >= 4 ? 4 : E;
+    pl->n_passes = (E + pl->e_chunk - 1) / pl->e_chunk;
+    pl->ent = find_direct(D, pl->e_chunk, kid, norm);
+    if (!pl->ent) return set_error(KMB_ERR_UNSUPPORTED, "no direct kernel for D=%d E=%d kernel=%d", D, E, kid);
+    const DirectEntry& e = *pl->ent;
+    pl->n_tiles = (N + e.TILE_ROWS - 1) / e.TILE_ROWS;
+    pl->nsb = (M + e.SB - 1) / e.SB;
+    pl->M_pad = pl->nsb * e.SB;
+    int sms = 0;
+    if (int rc = device_sm_count(&sms)) return rc;
+    pl->grid_max = sms * 2;
+    pl->rec_bytes = align_up(static_cast<size_t>(pl->M_pad) * e.RECV * 16, 256);
+    pl->partial_bytes = align_up(static_cast<size_t>(pl->grid_max) * 2 * e.TILE_ROWS * e.PS * 4, 256);
+    pl->counter_bytes = align_up(static_cast<size_t>(pl->n_tiles) * 4, 256);
+    pl->total_bytes = pl->rec_bytes + pl->partial_bytes + pl->counter_bytes;
+    return KMB_OK;
+}
+
+__global__ void fill_kernel(float* out, long long n, float v) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
+static int check_product_args(int64_t N, int64_t M, int D, int E, int kid, int flags, int path) {
+    if (N < 0 || M < 1 || D < 1 || E < 1) return set_error(KMB_ERR_INVALID, "bad sizes N=%lld M=%lld D=%d E=%d", (long long)N, (long long)M, D, E);
+    if (kid < 0 || kid > KMB_KERNEL_INVERSE_DISTANCE) return set_error(KMB_ERR_UNSUPPORTED, "unknown kernel id %d", kid);
+    if (flags & ~(KMB_FLAG_NORMALIZE_ROWS | KMB_FLAG_DENSITY)) return set_error(KMB_ERR_INVALID, "unknown flags 0x%x", flags);
+    if ((flags & KMB_FLAG_DENSITY) && E != 1) return set_error(KMB_ERR_INVALID, "density estimation implies E == 1 (got %d)", E);
+    if (path < KMB_PATH_AUTO || path > KMB_PATH_TENSOR_3XTF32) return set_error(KMB_ERR_INVALID, "unknown path %d", path);
+    return KMB_OK;
+}
+
+static int resolve_path(int D, int path) {
+    if (path != KMB_PATH_AUTO) return path;
+    return D <= 16 ? KMB_PATH_DIRECT_F32 : KMB_PATH_TENSOR_3XTF32;
+}
+
+}  // namespace kmb
+
+using namespace kmb;
+
+extern "C" {
+
+int kmb_abi_version(void) { return KMB_ABI_VERSION; }
+const char* kmb_last_error(void) { return g_err; }
+int kmb_last_launch_count(void) { return g_launches; }
+
+int kmb_set_profiling(int enabled) {
+    g_profile = enabled != 0;
+    g_ev_valid = false;
+    return KMB_OK;
+}
+int kmb_last_main_kernel_ms(float* ms) {
+    if (!ms) return set_error(KMB_ERR_INVALID, "ms is NULL");
+    if (!g_ev_valid) return set_error(KMB_ERR_INVALID, "no profiled product call on this thread");
+    KMB_CUDA_CHECK(cudaEventSynchronize(g_ev1));
+    KMB_CUDA_CHECK(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+    return KMB_OK;
+}
+
+int kmb_get_device_info(int device, kmb_device_info* info) {
+    if (!info) return set_error(KMB_ERR_INVALID, "info is NULL");
+    cudaDeviceProp p;
+    KMB_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    info->sm_count = p.multiProcessorCount;
+    info->cc_major = p.major;
+    info->cc_minor = p.minor;
+    KMB_CUDA_CHECK(cudaDeviceGetAttribute(&info->clock_khz, cudaDevAttrClockRate, device));
+    info->l2_bytes = p.l2CacheSize;
+    info->smem_per_block_optin = static_cast<int>(p.sharedMemPerBlockOptin);
+    info->total_mem = p.totalGlobalMem;
+    return KMB_OK;
+}
+
+int kmb_product_workspace_bytes(int64_t N, int64_t M, int D, int E, int kernel_id, int flags, int path,
+                                size_t* bytes) {
+    if (!bytes) return set_error(KMB_ERR_INVALID, "bytes is NULL");
+    if (int rc = check_product_args(N, M, D, E, kernel_id, flags, path)) return rc;
+    *bytes = 256;
+    if ((flags & KMB_FLAG_NORMALIZE_ROWS) && (flags & KMB_FLAG_DENSITY)) return KMB_OK;
+    const int p = resolve_path(D, path);
+    if (p == KMB_PATH_DIRECT_F32) {
+        DirectPlan pl;
+        if (int rc = plan_direct(N, M, D, E, kernel_id, flags, &pl)) return rc;
+        *bytes = pl.total_bytes;
+        return KMB_OK;
+    }
+    return set_error(KMB_ERR_UNSUPPORTED, "tensor-core path (D=%d) is not built yet", D);
+}
+
+int kmb_product_f32(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D,
+                    int E, int kernel_id, int flags, int path, int64_t row_offset, void* workspace,
+                    size_t workspace_bytes, void* stream_) {
+    g_launches = 0;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_product_args(N, M, D, E, kernel_id, flags, path)) return rc;
+    if (!x || !y || !out) return set_error(KMB_ERR_INVALID, "x, y and out must not be NULL");
+    const bool density = flags & KMB_FLAG_DENSITY;
+    if (!density && !b) return set_error(KMB_ERR_INVALID, "b is NULL without KMB_FLAG_DENSITY");
+    if (N == 0) return KMB_OK;
+
+    if ((flags & KMB_FLAG_NORMALIZE_ROWS) && density) {  // bruteforce.py:134-138
+        fill_kernel<<<static_cast<unsigned>((N + 255) / 256), 256, 0, stream>>>(out, N, 1.0f);
+        KMB_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+        return KMB_OK;
+    }
+    const int p = resolve_path(D, path);
+    if (p != KMB_PATH_DIRECT_F32)
+        return set_error(KMB_ERR_UNSUPPORTED, "tensor-core path (D=%d) is not built yet", D);
+
+    DirectPlan pl;
+    if (int rc = plan_direct(N, M, D, E, kernel_id, flags, &pl)) return rc;
+    if (!workspace || workspace_bytes < pl.total_bytes)
+        return set_error(KMB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total_bytes, workspace_bytes);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256)
+        return set_error(KMB_ERR_INVALID, "workspace must be 256-byte aligned");
+    const DirectEntry& ent = *pl.ent;
+    char* ws = static_cast<char*>(workspace);
+    float2* rec = reinterpret_cast<float2*>(ws);
+    float* partial = reinterpret_cast<float*>(ws + pl.rec_bytes);
+    int* counters = reinterpret_cast<int*>(ws + pl.rec_bytes + pl.partial_bytes);
+    KMB_CUDA_CHECK(cudaMemsetAsync(counters, 0, pl.counter_bytes, stream));
+
+    // resident CTAs of this instantiation (cached per kernel function)
+    static const void* occ_func[64];
+    static int occ_val[64], occ_n = 0;
+    int per_sm = 0;
+    for (int i = 0; i < occ_n; ++i)
+        if (occ_func[i] == ent.func) per_sm = occ_val[i];
+    if (!per_sm) {
+        KMB_CUDA_CHECK(cudaFuncSetAttribute(ent.func, cudaFuncAttributeMaxDynamicSharedMemorySize, ent.SMEM));
+        KMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ent.func, ent.THREADS, ent.SMEM));
+        if (per_sm < 1) return set_error(KMB_ERR_CUDA, "kernel does not fit on an SM (smem %d B)", ent.SMEM);
+        if (per_sm > 2) per_sm = 2;
+        if (occ_n < 64) { occ_func[occ_n] = ent.func; occ_val[occ_n++] = per_sm; }
+    }
+    const long long units = pl.n_tiles * pl.nsb;
+    long long grid = static_cast<long long>(pl.grid_max / 2) * per_sm;
+    if (grid > units) grid = units;
+
+    const float scale = coord_scale(kernel_id);
+    for (int pass = 0; pass < pl.n_passes; ++pass) {
+        const int e0 = pass * pl.e_chunk;
+        pack_sources_kernel<<<static_cast<unsigned>((pl.M_pad + 255) / 256), 256, 0, stream>>>(
+            y, density ? nullptr : b, rec, M, pl.M_pad, D, E, ent.DP, ent.EP, ent.RECV * 2, e0, scale);
+        KMB_CUDA_CHECK(cudaGetLastError());
+        DirectParams P;
+        P.x = x;
+        P.rec = reinterpret_cast<const float4*>(rec);
+        P.out = out;
+        P.partial = partial;
+        P.tile_counter = counters;
+        P.N = N;
+        P.M = M;
+        P.row_offset = row_offset;
+        P.D = D;
+        P.E = E;
+        P.e0 = e0;
+        P.n_tiles = static_cast<int>(pl.n_tiles);
+        P.n_src_blocks = static_cast<int>(pl.nsb);
+        P.xscale = scale;
+        if (g_profile) {
+            if (!g_ev0) {
+                KMB_CUDA_CHECK(cudaEventCreate(&g_ev0));
+                KMB_CUDA_CHECK(cudaEventCreate(&g_ev1));
+            }
+            KMB_CUDA_CHECK(cudaEventRecord(g_ev0, stream));
+        }
+        KMB_CUDA_CHECK(ent.launch(P, static_cast<int>(grid), stream));
+        if (g_profile) {
+            KMB_CUDA_CHECK(cudaEventRecord(g_ev1, stream));
+            g_ev_valid = true;
+        }
+        count_launch(2);
+    }
+    return KMB_OK;
+}
+
+}  // extern "C"

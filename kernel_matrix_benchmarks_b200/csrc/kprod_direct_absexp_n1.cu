@@ -1,0 +1,3 @@
+// Instantiations of kprod_direct_kernel: kernel absexp, normalize_rows=1 (split per file to build in parallel).
+#include "kprod_direct.cuh"
+KMB_DIRECT_TABLE(kDirect_absexp_n1, 1, true)

@@ -1,0 +1,3 @@
+// Instantiations of kprod_direct_kernel: kernel invdist, normalize_rows=1 (split per file to build in parallel).
+#include "kprod_direct.cuh"
+KMB_DIRECT_TABLE(kDirect_invdist_n1, 2, true)

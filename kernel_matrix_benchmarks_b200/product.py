@@ -1,0 +1,100 @@
+"""Device-level entry points: torch tensors in, torch tensors out, libkmb_b200 kernels inside.
+
+PyTorch only provides device memory and streams here; every FLOP of the hot
+path runs in the hand-written sm_100a kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_f32(name, t, cols=None):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 2):
+        raise ValueError(f"{name} must be a contiguous 2-D float32 CUDA tensor")
+    if cols is not None and t.shape[1] != cols:
+        raise ValueError(f"{name} has {t.shape[1]} columns, expected {cols}")
+
+
+class Workspace:
+    """A grow-only device buffer handed to the C ABI (the library never allocates)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+_default_ws = {}
+
+
+def kernel_product(x, y, b, *, kernel="gaussian", normalize_rows=False, density_estimation=False, path="auto",
+                   row_offset=0, out=None, workspace=None):
+    """a_i = sum_j k(x_i, y_j) b_j on the current CUDA device (kmb_product_f32).
+
+    x (N, D), y (M, D), b (M, E) float32 CUDA tensors; b is ignored (may be None)
+    under ``density_estimation``.  Asynchronous on the current stream.
+    """
+    lib = _lib.load()
+    if kernel not in _lib.KERNEL_IDS:
+        raise NotImplementedError(f"B200 kernel product doesn't support kernel {kernel}.")
+    _check_f32("target points", x)
+    _check_f32("source points", y, x.shape[1])
+    N, D = x.shape
+    M = y.shape[0]
+    flags = (_lib.FLAG_NORMALIZE_ROWS if normalize_rows else 0) | (_lib.FLAG_DENSITY if density_estimation else 0)
+    if density_estimation:
+        b, E = None, 1
+    else:
+        _check_f32("source signal", b)
+        if b.shape[0] != M:
+            raise ValueError("source signal and source points disagree on M")
+        E = b.shape[1]
+    if out is None:
+        out = torch.empty((N, E), dtype=torch.float32, device=x.device)
+    else:
+        _check_f32("out", out, E)
+    kid, pid = _lib.KERNEL_IDS[kernel], _lib.PATH_IDS[path]
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.kmb_product_workspace_bytes(N, M, D, E, kid, flags, pid, ctypes.byref(need)))
+    if workspace is None:
+        workspace = _default_ws.setdefault(x.device, Workspace())
+    ws = workspace.get(need.value, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.kmb_product_f32(_ptr(x), _ptr(y), _ptr(b), _ptr(out), N, M, D, E, kid, flags, pid, int(row_offset),
+                                       _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
+def last_launch_count():
+    return int(_lib.load().kmb_last_launch_count())
+
+
+def device_info(device=0):
+    info = _lib.DeviceInfo()
+    _lib.check(_lib.load().kmb_get_device_info(int(device), ctypes.byref(info)))
+    return {f: getattr(info, f) for f, _ in info._fields_}
+
+
+def set_profiling(enabled):
+    _lib.check(_lib.load().kmb_set_profiling(int(bool(enabled))))
+
+
+def last_main_kernel_ms():
+    ms = ctypes.c_float(0)
+    _lib.check(_lib.load().kmb_last_main_kernel_ms(ctypes.byref(ms)))
+    return float(ms.value)

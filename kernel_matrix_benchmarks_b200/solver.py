@@ -1,0 +1,161 @@
+"""Conjugate gradients on (K + lambda I) b = a with a row-sharded kernel matvec.
+
+The reference solves the dense system with LAPACK
+(/root/reference/kernel_matrix_benchmarks/algorithms/bruteforce.py:205-207),
+which cannot exist at N = 10^6 (the matrix would be 8 TB).  Here the matrix is
+never formed: every iteration applies it through the on-the-fly product.
+
+Sharding (BASELINE.json north_star): rows of x, r, p, Ap are split by target
+across ranks; each rank needs the *whole* search direction as the source signal
+of its matvec, so the one real exchange per iteration is an all-gather of p
+(plus two E-float all-reduces for the dot products).
+
+The loop is written against two small interfaces so the same host logic runs
+on the GPU (``CudaShardOps`` + NCCL) and in the CPU gloo tests (tests/ inject an
+oracle-backed ops object):
+
+    ops.init(a)                  -> x, r, p, rs          (local rows; rs: E partial sums)
+    ops.matvec(p_full)           -> Ap                   (local rows of K @ p_full)
+    ops.shift_dot(Ap, p, lam)    -> pAp                  (Ap += lam p; partial p.Ap)
+    ops.update(x, r, p, Ap, rs, pAp, rs_new)             (x += a p; r -= a Ap; partial r.r)
+    ops.direction(p, r, rs_new, rs)                      (p = r + (rs_new/rs) p)
+    comm.all_gather(p_local)     -> p_full (N, E)
+    comm.all_reduce(t)           sums the E partials in place
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from .product import Workspace, _ptr, _stream, kernel_product
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous row block of ``rank``: equal ceil(n / world) blocks, the last ones short or empty."""
+    per = -(-n // world)
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per), per
+
+
+class LocalComm:
+    """world_size == 1: nothing to exchange."""
+
+    rank, world = 0, 1
+
+    def all_gather(self, p_local, n_total):
+        return p_local
+
+    def all_reduce(self, t):
+        return t
+
+
+class TorchDistComm:
+    """One process per GPU; NCCL on the GPU box, gloo in the CPU tests."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._buf = None
+
+    def all_gather(self, p_local, n_total):
+        per = -(-n_total // self.world)
+        E = p_local.shape[1]
+        if self._buf is None or self._buf.shape != (self.world * per, E) or self._buf.device != p_local.device:
+            self._buf = torch.zeros((self.world * per, E), dtype=p_local.dtype, device=p_local.device)
+            self._pad = torch.zeros((per, E), dtype=p_local.dtype, device=p_local.device)
+        send = p_local
+        if p_local.shape[0] != per:  # short (or empty) last shard: pad to the common size
+            self._pad[: p_local.shape[0]] = p_local
+            send = self._pad
+        self.dist.all_gather_into_tensor(self._buf, send, group=self.group)
+        return self._buf[:n_total]
+
+    def all_reduce(self, t):
+        self.dist.all_reduce(t, group=self.group)
+        return t
+
+
+class CudaShardOps:
+    """The CUDA side of one rank: product kernel for the matvec + fused CG vector kernels."""
+
+    def __init__(self, points, kernel, row_lo, row_hi, path="auto"):
+        self.lib = _lib.load()
+        self.y = points  # (N, D) all source points, replicated
+        self.x = points[row_lo:row_hi]  # this rank's target rows (a view: same memory)
+        self.kernel, self.path, self.row_lo = kernel, path, row_lo
+        self.n_local = row_hi - row_lo
+        self.ws = Workspace()
+        self.scratch = torch.zeros(int(self.lib.kmb_cg_scratch_bytes()), dtype=torch.uint8, device=points.device)
+        self.launches = 0
+
+    def _new(self, E):
+        return torch.empty((self.n_local, E), dtype=torch.float32, device=self.y.device)
+
+    def init(self, a):
+        E = a.shape[1]
+        x, r, p = self._new(E), self._new(E), self._new(E)
+        rs = torch.empty(E, dtype=torch.float32, device=a.device)
+        self.Ap = self._new(E)
+        _lib.check(self.lib.kmb_cg_init_f32(_ptr(a), _ptr(x), _ptr(r), _ptr(p), _ptr(rs), self.n_local, E,
+                                            _ptr(self.scratch), _stream()))
+        self.launches += 1
+        return x, r, p, rs
+
+    def matvec(self, p_full):
+        kernel_product(self.x, self.y, p_full, kernel=self.kernel, path=self.path, row_offset=self.row_lo,
+                       out=self.Ap, workspace=self.ws)
+        self.launches += int(self.lib.kmb_last_launch_count())
+        return self.Ap
+
+    def shift_dot(self, Ap, p, lam, out):
+        _lib.check(self.lib.kmb_cg_shift_dot_f32(_ptr(Ap), _ptr(p), ctypes.c_float(lam), _ptr(out), self.n_local,
+                                                 p.shape[1], _ptr(self.scratch), _stream()))
+        self.launches += 1
+        return out
+
+    def update(self, x, r, p, Ap, rs, pAp, rs_new):
+        _lib.check(self.lib.kmb_cg_update_f32(_ptr(x), _ptr(r), _ptr(p), _ptr(Ap), _ptr(rs), _ptr(pAp), _ptr(rs_new),
+                                              self.n_local, p.shape[1], _ptr(self.scratch), _stream()))
+        self.launches += 1
+        return rs_new
+
+    def direction(self, p, r, rs_new, rs):
+        _lib.check(self.lib.kmb_cg_direction_f32(_ptr(p), _ptr(r), _ptr(rs_new), _ptr(rs), self.n_local, p.shape[1],
+                                                 _stream()))
+        self.launches += 1
+
+
+@dataclass
+class CgResult:
+    x: torch.Tensor  # local rows of the solution
+    iterations: int
+    rel_residual: float  # max over right-hand sides of |r| / |a| (recurrence residual)
+    converged: bool
+
+
+def cg_solve(ops, comm, a_local, n_total, *, lam=0.0, rtol=1e-6, max_iter=500, check_every=1):
+    """Solve (K + lam I) x = a for the rows this rank owns.  Every rank runs the same loop."""
+    x, r, p, rs = ops.init(a_local)
+    comm.all_reduce(rs)
+    rs0 = rs.clone()
+    pAp, rs_new = torch.empty_like(rs), torch.empty_like(rs)
+    tol2 = float(rtol) ** 2
+    it, done = 0, bool((rs0 <= 0).all())
+    while not done and it < max_iter:
+        p_full = comm.all_gather(p, n_total)
+        Ap = ops.matvec(p_full)
+        comm.all_reduce(ops.shift_dot(Ap, p, float(lam), pAp))
+        comm.all_reduce(ops.update(x, r, p, Ap, rs, pAp, rs_new))
+        ops.direction(p, r, rs_new, rs)
+        rs, rs_new = rs_new, rs
+        it += 1
+        if it % check_every == 0 or it == max_iter:
+            done = bool((rs <= tol2 * rs0).all())  # the only host synchronisation in the loop
+    safe = torch.where(rs0 > 0, rs0, torch.ones_like(rs0))
+    rel = float(torch.sqrt(rs / safe).max()) if rs0.numel() else 0.0
+    return CgResult(x=x, iterations=it, rel_residual=rel, converged=bool((rs <= tol2 * rs0).all()))

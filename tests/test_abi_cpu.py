@@ -1,0 +1,107 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the
+header declares, the plugin classes mirror the reference interface, and nothing falls back to CPU."""
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+
+HEADER = os.path.join(REPO, "include", "kmb_b200.h")
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kmb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from kernel_matrix_benchmarks_b200 import _lib
+
+    lib = _lib.load()  # raises if the .so has not been built: there is no fallback
+    declared = _declared_symbols()
+    assert len(declared) >= 11
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/kmb_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes signatures and header disagree"
+    assert lib.kmb_abi_version() == 1
+
+
+def test_error_codes_without_touching_the_gpu():
+    from kernel_matrix_benchmarks_b200 import _lib
+    import ctypes
+
+    lib = _lib.load()
+    need = ctypes.c_size_t(0)
+    # argument validation happens before any CUDA call
+    assert lib.kmb_product_workspace_bytes(10, 0, 3, 1, 0, 0, 0, ctypes.byref(need)) == _lib.KMB_ERR_INVALID
+    assert b"bad sizes" in lib.kmb_last_error()
+    assert lib.kmb_product_workspace_bytes(10, 10, 3, 1, 7, 0, 0, ctypes.byref(need)) == _lib.KMB_ERR_UNSUPPORTED
+    assert lib.kmb_product_workspace_bytes(10, 10, 3, 2, 0, _lib.FLAG_DENSITY, 0, ctypes.byref(need)) == _lib.KMB_ERR_INVALID
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.KMB_ERR_UNSUPPORTED)
+    with pytest.raises(ValueError):
+        _lib.check(_lib.KMB_ERR_INVALID)
+
+
+def test_plugin_interface_mirrors_reference_base_classes():
+    """Method names and keyword arguments of base.py:7-167 (what runner.py:73-176 calls)."""
+    from kernel_matrix_benchmarks_b200.algorithms.b200 import B200Product, B200Solver
+
+    assert B200Product.task == "product" and B200Solver.task == "solver"
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(B200Product.prepare_data) == ["self", "source_points", "target_points", "same_points", "density_estimation"]
+    assert sig(B200Product.prepare_query) == ["self", "source_signal"]
+    assert sig(B200Solver.prepare_data) == ["self", "source_points"]
+    assert sig(B200Solver.prepare_query) == ["self", "target_signal"]
+    for cls in (B200Product, B200Solver):
+        ctor = inspect.signature(cls.__init__).parameters
+        assert all(ctor[k].kind is inspect.Parameter.KEYWORD_ONLY for k in ("kernel", "dimension", "normalize_rows", "precision"))
+        for m in ("fit", "query", "get_result", "set_query_arguments", "get_additional", "get_memory_usage", "done", "__str__"):
+            assert callable(getattr(cls, m))
+
+
+def test_plugin_rejects_what_the_reference_rejects():
+    from kernel_matrix_benchmarks_b200.algorithms.b200 import B200Product, B200Solver
+
+    for cls in (B200Product, B200Solver):
+        with pytest.raises(NotImplementedError):  # bruteforce.py:82-85
+            cls(kernel="laplace", dimension=3)
+        with pytest.raises(NotImplementedError):
+            cls(kernel="gaussian", dimension=3, precision=np.float64)
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the plugin must refuse to run rather than compute on the host."""
+    import torch
+    from kernel_matrix_benchmarks_b200.algorithms.b200 import B200Product
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        B200Product(kernel="gaussian", dimension=3, precision="float32")
+
+
+def test_product_code_does_not_import_the_oracle():
+    pkg = os.path.join(REPO, "kernel_matrix_benchmarks_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+\.*oracle|libkmb_oracle|oracle/", src, flags=re.M), \
+                    f"{f} reaches into oracle/"
+
+
+def test_datasets_follow_reference_generator():
+    from kernel_matrix_benchmarks_b200 import datasets
+
+    ds = datasets.uniform_cube(100, 3)
+    np.random.seed(103)
+    assert np.array_equal(ds.source_points, np.random.rand(100, 3))
+    assert ds.name == "product-cube-D3-E1-M100-N100-gaussian" and ds.same_points
+    c4 = datasets.config_c4(n=64)
+    assert c4.normalize_rows and c4.E == 64 and c4.D == 64 and not c4.same_points
+    assert abs(datasets.scaled_radius(784) - (3 / 784) ** 0.5) < 1e-15

@@ -1,0 +1,175 @@
+"""Parity of the CUDA product path with the oracle / reference golden vectors (needs a B200).
+
+Tolerances are BASELINE.json's: relative L2 <= 1e-5 on the FP32 direct path, <= 1e-4 on the
+tensor-core (3xTF32) path.  Everything goes through the plugin or the C ABI; the oracle only checks.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+from oracle import bruteforce_oracle as orc
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL_DIRECT = 1e-5
+TOL_TENSOR = 1e-4
+PRODUCT_CASES = [n for n in golden_names() if not n.startswith("solver_")]
+
+
+def run_plugin(kernel, y, x, b, *, same_points=False, normalize_rows=False, density=False, path="auto"):
+    """The call sequence of runner.py:73-143."""
+    from kernel_matrix_benchmarks_b200.algorithms.b200 import B200Product
+
+    algo = B200Product(kernel=kernel, dimension=y.shape[1], normalize_rows=normalize_rows, precision="float32", path=path)
+    try:
+        algo.prepare_data(source_points=y, target_points=y if x is None else x, same_points=same_points,
+                          density_estimation=density)
+        algo.fit()
+        algo.prepare_query(source_signal=b)
+        algo.query()
+        out = algo.get_result()
+        extra = algo.get_additional()
+    finally:
+        algo.done()
+    assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
+    return out, extra
+
+
+@pytest.mark.parametrize("name", PRODUCT_CASES)
+def test_golden_vectors(name):
+    g = load_golden(name)
+    D = g["source_points"].shape[1]
+    out, extra = run_plugin(g["kernel"], g["source_points"], g["target_points"], g["source_signal"],
+                            same_points=g["same_points"], normalize_rows=g["normalize_rows"], density=g["density_estimation"])
+    assert out.shape == g["truth"].shape
+    tol = TOL_DIRECT if D <= 16 else TOL_TENSOR
+    err = orc.rel_l2(out, g["truth"])
+    assert err <= tol, f"{name}: rel-L2 {err:.3e} > {tol:g}"
+    assert extra["gpu_launches"] >= 1
+
+
+@pytest.mark.parametrize("kernel", ["gaussian", "absolute-exponential", "inverse-distance"])
+@pytest.mark.parametrize("N,M", [(1, 1), (7, 513), (255, 1), (2049, 511), (4097, 1537), (300, 40000)])
+def test_ragged_sizes(kernel, N, M):
+    rng = np.random.RandomState(N * 131 + M)
+    y, x, b = rng.rand(M, 3), rng.rand(N, 3), rng.randn(M, 1)
+    out, _ = run_plugin(kernel, y, x, b)
+    want = c_oracle.kernel_product(kernel, y, x, b)
+    assert orc.rel_l2(out, want) <= TOL_DIRECT
+
+
+@pytest.mark.parametrize("D", [1, 2, 3, 4, 5, 8, 11, 16])
+@pytest.mark.parametrize("E", [1, 2, 3, 4, 5, 9])
+def test_dims(D, E):
+    rng = np.random.RandomState(D * 17 + E)
+    r = (3.0 / max(D, 3)) ** 0.5
+    y, x, b = r * rng.rand(700, D), r * rng.rand(333, D), rng.randn(700, E)
+    out, _ = run_plugin("gaussian", y, x, b)
+    assert orc.rel_l2(out, c_oracle.kernel_product("gaussian", y, x, b)) <= TOL_DIRECT
+    out, _ = run_plugin("gaussian", y, x, b, normalize_rows=True)
+    assert orc.rel_l2(out, c_oracle.kernel_product("gaussian", y, x, b, normalize_rows=True)) <= TOL_DIRECT
+
+
+@pytest.mark.parametrize("kernel", ["gaussian", "absolute-exponential"])
+def test_attention_survives_fp32_underflow(kernel):
+    """Rows far from every source: exp(-d2) underflows in FP32 (d2 > 104) but not in the float64
+    reference (d2 < 745); the online max-rescale must still normalise them."""
+    rng = np.random.RandomState(5)
+    y, b = rng.rand(900, 3), rng.randn(900, 2)
+    x = rng.rand(64, 3) + (12.0 if kernel == "gaussian" else 150.0)
+    out, _ = run_plugin(kernel, y, x, b, normalize_rows=True)
+    want = orc.kernel_product(kernel, y, x, b, normalize_rows=True)
+    assert np.isfinite(out).all()
+    assert orc.rel_l2(out, want) <= 2e-4  # the exponent itself is ~1e3 ulps of FP32 away from zero here
+
+
+def test_inverse_distance_zeroing_follows_global_rows():
+    """row_offset shifts the zeroed column (bruteforce.py:12-14 works on the global flat index)."""
+    import torch
+    from kernel_matrix_benchmarks_b200.product import kernel_product
+
+    g = load_golden("product_invdist_tall_d3")
+    y = torch.tensor(g["source_points"], dtype=torch.float32, device="cuda")
+    x = torch.tensor(g["target_points"], dtype=torch.float32, device="cuda")
+    b = torch.tensor(g["source_signal"], dtype=torch.float32, device="cuda")
+    lo, hi = 40, 120
+    part = kernel_product(x[lo:hi].contiguous(), y, b, kernel="inverse-distance", row_offset=lo).cpu().numpy()
+    assert orc.rel_l2(part, g["truth"][lo:hi]) <= TOL_DIRECT
+
+
+def test_config_c1_full():
+    """BASELINE config 1: Gaussian N=M=10k, D=3, E=1, all rows against the float64 oracle."""
+    from kernel_matrix_benchmarks_b200 import datasets
+
+    ds = datasets.config_c1()
+    out, extra = run_plugin("gaussian", ds.source_points, None, ds.source_signal, same_points=True)
+    want = c_oracle.kernel_product("gaussian", ds.source_points, None, ds.source_signal)
+    err = orc.rel_l2(out, want)
+    print(f"C1 rel-L2 {err:.2e} {extra}")
+    assert err <= TOL_DIRECT
+
+
+def test_config_c2_full_size_sampled_and_properties():
+    """BASELINE config 2 at full size (N=M=1M, D=3): sampled rows against the oracle, plus
+    size-independent properties: bitwise determinism, linearity in b, density == product with ones."""
+    import torch
+    from kernel_matrix_benchmarks_b200 import datasets
+    from kernel_matrix_benchmarks_b200.product import kernel_product
+
+    ds = datasets.config_c2()
+    n = ds.N
+    out, extra = run_plugin("gaussian", ds.source_points, None, ds.source_signal, same_points=True)
+    rows = np.random.RandomState(0).choice(n, 768, replace=False)
+    want = c_oracle.kernel_product("gaussian", ds.source_points, None, ds.source_signal, rows=rows)
+    err = orc.rel_l2(out[rows], want)
+    print(f"C2 sampled rel-L2 {err:.2e} {extra}")
+    assert err <= TOL_DIRECT
+
+    y = torch.tensor(ds.source_points, dtype=torch.float32, device="cuda")
+    b1 = torch.tensor(ds.source_signal, dtype=torch.float32, device="cuda")
+    b2 = torch.randn(n, 1, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    a1 = kernel_product(y, y, b1)
+    assert torch.equal(a1, kernel_product(y, y, b1)), "stream-K combination must be deterministic"
+    assert np.array_equal(a1.cpu().numpy().astype(np.float64), out)
+    a2 = kernel_product(y, y, b2)
+    a12 = kernel_product(y, y, 0.5 * b1 - 2.0 * b2)
+    lin = (a12 - (0.5 * a1 - 2.0 * a2)).norm() / a12.norm()
+    assert float(lin) <= 1e-5
+    dens = kernel_product(y, y, None, density_estimation=True)
+    ones = kernel_product(y, y, torch.ones_like(b1))
+    assert torch.equal(dens, ones)
+    att = kernel_product(y, y, torch.full_like(b1, 3.25), normalize_rows=True)
+    assert float((att - 3.25).abs().max()) <= 1e-5
+
+
+def test_density_attention_is_ones():
+    g = load_golden("density_attention_gaussian_cube_d3")
+    out, _ = run_plugin("gaussian", g["source_points"], None, g["source_signal"], same_points=True, normalize_rows=True, density=True)
+    assert np.array_equal(out, np.ones_like(g["truth"]))
+
+
+def test_c_abi_error_paths():
+    import torch
+    from kernel_matrix_benchmarks_b200 import _lib
+    from kernel_matrix_benchmarks_b200.product import kernel_product
+
+    lib = _lib.load()
+    x = torch.rand(10, 3, device="cuda")
+    b = torch.rand(10, 1, device="cuda")
+    out = torch.empty(10, 1, device="cuda")
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    # workspace too small
+    rc = lib.kmb_product_f32(P(x), P(x), P(b), P(out), 10, 10, 3, 1, 0, 0, 0, 0, P(out), 4, None)
+    assert rc == _lib.KMB_ERR_WORKSPACE and b"workspace too small" in lib.kmb_last_error()
+    # NULL signal without the density flag
+    rc = lib.kmb_product_f32(P(x), P(x), None, P(out), 10, 10, 3, 1, 0, 0, 0, 0, P(out), 4, None)
+    assert rc == _lib.KMB_ERR_INVALID
+    with pytest.raises(NotImplementedError):
+        kernel_product(x, x, b, kernel="laplace")
+    with pytest.raises(ValueError):
+        kernel_product(x.double(), x, b)
+    with pytest.raises(NotImplementedError):
+        kernel_product(torch.rand(4, 20, device="cuda"), torch.rand(4, 20, device="cuda"), torch.rand(4, 1, device="cuda"), path="direct")
