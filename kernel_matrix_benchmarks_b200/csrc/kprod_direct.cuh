@@ -36,14 +36,16 @@ struct DirectParams {
     float xscale;         // coordinate scale folded into x (same as the records')
 };
 
-template <int DP_, int EP_, int R_, int KID_, bool NORM_, bool PACKED_ = true>
+template <int DP_, int EP_, int R_, int KID_, bool NORM_, int CONSUMERS_ = 256, int UNROLL_ = 2, int MINB_ = 0,
+          int STAGES_ = 4>
 struct DirectCfg {
     static constexpr int DP = DP_, EP = EP_, R = R_, KID = KID_;
-    static constexpr bool NORM = NORM_, PACKED = PACKED_;
-    static constexpr int CONSUMERS = 256;
+    static constexpr bool NORM = NORM_;
+    static constexpr int CONSUMERS = CONSUMERS_;
+    static constexpr int UNROLL = UNROLL_;
     static constexpr int THREADS = CONSUMERS + 32;  // + one producer warp
     static constexpr int TILE_ROWS = CONSUMERS * R;
-    static constexpr int STAGES = 4;
+    static constexpr int STAGES = STAGES_;
     static constexpr int PAIRS = DP + EP;           // float2 per record
     static constexpr int RECV = (PAIRS + 1) / 2;    // float4 per record
     // source records per stage: ~16 KB stages whatever the record size
@@ -54,6 +56,8 @@ struct DirectCfg {
     static constexpr bool ONLINE_MAX = NORM && (KID != KMB_KERNEL_INVERSE_DISTANCE);
     // floats of partial state per row when a tile is split across CTAs
     static constexpr int PS = EP + (NORM ? 1 : 0) + (ONLINE_MAX ? 1 : 0);
+    // resident CTAs per SM the register allocator is asked to make room for
+    static constexpr int MINB = MINB_ > 0 ? MINB_ : ((!ONLINE_MAX && DP * R <= 32 && EP * R <= 16) ? 2 : 1);
     static_assert(R % 2 == 0, "rows are processed as packed pairs");
 };
 
@@ -76,7 +80,7 @@ __device__ __forceinline__ float kernel_log2(float s) {
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::THREADS, (!C::ONLINE_MAX && C::DP * C::R <= 32 && C::EP * C::R <= 16) ? 2 : 1)
+__global__ void __launch_bounds__(C::THREADS, C::MINB)
 kprod_direct_kernel(const DirectParams P) {
     constexpr int DP = C::DP, EP = C::EP, R = C::R, RP = C::R / 2, KID = C::KID;
     constexpr int SB = C::SB, STAGES = C::STAGES, RECV = C::RECV;
@@ -160,7 +164,7 @@ kprod_direct_kernel(const DirectParams P) {
             [[maybe_unused]] const long long j_base = (sb0 + k) * SB;
 
             if constexpr (!C::ONLINE_MAX) {
-#pragma unroll 2
+#pragma unroll(C::UNROLL)
                 for (int j = 0; j < SB; ++j) {
                     float4 v[RECV];
 #pragma unroll

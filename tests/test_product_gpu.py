@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 TOL_DIRECT = 1e-5
 TOL_TENSOR = 1e-4
 PRODUCT_CASES = [n for n in golden_names() if not n.startswith("solver_")]
+TENSOR_PATH_BUILT = False  # flipped when kmb_product_f32 grows KMB_PATH_TENSOR_3XTF32
 
 
 def run_plugin(kernel, y, x, b, *, same_points=False, normalize_rows=False, density=False, path="auto"):
@@ -38,7 +39,18 @@ def run_plugin(kernel, y, x, b, *, same_points=False, normalize_rows=False, dens
     return out, extra
 
 
-@pytest.mark.parametrize("name", PRODUCT_CASES)
+def _golden_params():
+    out = []
+    for n in PRODUCT_CASES:
+        D = load_golden(n)["source_points"].shape[1]
+        marks = []
+        if D > 16 and not TENSOR_PATH_BUILT:
+            marks = [pytest.mark.xfail(reason="tcgen05 3xTF32 path not built yet", raises=NotImplementedError, strict=True)]
+        out.append(pytest.param(n, marks=marks))
+    return out
+
+
+@pytest.mark.parametrize("name", _golden_params())
 def test_golden_vectors(name):
     g = load_golden(name)
     D = g["source_points"].shape[1]

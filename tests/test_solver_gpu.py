@@ -1,0 +1,65 @@
+"""CG solver plugin on the GPU against the dense SPD oracle (needs a B200)."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+from oracle import bruteforce_oracle as orc
+
+pytestmark = pytest.mark.gpu
+SOLVER_CASES = [n for n in golden_names() if n.startswith("solver_")]
+
+
+def run_solver(kernel, points, rhs, **kw):
+    """The call sequence of runner.py:87-143 for a solver task."""
+    from kernel_matrix_benchmarks_b200.algorithms.b200 import B200Solver
+
+    algo = B200Solver(kernel=kernel, dimension=points.shape[1], precision="float32", **kw)
+    try:
+        algo.prepare_data(source_points=points)
+        algo.fit()
+        algo.prepare_query(target_signal=rhs)
+        algo.query()
+        out, extra = algo.get_result(), algo.get_additional()
+    finally:
+        algo.done()
+    return out, extra
+
+
+@pytest.mark.parametrize("name", SOLVER_CASES)
+def test_cg_matches_dense_spd_solve(name):
+    g = load_golden(name)
+    lam = float(g["lam"])
+    x, extra = run_solver(g["kernel"], g["source_points"], g["rhs"], lam=lam, rtol=1e-6, max_iter=2000)
+    assert x.shape == g["spd_solution"].shape and x.dtype == np.float64
+    assert extra["cg_converged"], extra
+    # residual scored with the float64 oracle product
+    res = orc.rel_l2(orc.regularised_matvec(g["kernel"], g["source_points"], x, lam), g["rhs"])
+    assert res <= 5e-6, (res, extra)
+    # FP32 CG reaches the dense float64 solution up to cond(K + lam I) * eps32
+    tol = 1e-4 if lam >= 1 else 5e-3
+    assert orc.rel_l2(x, g["spd_solution"]) <= tol, extra
+
+
+def test_cg_multiple_right_hand_sides_and_query_args():
+    from kernel_matrix_benchmarks_b200 import datasets
+    from kernel_matrix_benchmarks_b200.algorithms.b200 import B200Solver
+
+    ds = datasets.uniform_cube(3000, 3, 1.0, "gaussian", "solver", signal_dim=3)
+    lam = 1.0
+    rhs = orc.regularised_matvec("gaussian", ds.source_points, ds.source_signal, lam)
+    algo = B200Solver(kernel="gaussian", dimension=3, precision="float32", lam=0.0, rtol=1e-2)
+    algo.prepare_data(source_points=ds.source_points)
+    algo.fit()
+    algo.set_query_arguments(lam=lam, rtol=1e-6, max_iter=300)  # algos.yaml query-args (runner.py:123)
+    algo.prepare_query(target_signal=rhs)
+    algo.query()
+    x, extra = algo.get_result(), algo.get_additional()
+    algo.done()
+    assert x.shape == (3000, 3) and extra["cg_converged"]
+    assert orc.rel_l2(x, ds.source_signal) <= 1e-4
+
+
+def test_cg_zero_rhs_returns_zero():
+    pts = np.random.RandomState(0).rand(500, 3)
+    x, extra = run_solver("gaussian", pts, np.zeros((500, 1)), lam=1.0)
+    assert np.array_equal(x, np.zeros((500, 1))) and extra["cg_iterations"] == 0
