@@ -57,8 +57,13 @@ enum {
 /* evaluation paths */
 enum {
     KMB_PATH_AUTO = 0,
-    KMB_PATH_DIRECT_F32 = 1,  /* sum of squared differences (bruteforce.py:53-54) in FP32 FMAs, D <= 16 */
-    KMB_PATH_TENSOR_3XTF32 = 2 /* |x|^2+|y|^2-2x.y (bruteforce.py:36-49) on tcgen05, 3xTF32 split, D >= 32 */
+    KMB_PATH_DIRECT_F32 = 1,   /* FP32 FMA + MUFU path, D <= 16.  Squared distances as a sum of squared
+                                  differences (bruteforce.py:53-54); for the Gaussian kernel on data whose
+                                  centred bounding box is small (log2(e) * half-diagonal^2 <= 6, decided on
+                                  the device) the algebraically equal product form
+                                  2^(-|u|^2) 2^(2u.v) 2^(-|v|^2) is used instead (4 FMA slots per pair, not 7) */
+    KMB_PATH_TENSOR_3XTF32 = 2, /* |x|^2+|y|^2-2x.y (bruteforce.py:36-49) on tcgen05, 3xTF32 split, D >= 32 */
+    KMB_PATH_DIRECT_DIFF = 3   /* KMB_PATH_DIRECT_F32 restricted to the difference form */
 };
 
 typedef struct {

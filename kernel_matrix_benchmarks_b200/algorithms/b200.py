@@ -134,7 +134,15 @@ class B200Product(BaseProduct):
             "gpairs_per_s": pairs / (self.query_ms * 1e-3) / 1e9,
             "gpu_launches": int(self.launches),
             "path": self.path,
+            "form": self._form(),
         }
+
+    def _form(self):
+        if self.source_points.shape[1] > 16 or (self.normalize_rows and self.density_estimation):
+            return "n/a"
+        from ..product import direct_stats
+
+        return direct_stats(self.workspace)["form"]
 
     def get_memory_usage(self):
         """Host RSS as the reference reports, plus device bytes in kB."""

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 
 #include "kprod_direct.cuh"
 
@@ -33,18 +34,21 @@ KMB_DECLARE_TABLE(kDirect_absexp_n0)
 KMB_DECLARE_TABLE(kDirect_absexp_n1)
 KMB_DECLARE_TABLE(kDirect_invdist_n0)
 KMB_DECLARE_TABLE(kDirect_invdist_n1)
+KMB_DECLARE_TABLE(kDirect_gaussprod_n0)
+KMB_DECLARE_TABLE(kDirect_gaussprod_n1)
 
-static const DirectEntry* find_direct(int D, int e_chunk, int kid, bool norm) {
+static const DirectEntry* find_direct(int D, int e_chunk, int kid, bool norm, int form) {
     const DirectEntry* tab = nullptr;
     int n = 0;
-#define KMB_PICK(K, NAME0, NAME1)            \
-    if (kid == K) {                          \
-        tab = norm ? NAME1 : NAME0;          \
+#define KMB_PICK(K, F, NAME0, NAME1)              \
+    if (kid == K && form == F) {                  \
+        tab = norm ? NAME1 : NAME0;               \
         n = norm ? NAME1##_count : NAME0##_count; \
     }
-    KMB_PICK(KMB_KERNEL_GAUSSIAN, kDirect_gauss_n0, kDirect_gauss_n1)
-    KMB_PICK(KMB_KERNEL_ABSOLUTE_EXPONENTIAL, kDirect_absexp_n0, kDirect_absexp_n1)
-    KMB_PICK(KMB_KERNEL_INVERSE_DISTANCE, kDirect_invdist_n0, kDirect_invdist_n1)
+    KMB_PICK(KMB_KERNEL_GAUSSIAN, 0, kDirect_gauss_n0, kDirect_gauss_n1)
+    KMB_PICK(KMB_KERNEL_GAUSSIAN, 1, kDirect_gaussprod_n0, kDirect_gaussprod_n1)
+    KMB_PICK(KMB_KERNEL_ABSOLUTE_EXPONENTIAL, 0, kDirect_absexp_n0, kDirect_absexp_n1)
+    KMB_PICK(KMB_KERNEL_INVERSE_DISTANCE, 0, kDirect_invdist_n0, kDirect_invdist_n1)
 #undef KMB_PICK
     const DirectEntry* best = nullptr;
     for (int i = 0; i < n; ++i) {
@@ -64,12 +68,15 @@ static float coord_scale(int kid) {
     return 1.0f;
 }
 
+struct FormPlan {   // one evaluation form's kernel and geometry
+    const DirectEntry* ent = nullptr;
+    long long n_tiles = 0, nsb = 0, M_pad = 0;
+};
 struct DirectPlan {
-    const DirectEntry* ent;
+    FormPlan form[2];   // [0] difference form (always), [1] Gaussian product form (optional)
     int e_chunk, n_passes;
-    long long n_tiles, nsb, M_pad;
     int grid_max;
-    size_t rec_bytes, partial_bytes, counter_bytes, total_bytes;
+    size_t stats_bytes, rec_bytes, partial_bytes, counter_bytes, total_bytes;
 };
 
 static int device_sm_count(int* sms) {
@@ -84,24 +91,30 @@ static int device_sm_count(int* sms) {
     return KMB_OK;
 }
 
-static int plan_direct(int64_t N, int64_t M, int D, int E, int kid, int flags, DirectPlan* pl) {
+static int plan_direct(int64_t N, int64_t M, int D, int E, int kid, int flags, int path, DirectPlan* pl) {
     const bool norm = flags & KMB_FLAG_NORMALIZE_ROWS;
     if (D > 16) return set_error(KMB_ERR_UNSUPPORTED, "direct FP32 path supports D <= 16 (got D=%d)", D);
     pl->e_chunk = E >= 4 ? 4 : E;
     pl->n_passes = (E + pl->e_chunk - 1) / pl->e_chunk;
-    pl->ent = find_direct(D, pl->e_chunk, kid, norm);
-    if (!pl->ent) return set_error(KMB_ERR_UNSUPPORTED, "no direct kernel for D=%d E=%d kernel=%d", D, E, kid);
-    const DirectEntry& e = *pl->ent;
-    pl->n_tiles = (N + e.TILE_ROWS - 1) / e.TILE_ROWS;
-    pl->nsb = (M + e.SB - 1) / e.SB;
-    pl->M_pad = pl->nsb * e.SB;
+    pl->form[0].ent = find_direct(D, pl->e_chunk, kid, norm, 0);
+    if (!pl->form[0].ent) return set_error(KMB_ERR_UNSUPPORTED, "no direct kernel for D=%d E=%d kernel=%d", D, E, kid);
+    pl->form[1].ent = (kid == KMB_KERNEL_GAUSSIAN && path != KMB_PATH_DIRECT_DIFF) ? find_direct(D, pl->e_chunk, kid, norm, 1) : nullptr;
     int sms = 0;
     if (int rc = device_sm_count(&sms)) return rc;
     pl->grid_max = sms * 2;
-    pl->rec_bytes = align_up(static_cast<size_t>(pl->M_pad) * e.RECV * 16, 256);
-    pl->partial_bytes = align_up(static_cast<size_t>(pl->grid_max) * 2 * e.TILE_ROWS * e.PS * 4, 256);
-    pl->counter_bytes = align_up(static_cast<size_t>(pl->n_tiles) * 4, 256);
-    pl->total_bytes = pl->rec_bytes + pl->partial_bytes + pl->counter_bytes;
+    pl->stats_bytes = align_up(sizeof(DirectStats), 256) + align_up(sizeof(float) * STATS_MAX_BLOCKS * 2 * 16, 256);
+    pl->rec_bytes = pl->partial_bytes = pl->counter_bytes = 0;
+    for (FormPlan& f : pl->form) {
+        if (!f.ent) continue;
+        const DirectEntry& e = *f.ent;
+        f.n_tiles = (N + e.TILE_ROWS - 1) / e.TILE_ROWS;
+        f.nsb = (M + e.SB - 1) / e.SB;
+        f.M_pad = f.nsb * e.SB;
+        pl->rec_bytes = std::max(pl->rec_bytes, align_up(static_cast<size_t>(f.M_pad) * e.RECV * 16, 256));
+        pl->partial_bytes = std::max(pl->partial_bytes, align_up(static_cast<size_t>(pl->grid_max) * 2 * e.TILE_ROWS * e.PS * 4, 256));
+        pl->counter_bytes = std::max(pl->counter_bytes, align_up(static_cast<size_t>(f.n_tiles) * 4, 256));
+    }
+    pl->total_bytes = pl->stats_bytes + pl->rec_bytes + pl->partial_bytes + pl->counter_bytes;
     return KMB_OK;
 }
 
@@ -115,7 +128,7 @@ static int check_product_args(int64_t N, int64_t M, int D, int E, int kid, int f
     if (kid < 0 || kid > KMB_KERNEL_INVERSE_DISTANCE) return set_error(KMB_ERR_UNSUPPORTED, "unknown kernel id %d", kid);
     if (flags & ~(KMB_FLAG_NORMALIZE_ROWS | KMB_FLAG_DENSITY)) return set_error(KMB_ERR_INVALID, "unknown flags 0x%x", flags);
     if ((flags & KMB_FLAG_DENSITY) && E != 1) return set_error(KMB_ERR_INVALID, "density estimation implies E == 1 (got %d)", E);
-    if (path < KMB_PATH_AUTO || path > KMB_PATH_TENSOR_3XTF32) return set_error(KMB_ERR_INVALID, "unknown path %d", path);
+    if (path < KMB_PATH_AUTO || path > KMB_PATH_DIRECT_DIFF) return set_error(KMB_ERR_INVALID, "unknown path %d", path);
     return KMB_OK;
 }
 
@@ -168,9 +181,9 @@ int kmb_product_workspace_bytes(int64_t N, int64_t M, int D, int E, int kernel_i
     *bytes = 256;
     if ((flags & KMB_FLAG_NORMALIZE_ROWS) && (flags & KMB_FLAG_DENSITY)) return KMB_OK;
     const int p = resolve_path(D, path);
-    if (p == KMB_PATH_DIRECT_F32) {
+    if (p == KMB_PATH_DIRECT_F32 || p == KMB_PATH_DIRECT_DIFF) {
         DirectPlan pl;
-        if (int rc = plan_direct(N, M, D, E, kernel_id, flags, &pl)) return rc;
+        if (int rc = plan_direct(N, M, D, E, kernel_id, flags, p, &pl)) return rc;
         *bytes = pl.total_bytes;
         return KMB_OK;
     }
@@ -195,60 +208,66 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
         return KMB_OK;
     }
     const int p = resolve_path(D, path);
-    if (p != KMB_PATH_DIRECT_F32)
+    if (p != KMB_PATH_DIRECT_F32 && p != KMB_PATH_DIRECT_DIFF)
         return set_error(KMB_ERR_UNSUPPORTED, "tensor-core path (D=%d) is not built yet", D);
 
     DirectPlan pl;
-    if (int rc = plan_direct(N, M, D, E, kernel_id, flags, &pl)) return rc;
+    if (int rc = plan_direct(N, M, D, E, kernel_id, flags, p, &pl)) return rc;
     if (!workspace || workspace_bytes < pl.total_bytes)
         return set_error(KMB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total_bytes, workspace_bytes);
     if (reinterpret_cast<uintptr_t>(workspace) % 256)
         return set_error(KMB_ERR_INVALID, "workspace must be 256-byte aligned");
-    const DirectEntry& ent = *pl.ent;
     char* ws = static_cast<char*>(workspace);
-    float2* rec = reinterpret_cast<float2*>(ws);
-    float* partial = reinterpret_cast<float*>(ws + pl.rec_bytes);
-    int* counters = reinterpret_cast<int*>(ws + pl.rec_bytes + pl.partial_bytes);
+    DirectStats* stats = reinterpret_cast<DirectStats*>(ws);
+    float* block_box = reinterpret_cast<float*>(ws + align_up(sizeof(DirectStats), 256));
+    float2* rec = reinterpret_cast<float2*>(ws + pl.stats_bytes);
+    float* partial = reinterpret_cast<float*>(ws + pl.stats_bytes + pl.rec_bytes);
+    int* counters = reinterpret_cast<int*>(ws + pl.stats_bytes + pl.rec_bytes + pl.partial_bytes);
+    KMB_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(DirectStats), stream));
     KMB_CUDA_CHECK(cudaMemsetAsync(counters, 0, pl.counter_bytes, stream));
 
-    // resident CTAs of this instantiation (cached per kernel function)
-    static const void* occ_func[64];
-    static int occ_val[64], occ_n = 0;
-    int per_sm = 0;
-    for (int i = 0; i < occ_n; ++i)
-        if (occ_func[i] == ent.func) per_sm = occ_val[i];
-    if (!per_sm) {
-        KMB_CUDA_CHECK(cudaFuncSetAttribute(ent.func, cudaFuncAttributeMaxDynamicSharedMemorySize, ent.SMEM));
-        KMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ent.func, ent.THREADS, ent.SMEM));
-        if (per_sm < 1) return set_error(KMB_ERR_CUDA, "kernel does not fit on an SM (smem %d B)", ent.SMEM);
-        if (per_sm > 2) per_sm = 2;
-        if (occ_n < 64) { occ_func[occ_n] = ent.func; occ_val[occ_n++] = per_sm; }
+    // bounding box -> centre, radius, evaluation form (stays on the device)
+    {
+        const long long pts = M + ((x == y && N == M) ? 0 : N);
+        long long blocks = (pts + STATS_THREADS * 8 - 1) / (STATS_THREADS * 8);
+        blocks = std::max(1LL, std::min<long long>(blocks, STATS_MAX_BLOCKS));
+        direct_stats_kernel<<<static_cast<unsigned>(blocks), STATS_THREADS, 0, stream>>>(x, N, y, M, D, block_box, stats,
+                                                                                         pl.form[1].ent ? 1 : 0);
+        KMB_CUDA_CHECK(cudaGetLastError());
+        count_launch();
     }
-    const long long units = pl.n_tiles * pl.nsb;
-    long long grid = static_cast<long long>(pl.grid_max / 2) * per_sm;
-    if (grid > units) grid = units;
+
+    // resident CTAs per SM of each instantiation (cached per kernel function)
+    static const void* occ_func[128];
+    static int occ_val[128], occ_n = 0;
+    auto resident = [&](const DirectEntry& ent, int* per_sm) -> int {
+        for (int i = 0; i < occ_n; ++i)
+            if (occ_func[i] == ent.func) { *per_sm = occ_val[i]; return KMB_OK; }
+        KMB_CUDA_CHECK(cudaFuncSetAttribute(ent.func, cudaFuncAttributeMaxDynamicSharedMemorySize, ent.SMEM));
+        KMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, ent.func, ent.THREADS, ent.SMEM));
+        if (*per_sm < 1) return set_error(KMB_ERR_CUDA, "kernel does not fit on an SM (smem %d B)", ent.SMEM);
+        if (*per_sm > 2) *per_sm = 2;
+        if (occ_n < 128) { occ_func[occ_n] = ent.func; occ_val[occ_n++] = *per_sm; }
+        return KMB_OK;
+    };
 
     const float scale = coord_scale(kernel_id);
+    const DirectEntry& e0ent = *pl.form[0].ent;
+    PackLayout lay[2];
+    for (int f = 0; f < 2; ++f) {
+        const DirectEntry* e = pl.form[f].ent ? pl.form[f].ent : pl.form[0].ent;
+        const FormPlan& fp = pl.form[f].ent ? pl.form[f] : pl.form[0];
+        lay[f].M_pad = fp.M_pad;
+        lay[f].wcol = e->WCOL;
+        lay[f].pairs_per_rec = e->RECV * 2;
+    }
+    const long long pack_rows = std::max(lay[0].M_pad, lay[1].M_pad);
     for (int pass = 0; pass < pl.n_passes; ++pass) {
         const int e0 = pass * pl.e_chunk;
-        pack_sources_kernel<<<static_cast<unsigned>((pl.M_pad + 255) / 256), 256, 0, stream>>>(
-            y, density ? nullptr : b, rec, M, pl.M_pad, D, E, ent.DP, ent.EP, ent.RECV * 2, e0, scale);
+        pack_sources_kernel<<<static_cast<unsigned>((pack_rows + 255) / 256), 256, 0, stream>>>(
+            y, density ? nullptr : b, rec, stats, M, D, E, e0ent.DP, e0ent.EP, lay[0], lay[1], e0, scale);
         KMB_CUDA_CHECK(cudaGetLastError());
-        DirectParams P;
-        P.x = x;
-        P.rec = reinterpret_cast<const float4*>(rec);
-        P.out = out;
-        P.partial = partial;
-        P.tile_counter = counters;
-        P.N = N;
-        P.M = M;
-        P.row_offset = row_offset;
-        P.D = D;
-        P.E = E;
-        P.e0 = e0;
-        P.n_tiles = static_cast<int>(pl.n_tiles);
-        P.n_src_blocks = static_cast<int>(pl.nsb);
-        P.xscale = scale;
+        count_launch();
         if (g_profile) {
             if (!g_ev0) {
                 KMB_CUDA_CHECK(cudaEventCreate(&g_ev0));
@@ -256,12 +275,38 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
             }
             KMB_CUDA_CHECK(cudaEventRecord(g_ev0, stream));
         }
-        KMB_CUDA_CHECK(ent.launch(P, static_cast<int>(grid), stream));
+        // both forms are enqueued; the one the data did not select returns at once
+        for (int f = 1; f >= 0; --f) {
+            if (!pl.form[f].ent) continue;
+            const DirectEntry& ent = *pl.form[f].ent;
+            int per_sm = 0;
+            if (int rc = resident(ent, &per_sm)) return rc;
+            const long long units = pl.form[f].n_tiles * pl.form[f].nsb;
+            long long grid = static_cast<long long>(pl.grid_max / 2) * per_sm;
+            if (grid > units) grid = units;
+            DirectParams P;
+            P.x = x;
+            P.stats = stats;
+            P.rec = reinterpret_cast<const float4*>(rec);
+            P.out = out;
+            P.partial = partial;
+            P.tile_counter = counters;
+            P.N = N;
+            P.M = M;
+            P.row_offset = row_offset;
+            P.D = D;
+            P.E = E;
+            P.e0 = e0;
+            P.n_tiles = static_cast<int>(pl.form[f].n_tiles);
+            P.n_src_blocks = static_cast<int>(pl.form[f].nsb);
+            P.xscale = scale;
+            KMB_CUDA_CHECK(ent.launch(P, static_cast<int>(grid), stream));
+            count_launch();
+        }
         if (g_profile) {
             KMB_CUDA_CHECK(cudaEventRecord(g_ev1, stream));
             g_ev_valid = true;
         }
-        count_launch(2);
     }
     return KMB_OK;
 }

@@ -50,6 +50,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Producer-side wait: the slot frees once per ~10^4 cycles, so sleep between probes instead of
+// competing with the consumer warps for issue slots.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
                                              uint64_t* bar) {

@@ -22,8 +22,27 @@
 
 namespace kmb {
 
+// Filled on the device by direct_stats_kernel (no host round trip): the bounding-box centre the
+// coordinates are shifted by, and which evaluation form the Gaussian kernel may use.
+struct DirectStats {
+    float center[16];
+    float radius2;      // log2(e) * squared half-diagonal of the bounding box of x and y
+    int use_product;    // 1: product form is accurate for this data (radius2 <= kProductFormRadius2)
+    unsigned int counter;
+    int pad;
+};
+// Gaussian "product form": with u = s(x-c), v = s(y-c), s^2 = log2(e):
+//   exp(-|x-y|^2) = 2^(-|u|^2) * 2^(2 u.v) * 2^(-|v|^2)
+// 2^(-|v|^2) is folded into the packed signal, 2^(-|u|^2) into the final store, which leaves
+// FMUL2 + 2 FFMA2 + 2 MUFU + FFMA2 per two pairs (4 FMA-pipe slots instead of 7).  The exponent
+// 2u.v is computed to ~3 ulp of its magnitude, so the form is only used when the centred data
+// are small: |2u.v| <= 2*radius2 <= 12 keeps the relative error of every k below ~1e-6 and all
+// factors within 2^+-12 (no overflow / underflow).  Otherwise the difference form runs.
+constexpr float kProductFormRadius2 = 6.0f;
+
 struct DirectParams {
     const float* x;       // (N, D) targets, unscaled
+    const DirectStats* stats;
     const float4* rec;    // packed source records: n_src_blocks * SB records of RECV float4
     float* out;           // (N, E)
     float* partial;       // G * 2 slots * TILE_ROWS * PS floats
@@ -36,24 +55,29 @@ struct DirectParams {
     float xscale;         // coordinate scale folded into x (same as the records')
 };
 
-template <int DP_, int EP_, int R_, int KID_, bool NORM_, int CONSUMERS_ = 256, int UNROLL_ = 2, int MINB_ = 0,
-          int STAGES_ = 4>
+// FORM_: 0 = difference form (any kernel), 1 = Gaussian product form
+template <int DP_, int EP_, int R_, int KID_, bool NORM_, int FORM_ = 0, int CONSUMERS_ = 256, int UNROLL_ = 4,
+          int MINB_ = 0, int STAGES_ = 4>
 struct DirectCfg {
-    static constexpr int DP = DP_, EP = EP_, R = R_, KID = KID_;
+    static constexpr int DP = DP_, EP = EP_, R = R_, KID = KID_, FORM = FORM_;
     static constexpr bool NORM = NORM_;
+    static_assert(FORM == 0 || KID == KMB_KERNEL_GAUSSIAN, "product form is Gaussian-only");
+    // product form + row normalisation: the record carries 2^(-|v|^2) as one more signal column
+    static constexpr int WCOL = (FORM == 1 && NORM) ? 1 : 0;
     static constexpr int CONSUMERS = CONSUMERS_;
     static constexpr int UNROLL = UNROLL_;
     static constexpr int THREADS = CONSUMERS + 32;  // + one producer warp
     static constexpr int TILE_ROWS = CONSUMERS * R;
     static constexpr int STAGES = STAGES_;
-    static constexpr int PAIRS = DP + EP;           // float2 per record
+    static constexpr int PAIRS = DP + EP + WCOL;    // float2 per record
     static constexpr int RECV = (PAIRS + 1) / 2;    // float4 per record
     // source records per stage: ~16 KB stages whatever the record size
     static constexpr int SB = RECV <= 2 ? 512 : RECV <= 4 ? 256 : RECV <= 8 ? 128 : 64;
     static constexpr int STAGE_BYTES = SB * RECV * 16;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 16;
     // exp-type kernels under row normalisation carry a running max (online rescale)
-    static constexpr bool ONLINE_MAX = NORM && (KID != KMB_KERNEL_INVERSE_DISTANCE);
+    // (the product form only runs on data where nothing can underflow)
+    static constexpr bool ONLINE_MAX = NORM && (KID != KMB_KERNEL_INVERSE_DISTANCE) && FORM == 0;
     // floats of partial state per row when a tile is split across CTAs
     static constexpr int PS = EP + (NORM ? 1 : 0) + (ONLINE_MAX ? 1 : 0);
     // resident CTAs per SM the register allocator is asked to make room for
@@ -79,6 +103,18 @@ __device__ __forceinline__ float kernel_log2(float s) {
     else return -sqrt_approx(s);
 }
 
+// 2^(-|u|^2) of one target row (product form), recomputed at store time to keep it out of the loop
+template <int DP>
+__device__ __forceinline__ float product_row_scale(const DirectParams& P, long long row) {
+    float n2 = 0.f;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+        const float u = d < P.D ? (__ldg(P.x + row * P.D + d) - P.stats->center[d]) * P.xscale : 0.f;
+        n2 = fmaf(u, u, n2);
+    }
+    return exp2f(-n2);
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
 kprod_direct_kernel(const DirectParams P) {
@@ -89,6 +125,9 @@ kprod_direct_kernel(const DirectParams P) {
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + STAGES * C::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     int* s_flag = reinterpret_cast<int*>(empty_bar + STAGES);
+
+    // both forms of a Gaussian product are enqueued; the data decide (on the device) which one runs
+    if ((P.stats->use_product != 0) != (C::FORM == 1)) return;
 
     const int tid = threadIdx.x;
     const int G = gridDim.x;
@@ -113,7 +152,7 @@ kprod_direct_kernel(const DirectParams P) {
             for (long long u = u0; u < u1; ++u, ++it) {
                 const int stage = it % STAGES;
                 const uint32_t parity = (it / STAGES) & 1;
-                mbar_wait(&empty_bar[stage], parity ^ 1);
+                mbar_wait_backoff(&empty_bar[stage], parity ^ 1);
                 mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
                 const long long sblk = u % nsb;
                 tma_bulk_g2s(stage_base + stage * (SB * RECV), P.rec + sblk * (SB * RECV), C::STAGE_BYTES,
@@ -141,7 +180,9 @@ kprod_direct_kernel(const DirectParams P) {
             const bool ok = row < P.N;
 #pragma unroll
             for (int d = 0; d < DP; ++d) {
-                const float v = (ok && d < P.D) ? __ldg(P.x + row * P.D + d) * P.xscale : 0.f;
+                // centred, scaled target: -u for the difference form (records hold +v), 2u for the product form
+                float v = (ok && d < P.D) ? (__ldg(P.x + row * P.D + d) - P.stats->center[d]) * P.xscale : 0.f;
+                v = (C::FORM == 1) ? 2.f * v : -v;
                 if (r & 1) xr[d][r >> 1].y = v; else xr[d][r >> 1].x = v;
             }
             if constexpr (KID == KMB_KERNEL_INVERSE_DISTANCE) jz[r] = (P.row_offset + row) % (P.M + 1);
@@ -172,20 +213,30 @@ kprod_direct_kernel(const DirectParams P) {
                     const float2* pr = reinterpret_cast<const float2*>(v);
 #pragma unroll
                     for (int p = 0; p < RP; ++p) {
-                        float2 s;
+                        float2 s, kv;
+                        if constexpr (C::FORM == 1) {
+                            // 2 u.v, then k' = 2^(2 u.v); 2^(-|v|^2) rides in the signal, 2^(-|u|^2) in the store
 #pragma unroll
-                        for (int d = 0; d < DP; ++d) {
-                            const float2 diff = add2(xr[d][p], pr[d]);
-                            s = (d == 0) ? mul2(diff, diff) : fma2(diff, diff, s);
+                            for (int d = 0; d < DP; ++d) s = (d == 0) ? mul2(xr[d][p], pr[d]) : fma2(xr[d][p], pr[d], s);
+                            kv = make_float2(ex2_approx(s.x), ex2_approx(s.y));
+                        } else {
+#pragma unroll
+                            for (int d = 0; d < DP; ++d) {
+                                const float2 diff = add2(xr[d][p], pr[d]);
+                                s = (d == 0) ? mul2(diff, diff) : fma2(diff, diff, s);
+                            }
+                            kv = make_float2(kernel_value<KID>(s.x), kernel_value<KID>(s.y));
                         }
-                        float2 kv = make_float2(kernel_value<KID>(s.x), kernel_value<KID>(s.y));
                         if constexpr (KID == KMB_KERNEL_INVERSE_DISTANCE) {
                             if (j_base + j == jz[2 * p]) kv.x = 0.f;
                             if (j_base + j == jz[2 * p + 1]) kv.y = 0.f;
                         }
 #pragma unroll
                         for (int e = 0; e < EP; ++e) acc[e][p] = fma2(kv, pr[DP + e], acc[e][p]);
-                        if constexpr (C::NORM) ksum[p] = add2(ksum[p], kv);
+                        if constexpr (C::NORM) {
+                            if constexpr (C::WCOL) ksum[p] = fma2(kv, pr[DP + EP], ksum[p]);
+                            else ksum[p] = add2(ksum[p], kv);
+                        }
                     }
                 }
             } else {
@@ -247,9 +298,12 @@ kprod_direct_kernel(const DirectParams P) {
                 const long long row = row_base + static_cast<long long>(r) * C::CONSUMERS;
                 if (row < P.N) {
                     const float l = (r & 1) ? ksum[r >> 1].y : ksum[r >> 1].x;
+                    [[maybe_unused]] float urow = 1.f;
+                    if constexpr (C::FORM == 1 && !C::NORM) urow = product_row_scale<DP>(P, row);
 #pragma unroll
                     for (int e = 0; e < EP; ++e) {
                         float v = (r & 1) ? acc[e][r >> 1].y : acc[e][r >> 1].x;
+                        if constexpr (C::FORM == 1 && !C::NORM) v *= urow;
                         if constexpr (C::NORM) v = v / l;
                         if (P.e0 + e < P.E) P.out[row * P.E + P.e0 + e] = v;
                     }
@@ -312,9 +366,11 @@ kprod_direct_kernel(const DirectParams P) {
                         for (int e = 0; e < EP; ++e) tot[e] = fmaf(w, __ldcg(ps + e * C::TILE_ROWS + lr), tot[e]);
                         if constexpr (C::NORM) l = fmaf(w, __ldcg(ps + EP * C::TILE_ROWS + lr), l);
                     }
+                    [[maybe_unused]] float urow = 1.f;
+                    if constexpr (C::FORM == 1 && !C::NORM) urow = product_row_scale<DP>(P, row);
 #pragma unroll
                     for (int e = 0; e < EP; ++e)
-                        if (P.e0 + e < P.E) P.out[row * P.E + P.e0 + e] = C::NORM ? tot[e] / l : tot[e];
+                        if (P.e0 + e < P.E) P.out[row * P.E + P.e0 + e] = C::NORM ? tot[e] / l : tot[e] * urow;
                 }
             }
         }
@@ -322,34 +378,114 @@ kprod_direct_kernel(const DirectParams P) {
     }
 }
 
-// ---- source packing -------------------------------------------------------------------------
-// rec[j] = [-s*y_jd (dup) for d < DP | b_je (dup) for e < EP | zero pad], padding records (j >= M)
-// sit far away (k underflows to exactly 0 for the exp kernels) and carry b == 0.
-static __global__ void pack_sources_kernel(const float* __restrict__ y, const float* __restrict__ b, float2* __restrict__ rec,
-                                    long long M, long long M_pad, int D, int E, int DP, int EP, int pairs_per_rec,
-                                    int e0, float scale) {
-    const long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (j >= M_pad) return;
-    float2* o = rec + j * pairs_per_rec;
-    const bool live = j < M;
-    for (int d = 0; d < DP; ++d) {
-        float v = 0.f;
-        if (live) v = d < D ? -scale * y[j * D + d] : 0.f;
-        else v = (d == 0) ? -1.0e18f : 0.f;
-        o[d] = make_float2(v, v);
+// ---- data statistics: bounding box -> centre, radius, evaluation form ------------------------------
+// One pass over y (and x unless it aliases y).  Per-block partial boxes, combined by the last block.
+constexpr int STATS_THREADS = 256;
+constexpr int STATS_MAX_BLOCKS = 256;
+
+static __global__ void __launch_bounds__(STATS_THREADS)
+direct_stats_kernel(const float* __restrict__ x, long long N, const float* __restrict__ y, long long M, int D,
+                    float* __restrict__ block_box /* [blocks][2][16] */, DirectStats* stats, int allow_product) {
+    __shared__ float s_lo[STATS_THREADS / 32][16], s_hi[STATS_THREADS / 32][16];
+    __shared__ bool is_last;
+    float lo[16], hi[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) { lo[d] = INFINITY; hi[d] = -INFINITY; }
+    const long long total = M + (x == y && N == M ? 0 : N);
+    for (long long i = blockIdx.x * static_cast<long long>(STATS_THREADS) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * STATS_THREADS) {
+        const float* pnt = i < M ? y + i * D : x + (i - M) * D;
+#pragma unroll
+        for (int d = 0; d < 16; ++d)
+            if (d < D) { const float v = pnt[d]; lo[d] = fminf(lo[d], v); hi[d] = fmaxf(hi[d], v); }
     }
-    for (int e = 0; e < EP; ++e) {
-        float v = 0.f;
-        if (live && e0 + e < E) v = b ? b[j * E + e0 + e] : 1.f;
-        o[DP + e] = make_float2(v, v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+        if (d < D) {
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+                hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+            }
+            if (lane == 0) { s_lo[warp][d] = lo[d]; s_hi[warp][d] = hi[d]; }
+        }
     }
-    for (int q = DP + EP; q < pairs_per_rec; ++q) o[q] = make_float2(0.f, 0.f);
+    __syncthreads();
+    if (threadIdx.x < D) {
+        float l = INFINITY, h = -INFINITY;
+        for (int w = 0; w < STATS_THREADS / 32; ++w) { l = fminf(l, s_lo[w][threadIdx.x]); h = fmaxf(h, s_hi[w][threadIdx.x]); }
+        block_box[(blockIdx.x * 2 + 0) * 16 + threadIdx.x] = l;
+        block_box[(blockIdx.x * 2 + 1) * 16 + threadIdx.x] = h;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int old = atomicAdd(&stats->counter, 1u);
+        is_last = (old == gridDim.x - 1);
+        if (is_last) stats->counter = 0;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        float r2 = 0.f;
+        for (int d = 0; d < 16; ++d) {
+            float l = INFINITY, h = -INFINITY;
+            if (d < D)
+                for (unsigned int b = 0; b < gridDim.x; ++b) {
+                    l = fminf(l, __ldcg(&block_box[(b * 2 + 0) * 16 + d]));
+                    h = fmaxf(h, __ldcg(&block_box[(b * 2 + 1) * 16 + d]));
+                }
+            const float c = d < D ? 0.5f * (l + h) : 0.f, half = d < D ? 0.5f * (h - l) : 0.f;
+            stats->center[d] = c;
+            r2 = fmaf(half, half, r2);
+        }
+        r2 *= 1.4426950408889634f;
+        stats->radius2 = r2;
+        // NaN/inf coordinates fail the comparison and fall back to the difference form
+        stats->use_product = (allow_product && r2 <= kProductFormRadius2) ? 1 : 0;
+    }
 }
 
+// ---- source packing -------------------------------------------------------------------------
+// rec[j] = [v_jd (dup) for d < DP | b_je (dup) for e < EP | (w_j) | zero pad], v = s (y - c).
+//   difference form: signal as given; padding records (j >= M) sit far away (k underflows to
+//                    exactly 0 for the exp kernels) and carry b == 0.
+//   product form   : signal pre-multiplied by w_j = 2^(-|v_j|^2) (and w_j itself as the extra
+//                    column under row normalisation); padding records are all zero.
+struct PackLayout {   // per evaluation form: the record geometry of the kernel that will read it
+    long long M_pad;
+    int wcol, pairs_per_rec;
+};
+static __global__ void pack_sources_kernel(const float* __restrict__ y, const float* __restrict__ b, float2* __restrict__ rec,
+                                           const DirectStats* __restrict__ stats, long long M, int D, int E, int DP,
+                                           int EP, PackLayout diff_form, PackLayout prod_form, int e0, float scale) {
+    const bool product = stats->use_product != 0;
+    const PackLayout L = product ? prod_form : diff_form;
+    const long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (j >= L.M_pad) return;
+    float2* o = rec + j * L.pairs_per_rec;
+    const bool live = j < M;
+    float n2 = 0.f;
+    for (int d = 0; d < DP; ++d) {
+        float v = 0.f;
+        if (live) v = d < D ? scale * (y[j * D + d] - stats->center[d]) : 0.f;
+        else v = (d == 0 && !product) ? 1.0e18f : 0.f;
+        n2 = fmaf(v, v, n2);
+        o[d] = make_float2(v, v);
+    }
+    const float w = (product && live) ? exp2f(-n2) : (product ? 0.f : 1.f);
+    for (int e = 0; e < EP; ++e) {
+        float v = 0.f;
+        if (live && e0 + e < E) v = (b ? b[j * E + e0 + e] : 1.f) * w;
+        o[DP + e] = make_float2(v, v);
+    }
+    if (L.wcol) o[DP + EP] = make_float2(w, w);
+    for (int q = DP + EP + L.wcol; q < L.pairs_per_rec; ++q) o[q] = make_float2(0.f, 0.f);
+}
 
 // ---- dispatch table entry ---------------------------------------------------------------------
 struct DirectEntry {
-    int DP, EP, KID, NORM, R, SB, RECV, PS, TILE_ROWS, SMEM, THREADS;
+    int DP, EP, KID, NORM, FORM, WCOL, R, SB, RECV, PS, TILE_ROWS, SMEM, THREADS;
     const void* func;
     cudaError_t (*launch)(const DirectParams&, int grid, cudaStream_t stream);
 };
@@ -369,7 +505,7 @@ cudaError_t launch_direct(const DirectParams& P, int grid, cudaStream_t stream) 
 
 template <class C>
 constexpr DirectEntry make_direct_entry() {
-    return DirectEntry{C::DP, C::EP, C::KID, C::NORM ? 1 : 0, C::R, C::SB, C::RECV, C::PS, C::TILE_ROWS,
+    return DirectEntry{C::DP, C::EP, C::KID, C::NORM ? 1 : 0, C::FORM, C::WCOL, C::R, C::SB, C::RECV, C::PS, C::TILE_ROWS,
                        C::SMEM_BYTES, C::THREADS, reinterpret_cast<const void*>(&kprod_direct_kernel<C>),
                        &launch_direct<C>};
 }
@@ -382,19 +518,20 @@ constexpr int direct_rows(int DP, int EP, bool online_max) {
     return r < 2 ? 2 : r;
 }
 
-#define KMB_DIRECT_ENTRY(DP, EP, KID, NORM)                                                              \
+#define KMB_DIRECT_ENTRY(DP, EP, KID, NORM, FORM)                                                        \
     kmb::make_direct_entry<kmb::DirectCfg<DP, EP,                                                          \
-        kmb::direct_rows(DP, EP, (NORM) && (KID) != KMB_KERNEL_INVERSE_DISTANCE), KID, NORM>>()
-#define KMB_DIRECT_ENTRIES_FOR_DP(DP, KID, NORM) \
-    KMB_DIRECT_ENTRY(DP, 1, KID, NORM), KMB_DIRECT_ENTRY(DP, 2, KID, NORM), KMB_DIRECT_ENTRY(DP, 4, KID, NORM)
-#define KMB_DIRECT_TABLE(NAME, KID, NORM)                                                              \
-    namespace kmb {                                                                                    \
-    extern const DirectEntry NAME[];                                                                   \
-    extern const int NAME##_count;                                                                     \
-    const DirectEntry NAME[] = {KMB_DIRECT_ENTRIES_FOR_DP(2, KID, NORM), KMB_DIRECT_ENTRIES_FOR_DP(3, KID, NORM), \
-                                KMB_DIRECT_ENTRIES_FOR_DP(4, KID, NORM), KMB_DIRECT_ENTRIES_FOR_DP(8, KID, NORM), \
-                                KMB_DIRECT_ENTRIES_FOR_DP(16, KID, NORM)};                               \
-    const int NAME##_count = sizeof(NAME) / sizeof(NAME[0]);                                           \
+        kmb::direct_rows(DP, EP, (NORM) && (KID) != KMB_KERNEL_INVERSE_DISTANCE && (FORM) == 0), KID, NORM, FORM>>()
+#define KMB_DIRECT_ENTRIES_FOR_DP(DP, KID, NORM, FORM)                                  \
+    KMB_DIRECT_ENTRY(DP, 1, KID, NORM, FORM), KMB_DIRECT_ENTRY(DP, 2, KID, NORM, FORM), \
+        KMB_DIRECT_ENTRY(DP, 4, KID, NORM, FORM)
+#define KMB_DIRECT_TABLE(NAME, KID, NORM, FORM)                                                                      \
+    namespace kmb {                                                                                                  \
+    extern const DirectEntry NAME[];                                                                                 \
+    extern const int NAME##_count;                                                                                   \
+    const DirectEntry NAME[] = {KMB_DIRECT_ENTRIES_FOR_DP(2, KID, NORM, FORM), KMB_DIRECT_ENTRIES_FOR_DP(3, KID, NORM, FORM), \
+                                KMB_DIRECT_ENTRIES_FOR_DP(4, KID, NORM, FORM), KMB_DIRECT_ENTRIES_FOR_DP(8, KID, NORM, FORM), \
+                                KMB_DIRECT_ENTRIES_FOR_DP(16, KID, NORM, FORM)};                                       \
+    const int NAME##_count = sizeof(NAME) / sizeof(NAME[0]);                                                         \
     }
 
 }  // namespace kmb

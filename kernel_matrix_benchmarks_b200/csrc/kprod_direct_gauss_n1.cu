@@ -1,3 +1,4 @@
-// Instantiations of kprod_direct_kernel: kernel gauss, normalize_rows=1 (split per file to build in parallel).
+// Instantiations of kprod_direct_kernel: kernel gauss, normalize_rows=1, difference form
+// (split per file to build in parallel).
 #include "kprod_direct.cuh"
-KMB_DIRECT_TABLE(kDirect_gauss_n1, 0, true)
+KMB_DIRECT_TABLE(kDirect_gauss_n1, 0, true, 0)

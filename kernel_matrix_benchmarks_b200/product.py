@@ -80,6 +80,18 @@ def kernel_product(x, y, b, *, kernel="gaussian", normalize_rows=False, density_
     return out
 
 
+def direct_stats(workspace=None, device=None):
+    """What the device-side statistics pass of the last direct-path product decided (synchronises):
+    bounding-box centre, log2(e)*half-diagonal^2 and the evaluation form of the Gaussian kernel."""
+    import struct
+
+    if workspace is None:
+        workspace = _default_ws[torch.device(device) if device is not None else next(iter(_default_ws))]
+    raw = bytes(workspace.buf[:80].cpu().numpy())
+    vals = struct.unpack("16f f i I i", raw)
+    return {"center": vals[:16], "radius2": vals[16], "form": "product" if vals[17] else "difference"}
+
+
 def last_launch_count():
     return int(_lib.load().kmb_last_launch_count())
 

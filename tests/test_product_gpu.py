@@ -63,6 +63,30 @@ def test_golden_vectors(name):
     assert extra["gpu_launches"] >= 1
 
 
+@pytest.mark.parametrize("name", [n for n in PRODUCT_CASES if "gaussian" in n and "d64" not in n and "d784" not in n])
+def test_golden_vectors_difference_form(name):
+    """The Gaussian golden cases again with the product form switched off (path='direct_diff')."""
+    g = load_golden(name)
+    out, extra = run_plugin(g["kernel"], g["source_points"], g["target_points"], g["source_signal"], same_points=g["same_points"],
+                            normalize_rows=g["normalize_rows"], density=g["density_estimation"], path="direct_diff")
+    assert orc.rel_l2(out, g["truth"]) <= TOL_DIRECT
+    assert extra["form"] in ("difference", "n/a")
+
+
+def test_gaussian_form_selection():
+    """Unit-scale data -> product form; spread-out data -> difference form (decided on the device);
+    both within tolerance of the float64 oracle evaluated on the same float32-rounded inputs."""
+    rng = np.random.RandomState(3)
+    for scale, offset, want in [(1.0, 0.0, "product"), (1.0, 1000.0, "product"), (4.0, 0.0, "difference"), (30.0, -7.0, "difference")]:
+        y = (scale * rng.rand(3000, 3) + offset).astype(np.float32).astype(np.float64)
+        x = (scale * rng.rand(1111, 3) + offset).astype(np.float32).astype(np.float64)
+        b = rng.randn(3000, 2)
+        for norm in (False, True):
+            out, extra = run_plugin("gaussian", y, x, b, normalize_rows=norm)
+            assert extra["form"] == want, (scale, offset, extra)
+            assert orc.rel_l2(out, c_oracle.kernel_product("gaussian", y, x, b, normalize_rows=norm)) <= TOL_DIRECT, (scale, offset, norm)
+
+
 @pytest.mark.parametrize("kernel", ["gaussian", "absolute-exponential", "inverse-distance"])
 @pytest.mark.parametrize("N,M", [(1, 1), (7, 513), (255, 1), (2049, 511), (4097, 1537), (300, 40000)])
 def test_ragged_sizes(kernel, N, M):
