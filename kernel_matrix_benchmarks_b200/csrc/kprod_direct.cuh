@@ -56,7 +56,7 @@ struct DirectParams {
 };
 
 // FORM_: 0 = difference form (any kernel), 1 = Gaussian product form
-template <int DP_, int EP_, int R_, int KID_, bool NORM_, int FORM_ = 0, int CONSUMERS_ = 256, int UNROLL_ = 4,
+template <int DP_, int EP_, int R_, int KID_, bool NORM_, int FORM_ = 0, int CONSUMERS_ = 512, int UNROLL_ = 4,
           int MINB_ = 0, int STAGES_ = 4>
 struct DirectCfg {
     static constexpr int DP = DP_, EP = EP_, R = R_, KID = KID_, FORM = FORM_;
@@ -81,7 +81,8 @@ struct DirectCfg {
     // floats of partial state per row when a tile is split across CTAs
     static constexpr int PS = EP + (NORM ? 1 : 0) + (ONLINE_MAX ? 1 : 0);
     // resident CTAs per SM the register allocator is asked to make room for
-    static constexpr int MINB = MINB_ > 0 ? MINB_ : ((!ONLINE_MAX && DP * R <= 32 && EP * R <= 16) ? 2 : 1);
+    // (512 consumer threads + producer warp: 2 CTAs need <= 60 registers per thread)
+    static constexpr int MINB = MINB_ > 0 ? MINB_ : ((!ONLINE_MAX && KID != KMB_KERNEL_INVERSE_DISTANCE && (DP + EP + WCOL) * R <= 16) ? 2 : 1);
     static_assert(R % 2 == 0, "rows are processed as packed pairs");
 };
 
@@ -510,9 +511,11 @@ constexpr DirectEntry make_direct_entry() {
                        &launch_direct<C>};
 }
 
-// rows per thread: keep the register-resident targets (DP*R) and accumulators (EP*R) bounded
+// rows per thread: keep the register-resident targets (DP*R) and accumulators (EP*R) bounded.
+// Tuned on B200 with tools/tune_direct.cu: for D=3, E=1 the best shape is 512 consumer threads x
+// 4 rows, 2 CTAs/SM (34 warps/SM, ~56 registers); larger D trade rows for registers.
 constexpr int direct_rows(int DP, int EP, bool online_max) {
-    int r = DP <= 4 ? 8 : DP <= 8 ? 4 : 2;
+    int r = DP <= 4 ? 4 : DP <= 8 ? 4 : 2;
     if (online_max && r > 4) r = 4;
     if (EP * r > 16) r = 16 / EP;
     return r < 2 ? 2 : r;

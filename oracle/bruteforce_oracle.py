@@ -189,4 +189,8 @@ def rel_l2(result, truth):
     """Relative L2 error used by every parity test (BASELINE.json north_star)."""
     result = np.asarray(result, dtype=np.float64)
     truth = np.asarray(truth, dtype=np.float64)
-    return float(np.linalg.norm(result - truth) / np.linalg.norm(truth))
+    den = np.linalg.norm(truth)
+    num = np.linalg.norm(result - truth)
+    if den == 0:  # an all-zero truth (e.g. the 1 x 1 inverse-distance matrix): exact match or infinite error
+        return 0.0 if num == 0 else float("inf")
+    return float(num / den)
