@@ -178,7 +178,7 @@ def test_config_c2_full_size_sampled_and_properties():
     ones = kernel_product(y, y, torch.ones_like(b1))
     assert torch.equal(dens, ones)
     att = kernel_product(y, y, torch.full_like(b1, 3.25), normalize_rows=True)
-    assert float((att - 3.25).abs().max()) <= 1e-5
+    assert float((att - 3.25).abs().max()) <= 3.25e-5  # 1e-5 relative, worst row of 10^6
 
 
 def test_density_attention_is_ones():
