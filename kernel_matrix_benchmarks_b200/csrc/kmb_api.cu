@@ -6,6 +6,7 @@
 #include <algorithm>
 
 #include "kprod_direct.cuh"
+#include "kprod_tensor.cuh"
 
 namespace kmb {
 
@@ -187,7 +188,7 @@ int kmb_product_workspace_bytes(int64_t N, int64_t M, int D, int E, int kernel_i
         *bytes = pl.total_bytes;
         return KMB_OK;
     }
-    return set_error(KMB_ERR_UNSUPPORTED, "tensor-core path (D=%d) is not built yet", D);
+    return tensor_workspace_bytes(N, M, D, E, kernel_id, flags, bytes);
 }
 
 int kmb_product_f32(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D,
@@ -208,8 +209,18 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
         return KMB_OK;
     }
     const int p = resolve_path(D, path);
-    if (p != KMB_PATH_DIRECT_F32 && p != KMB_PATH_DIRECT_DIFF)
-        return set_error(KMB_ERR_UNSUPPORTED, "tensor-core path (D=%d) is not built yet", D);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256)
+        return set_error(KMB_ERR_INVALID, "workspace must be 256-byte aligned");
+    if (p == KMB_PATH_TENSOR_3XTF32) {
+        if (g_profile && !g_ev0) {
+            KMB_CUDA_CHECK(cudaEventCreate(&g_ev0));
+            KMB_CUDA_CHECK(cudaEventCreate(&g_ev1));
+        }
+        const int rc = tensor_product(x, y, density ? nullptr : b, out, N, M, D, E, kernel_id, flags, row_offset, workspace,
+                                      workspace_bytes, stream, g_profile ? g_ev0 : nullptr, g_profile ? g_ev1 : nullptr);
+        if (rc == KMB_OK && g_profile) g_ev_valid = true;
+        return rc;
+    }
 
     DirectPlan pl;
     if (int rc = plan_direct(N, M, D, E, kernel_id, flags, p, &pl)) return rc;

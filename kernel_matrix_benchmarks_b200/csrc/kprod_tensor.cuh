@@ -1,0 +1,18 @@
+// Tensor-core path (D > 16): squared distances through |x|^2 + |y|^2 - 2 x.y^T with the dot
+// products on tcgen05 (kind::tf32, FP32 accumulators in TMEM), 3xTF32 split for FP32-class accuracy.
+// Replaces kernel_matrix(..., fast_sqdists=True) + K @ b of the reference
+// (/root/reference/kernel_matrix_benchmarks/algorithms/bruteforce.py:36-49, 18-22, 130-153).
+#pragma once
+#include "kmb_common.cuh"
+
+namespace kmb {
+
+int tensor_workspace_bytes(int64_t N, int64_t M, int D, int E, int kid, int flags, size_t* bytes);
+
+// Enqueue the whole tensor-path product on `stream` (prepass + main kernel per signal chunk).
+// ev0/ev1: optional events recorded around the last main kernel.
+int tensor_product(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D, int E,
+                   int kid, int flags, int64_t row_offset, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1);
+
+}  // namespace kmb

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 TOL_DIRECT = 1e-5
 TOL_TENSOR = 1e-4
 PRODUCT_CASES = [n for n in golden_names() if not n.startswith("solver_")]
-TENSOR_PATH_BUILT = False  # flipped when kmb_product_f32 grows KMB_PATH_TENSOR_3XTF32
+TENSOR_PATH_BUILT = True  # flipped when kmb_product_f32 grows KMB_PATH_TENSOR_3XTF32
 
 
 def run_plugin(kernel, y, x, b, *, same_points=False, normalize_rows=False, density=False, path="auto"):
@@ -209,3 +209,72 @@ def test_c_abi_error_paths():
         kernel_product(x.double(), x, b)
     with pytest.raises(NotImplementedError):
         kernel_product(torch.rand(4, 20, device="cuda"), torch.rand(4, 20, device="cuda"), torch.rand(4, 1, device="cuda"), path="direct")
+
+
+# ---------------------------------------------------------------- tensor-core (3xTF32) path
+
+
+@pytest.mark.parametrize("kernel", ["gaussian", "absolute-exponential", "inverse-distance"])
+@pytest.mark.parametrize("N,M,D,E", [(1, 1, 17, 1), (130, 257, 33, 1), (300, 1000, 64, 2), (129, 640, 100, 5), (257, 129, 784, 1)])
+def test_tensor_path_shapes(kernel, N, M, D, E):
+    rng = np.random.RandomState(N + M + D)
+    r = (3.0 / D) ** 0.5
+    y, x, b = r * rng.rand(M, D), r * rng.rand(N, D), rng.randn(M, E)
+    for norm in (False, True):
+        out, extra = run_plugin(kernel, y, x, b, normalize_rows=norm)
+        want = c_oracle.kernel_product(kernel, y, x, b, normalize_rows=norm)
+        err = orc.rel_l2(out, want)
+        assert err <= TOL_TENSOR, (kernel, norm, err)
+
+
+def test_tensor_path_agrees_with_direct_path_on_small_d():
+    """Same D = 8 problem through both paths: FP32 FMA distances vs tcgen05 3xTF32 distances."""
+    rng = np.random.RandomState(8)
+    y, x, b = 0.6 * rng.rand(5000, 8), 0.6 * rng.rand(700, 8), rng.randn(5000, 2)
+    want = c_oracle.kernel_product("gaussian", y, x, b)
+    direct, _ = run_plugin("gaussian", y, x, b, path="direct")
+    tensor, _ = run_plugin("gaussian", y, x, b, path="tensor")
+    assert orc.rel_l2(direct, want) <= TOL_DIRECT
+    assert orc.rel_l2(tensor, want) <= TOL_TENSOR
+    assert orc.rel_l2(tensor, direct) <= TOL_TENSOR
+
+
+def test_tensor_path_uncentred_data():
+    """Offset data (all coordinates near 50): the prepass centres on the source mean, so the
+    cancellation in |x|^2 + |y|^2 - 2x.y stays at the scale of the spread, not of the offset."""
+    rng = np.random.RandomState(9)
+    y = (50.0 + 0.2 * rng.rand(2000, 64)).astype(np.float32).astype(np.float64)
+    x = (50.0 + 0.2 * rng.rand(300, 64)).astype(np.float32).astype(np.float64)
+    b = rng.randn(2000, 1)
+    out, _ = run_plugin("gaussian", y, x, b)
+    assert orc.rel_l2(out, c_oracle.kernel_product("gaussian", y, x, b)) <= TOL_TENSOR
+
+
+def test_config_c3_sampled():
+    """BASELINE config 3 at full size (M = 60k sources, N = 10k targets, D = 784, E = 1):
+    every 40th target row against the float64 oracle."""
+    from kernel_matrix_benchmarks_b200 import datasets
+
+    ds = datasets.config_c3()
+    out, extra = run_plugin("gaussian", ds.source_points, ds.target_points, ds.source_signal)
+    rows = np.arange(0, ds.N, 40)
+    want = c_oracle.kernel_product("gaussian", ds.source_points, ds.target_points, ds.source_signal, rows=rows)
+    err = orc.rel_l2(out[rows], want)
+    print(f"C3 sampled rel-L2 {err:.2e} {extra}")
+    assert err <= TOL_TENSOR
+
+
+def test_config_c4_reduced():
+    """BASELINE config 4 (row-normalised exponential kernel, D = 64, E = 64) at N = M = 16k:
+    sampled rows against the oracle; a constant signal must come back unchanged."""
+    from kernel_matrix_benchmarks_b200 import datasets
+
+    ds = datasets.config_c4(n=16384)
+    out, extra = run_plugin(ds.kernel, ds.source_points, ds.target_points, ds.source_signal, normalize_rows=True)
+    rows = np.arange(0, ds.N, 64)
+    want = c_oracle.kernel_product(ds.kernel, ds.source_points, ds.target_points, ds.source_signal, normalize_rows=True, rows=rows)
+    err = orc.rel_l2(out[rows], want)
+    print(f"C4 (16k) sampled rel-L2 {err:.2e} {extra}")
+    assert err <= TOL_TENSOR
+    const, _ = run_plugin(ds.kernel, ds.source_points, ds.target_points, np.full((ds.M, 1), -2.5), normalize_rows=True)
+    assert np.abs(const + 2.5).max() <= 2.5e-5
