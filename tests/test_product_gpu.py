@@ -223,6 +223,9 @@ def test_tensor_path_shapes(kernel, N, M, D, E):
     for norm in (False, True):
         out, extra = run_plugin(kernel, y, x, b, normalize_rows=norm)
         want = c_oracle.kernel_product(kernel, y, x, b, normalize_rows=norm)
+        if np.isnan(want).any():  # 0/0 rows (e.g. the 1 x 1 inverse-distance matrix): the reference returns NaN too
+            assert np.array_equal(np.isnan(out), np.isnan(want))
+            continue
         err = orc.rel_l2(out, want)
         assert err <= TOL_TENSOR, (kernel, norm, err)
 
