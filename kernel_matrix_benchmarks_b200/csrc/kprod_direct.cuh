@@ -234,8 +234,10 @@ kprod_direct_kernel(const DirectParams P) {
                             kv = make_float2(kernel_value<KID>(s.x), kernel_value<KID>(s.y));
                         }
                         if constexpr (KID == KMB_KERNEL_INVERSE_DISTANCE) {
-                            if (j_base + j == jz[2 * p]) kv.x = 0.f;
-                            if (j_base + j == jz[2 * p + 1]) kv.y = 0.f;
+                            // the reference's zeroing rule; padding records add exactly 0 (a 0/0 row stays NaN)
+                            const bool pad = j_base + j >= P.M;
+                            if (pad || j_base + j == jz[2 * p]) kv.x = 0.f;
+                            if (pad || j_base + j == jz[2 * p + 1]) kv.y = 0.f;
                         }
 #pragma unroll
                         for (int e = 0; e < EP; ++e) acc[e][p] = fma2(kv, pr[DP + e], acc[e][p]);

@@ -265,7 +265,7 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
                             const int jj = ch * 32 + c;
                             float kv = kernel_from_parts<KID>(s[c], un, ax[jj]);
                             if constexpr (KID == KMB_KERNEL_INVERSE_DISTANCE)
-                                if (j0 + jj == jz) kv = 0.f;
+                                if (j0 + jj == jz || j0 + jj >= P.M) kv = 0.f;  // zeroing rule; padding adds exactly 0
 #pragma unroll
                             for (int e = 0; e < EP; ++e) acc[e] = fmaf(kv, ax[TN + jj * EP + e], acc[e]);
                             if constexpr (NORM) ksum += kv;

@@ -181,6 +181,14 @@ def test_config_c2_full_size_sampled_and_properties():
     assert float((att - 3.25).abs().max()) <= 3.25e-5  # 1e-5 relative, worst row of 10^6
 
 
+def test_degenerate_attention_rows_are_nan_like_the_reference():
+    """1 x 1 inverse-distance attention is 0/0: the reference returns NaN (bruteforce.py:145), so do we."""
+    one = np.array([[0.3, 0.2, 0.1]])
+    out, _ = run_plugin("inverse-distance", one, one, np.array([[2.0]]), same_points=True, normalize_rows=True)
+    want = orc.kernel_product("inverse-distance", one, None, np.array([[2.0]]), normalize_rows=True)
+    assert np.isnan(want).all() and np.isnan(out).all()
+
+
 def test_density_attention_is_ones():
     g = load_golden("density_attention_gaussian_cube_d3")
     out, _ = run_plugin("gaussian", g["source_points"], None, g["source_signal"], same_points=True, normalize_rows=True, density=True)
