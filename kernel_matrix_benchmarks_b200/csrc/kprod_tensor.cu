@@ -12,20 +12,16 @@
 //                           the row-normalised variant
 //   work      stream-K over (128-row tile x 128-source block) units, as in the direct kernel: equal
 //             contiguous unit ranges per CTA, split tiles combined in CTA order by the last CTA to arrive.
-#include <cuda.h>
-
 #include <algorithm>
 
 #include "kprod_tensor.cuh"
+#include "tensor_common.cuh"
 
 namespace kmb {
 
 namespace tc {
 
-constexpr int TM = 128;            // target rows per tile  (UMMA M, one TMEM lane per row)
 constexpr int TN = 128;            // sources per tile      (UMMA N, one TMEM column per source)
-constexpr int TK = 32;             // floats per K block = one 128-byte swizzle atom
-constexpr int UMMA_K = 8;          // TF32: 32 bytes per instruction
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = TM * TK * 4;        // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A hi, A lo, B hi, B lo
@@ -46,78 +42,6 @@ struct Params {
     int E, e0;
     int n_tiles, nsb, kblocks;
 };
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread = lane = row)
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&r)[32]) {
-    uint32_t* u = reinterpret_cast<uint32_t*>(r);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
-          "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
-          "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 version 1): rows are 128 bytes,
-// 8-row atoms are 1024 bytes apart; the tile base is 1024-byte aligned.
-__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_tile, int byte_offset) {
-    const uint32_t addr = smem_u32(smem_tile) + byte_offset;
-    return static_cast<uint64_t>((addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(TN >> 3) << 17) |
-                                (static_cast<uint32_t>(TM >> 4) << 24);
-
-template <int KID>
-__device__ __forceinline__ float kernel_from_parts(float s, float un, float vn) {
-    // s = 2 u.v (log2-scaled data), so -(|u|^2 + |v|^2 - s) is the log2 of the Gaussian
-    if constexpr (KID == KMB_KERNEL_GAUSSIAN) return ex2_approx((s - vn) - un);
-    else {
-        const float d2 = fmaxf((un + vn) - s, 0.f);  // bruteforce.py:21 / :10: maximum(sqdists, 0)
-        if constexpr (KID == KMB_KERNEL_ABSOLUTE_EXPONENTIAL) return ex2_approx(-sqrt_approx(d2));
-        else return rsqrt_approx(d2);
-    }
-}
-template <int KID>
-__device__ __forceinline__ float log2_kernel_from_parts(float s, float un, float vn) {
-    if constexpr (KID == KMB_KERNEL_GAUSSIAN) return (s - vn) - un;
-    else return -sqrt_approx(fmaxf((un + vn) - s, 0.f));
-}
 
 template <int EP, int KID, bool NORM>
 struct Cfg {
@@ -202,9 +126,9 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
                         const uint64_t bh = umma_desc_sw128(st + 2 * TILE_BYTES, k * UMMA_K * 4);
                         const uint64_t bl = umma_desc_sw128(st + 3 * TILE_BYTES, k * UMMA_K * 4);
                         // 3xTF32: the two small cross terms first, then hi.hi
-                        umma_tf32(d_tmem, al, bh, kIdescTf32, (kb | k) != 0);
-                        umma_tf32(d_tmem, ah, bl, kIdescTf32, 1);
-                        umma_tf32(d_tmem, ah, bh, kIdescTf32, 1);
+                        umma_tf32(d_tmem, al, bh, idesc_tf32(TN), (kb | k) != 0);
+                        umma_tf32(d_tmem, ah, bl, idesc_tf32(TN), 1);
+                        umma_tf32(d_tmem, ah, bh, idesc_tf32(TN), 1);
                     }
                     umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
                 }
@@ -373,7 +297,6 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
 }
 
 // ---- prepass ---------------------------------------------------------------------------------------
-constexpr int CENTER_BLOCKS = 128;
 
 // partial[blk][col] = sum over this block's rows of y[row][col]
 static __global__ void __launch_bounds__(256) column_sum_kernel(const float* __restrict__ y, long long M, int D,
@@ -402,11 +325,6 @@ static __global__ void column_mean_kernel(const float* __restrict__ partial, int
     center[col] = col < D ? t / static_cast<float>(M) : 0.f;
 }
 
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
 // One warp per point: w = mult * s * (p - c); hi = tf32(w), lo = tf32(w - hi); norm2 = |s (p - c)|^2.
 static __global__ void __launch_bounds__(256) split_points_kernel(const float* __restrict__ pts, long long n, int D, int Dp,
                                                                   const float* __restrict__ center, float scale, float mult,
@@ -430,35 +348,22 @@ static __global__ void __launch_bounds__(256) split_points_kernel(const float* _
     if (lane == 0) norm2[row] = acc;
 }
 
-}  // namespace tc
-
-// ---- host side ---------------------------------------------------------------------------------------
-namespace {
-
-using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int get_encode(EncodeFn* fn) {
-    static EncodeFn cached = nullptr;
-    if (!cached) {
+// (rows, cols) fp32 row-major; box = 32 floats x box_rows rows, 128-byte swizzle, out-of-bounds reads as zero
+int make_tensor_map(CUtensorMap* map, const float* base, long long rows, int cols, int box_rows) {
+    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn enc = nullptr;
+    if (!enc) {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         KMB_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
         if (!p || q != cudaDriverEntryPointSuccess) return set_error(KMB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-        cached = reinterpret_cast<EncodeFn>(p);
+        enc = reinterpret_cast<EncodeFn>(p);
     }
-    *fn = cached;
-    return KMB_OK;
-}
-
-// (rows, Dp) fp32 row-major; box = 32 floats x 128 rows, 128-byte swizzle, out-of-bounds rows read as zero
-int make_map(CUtensorMap* map, const float* base, long long rows, int Dp) {
-    EncodeFn enc = nullptr;
-    if (int rc = get_encode(&enc)) return rc;
-    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(Dp), static_cast<cuuint64_t>(rows)};
-    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(Dp) * 4};
-    const cuuint32_t box[2] = {tc::TK, tc::TM};
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 4};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(TK), static_cast<cuuint32_t>(box_rows)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -466,6 +371,29 @@ int make_map(CUtensorMap* map, const float* base, long long rows, int Dp) {
     if (r != CUDA_SUCCESS) return set_error(KMB_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", static_cast<int>(r));
     return KMB_OK;
 }
+
+int tensor_prepass(const float* x, const float* y, int64_t N, int64_t M, int D, int Dp, int kid, float* center, float* cpart,
+                   float* uh, float* ul, float* vh, float* vl, float* un, float* vn, cudaStream_t stream) {
+    // scale folds log2(e) into the data as in the direct path; the A operand carries the factor 2 of 2 u.v
+    const float scale = kid == KMB_KERNEL_GAUSSIAN ? 1.2011224087864498f : kid == KMB_KERNEL_ABSOLUTE_EXPONENTIAL ? 1.4426950408889634f : 1.f;
+    const int cblocks = static_cast<int>(std::min<long long>(CENTER_BLOCKS, (M + 7) / 8));
+    dim3 g(cblocks, (D + 31) / 32);
+    column_sum_kernel<<<g, 256, 0, stream>>>(y, M, D, cpart);
+    KMB_CUDA_CHECK(cudaGetLastError());
+    column_mean_kernel<<<(Dp + 127) / 128, 128, 0, stream>>>(cpart, cblocks, M, D, Dp, center);
+    KMB_CUDA_CHECK(cudaGetLastError());
+    split_points_kernel<<<static_cast<unsigned>((N * 32 + 255) / 256), 256, 0, stream>>>(x, N, D, Dp, center, scale, 2.f, uh, ul, un);
+    KMB_CUDA_CHECK(cudaGetLastError());
+    split_points_kernel<<<static_cast<unsigned>((M * 32 + 255) / 256), 256, 0, stream>>>(y, M, D, Dp, center, scale, 1.f, vh, vl, vn);
+    KMB_CUDA_CHECK(cudaGetLastError());
+    count_launch(4);
+    return KMB_OK;
+}
+
+}  // namespace tc
+
+// ---- host side ---------------------------------------------------------------------------------------
+namespace {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -541,6 +469,7 @@ int launch_any(int kid, bool norm, int ep, const CUtensorMap* maps, const tc::Pa
 
 int tensor_workspace_bytes(int64_t N, int64_t M, int D, int E, int kid, int flags, size_t* bytes) {
     (void)kid;
+    if (tensor_pv_applicable(D, E)) return tensor_pv_workspace_bytes(N, M, D, E, bytes);
     TensorPlan pl{};
     if (int rc = plan_tensor(N, M, D, E, flags, &pl)) return rc;
     *bytes = pl.total;
@@ -571,27 +500,12 @@ int tensor_product(const float* x, const float* y, const float* b, float* out, i
     const bool density = flags & KMB_FLAG_DENSITY;
 
     KMB_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(int) * pl.n_tiles, stream));
-    // centre = column means of the sources; scale folds log2(e) into the data as in the direct path
-    const float scale = kid == KMB_KERNEL_GAUSSIAN ? 1.2011224087864498f : kid == KMB_KERNEL_ABSOLUTE_EXPONENTIAL ? 1.4426950408889634f : 1.f;
-    {
-        const int cblocks = static_cast<int>(std::min<long long>(tc::CENTER_BLOCKS, (M + 7) / 8));
-        dim3 g(cblocks, (D + 31) / 32);
-        tc::column_sum_kernel<<<g, 256, 0, stream>>>(y, M, D, cpart);
-        KMB_CUDA_CHECK(cudaGetLastError());
-        tc::column_mean_kernel<<<(pl.Dp + 127) / 128, 128, 0, stream>>>(cpart, cblocks, M, D, pl.Dp, center);
-        KMB_CUDA_CHECK(cudaGetLastError());
-        // A operand carries the factor 2 of 2 u.v
-        tc::split_points_kernel<<<static_cast<unsigned>((N * 32 + 255) / 256), 256, 0, stream>>>(x, N, D, pl.Dp, center, scale, 2.f, uh, ul, un);
-        KMB_CUDA_CHECK(cudaGetLastError());
-        tc::split_points_kernel<<<static_cast<unsigned>((M * 32 + 255) / 256), 256, 0, stream>>>(y, M, D, pl.Dp, center, scale, 1.f, vh, vl, vn);
-        KMB_CUDA_CHECK(cudaGetLastError());
-        count_launch(4);
-    }
+    if (int rc = tc::tensor_prepass(x, y, N, M, D, pl.Dp, kid, center, cpart, uh, ul, vh, vl, un, vn, stream)) return rc;
     CUtensorMap maps[4];
-    if (int rc = make_map(&maps[0], uh, N, pl.Dp)) return rc;
-    if (int rc = make_map(&maps[1], ul, N, pl.Dp)) return rc;
-    if (int rc = make_map(&maps[2], vh, M, pl.Dp)) return rc;
-    if (int rc = make_map(&maps[3], vl, M, pl.Dp)) return rc;
+    if (int rc = tc::make_tensor_map(&maps[0], uh, N, pl.Dp, tc::TM)) return rc;
+    if (int rc = tc::make_tensor_map(&maps[1], ul, N, pl.Dp, tc::TM)) return rc;
+    if (int rc = tc::make_tensor_map(&maps[2], vh, M, pl.Dp, tc::TN)) return rc;
+    if (int rc = tc::make_tensor_map(&maps[3], vl, M, pl.Dp, tc::TN)) return rc;
 
     const long long units = pl.n_tiles * pl.nsb;
     const int grid = static_cast<int>(std::min<long long>(pl.grid_max, units));
