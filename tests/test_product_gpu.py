@@ -289,3 +289,38 @@ def test_config_c4_reduced():
     assert err <= TOL_TENSOR
     const, _ = run_plugin(ds.kernel, ds.source_points, ds.target_points, np.full((ds.M, 1), -2.5), normalize_rows=True)
     assert np.abs(const + 2.5).max() <= 2.5e-5
+
+
+# ------------------------------------------- tensor path with the second contraction on tcgen05 (E > 4)
+
+
+@pytest.mark.parametrize("kernel", ["gaussian", "absolute-exponential", "inverse-distance"])
+@pytest.mark.parametrize("norm", [False, True])
+@pytest.mark.parametrize("N,M,D,E", [(100, 20000, 64, 64), (300, 1000, 32, 5), (129, 641, 100, 33), (1000, 130, 128, 70)])
+def test_tensor_pv_shapes(kernel, norm, N, M, D, E):
+    """P.B on the tensor cores: one row tile split over many CTAs (stream-K combine), ragged sizes,
+    E not a multiple of 32, two passes over the signal (E > 64)."""
+    rng = np.random.RandomState(N + M + D + E)
+    r = (3.0 / D) ** 0.5
+    y, x, b = r * rng.rand(M, D), r * rng.rand(N, D), rng.randn(M, E)
+    out, _ = run_plugin(kernel, y, x, b, normalize_rows=norm)
+    want = c_oracle.kernel_product(kernel, y, x, b, normalize_rows=norm)
+    assert out.shape == want.shape
+    assert orc.rel_l2(out, want) <= TOL_TENSOR
+
+
+@pytest.mark.parametrize("kernel", ["gaussian", "absolute-exponential"])
+def test_tensor_pv_lazy_rescale(kernel):
+    """Sources ordered far -> near: the running reference exponent must be rescaled (growth > 2^64)
+    and rows that only ever see far sources must still normalise (FP32 exp would underflow)."""
+    rng = np.random.RandomState(4)
+    D, E = 64, 16
+    far = 12.0 if kernel == "gaussian" else 150.0
+    near = 0.2 * rng.rand(500, D)
+    y = np.concatenate((near + far / np.sqrt(D) * 3, near + far / np.sqrt(D), near), axis=0)  # far, closer, near
+    x = np.concatenate((0.2 * rng.rand(200, D), 0.2 * rng.rand(56, D) - far / np.sqrt(D)), axis=0)
+    b = rng.randn(y.shape[0], E)
+    out, _ = run_plugin(kernel, y, x, b, normalize_rows=True)
+    want = orc.kernel_product(kernel, y, x, b, normalize_rows=True)
+    assert np.isfinite(out).all()
+    assert orc.rel_l2(out, want) <= 3e-4  # exponents of ~1e3: FP32 resolution of the exponent itself
