@@ -479,6 +479,8 @@ int tensor_workspace_bytes(int64_t N, int64_t M, int D, int E, int kid, int flag
 int tensor_product(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D, int E,
                    int kid, int flags, int64_t row_offset, void* workspace, size_t workspace_bytes, cudaStream_t stream,
                    cudaEvent_t ev0, cudaEvent_t ev1) {
+    if (tensor_pv_applicable(D, E))
+        return tensor_pv_product(x, y, b, out, N, M, D, E, kid, flags, row_offset, workspace, workspace_bytes, stream, ev0, ev1);
     TensorPlan pl{};
     if (int rc = plan_tensor(N, M, D, E, flags, &pl)) return rc;
     if (!workspace || workspace_bytes < pl.total)

@@ -315,7 +315,7 @@ def test_tensor_pv_lazy_rescale(kernel):
     and rows that only ever see far sources must still normalise (FP32 exp would underflow)."""
     rng = np.random.RandomState(4)
     D, E = 64, 16
-    far = 12.0 if kernel == "gaussian" else 150.0
+    far = 4.0 if kernel == "gaussian" else 60.0
     near = 0.2 * rng.rand(500, D)
     y = np.concatenate((near + far / np.sqrt(D) * 3, near + far / np.sqrt(D), near), axis=0)  # far, closer, near
     x = np.concatenate((0.2 * rng.rand(200, D), 0.2 * rng.rand(56, D) - far / np.sqrt(D)), axis=0)
