@@ -56,9 +56,14 @@ struct DirectParams {
 };
 
 // FORM_: 0 = difference form (any kernel), 1 = Gaussian product form
+// POLY_: product form only -- every POLY_-th exponential of a thread (0 = none) is evaluated on the
+//        FMA pipe (Cody-Waite + degree-5 polynomial, packed FP32) instead of MUFU.EX2, which moves the
+//        kernel past the 16 exp/clk/SM of the MUFU pipe
 template <int DP_, int EP_, int R_, int KID_, bool NORM_, int FORM_ = 0, int CONSUMERS_ = 512, int UNROLL_ = 4,
-          int MINB_ = 0, int STAGES_ = 4>
+          int MINB_ = 0, int STAGES_ = 4, int POLY_ = 0>
 struct DirectCfg {
+    static constexpr int POLY = POLY_;
+    static_assert(POLY_ == 0 || FORM_ == 1, "the polynomial exp2 needs the bounded exponents of the product form");
     static constexpr int DP = DP_, EP = EP_, R = R_, KID = KID_, FORM = FORM_;
     static constexpr bool NORM = NORM_;
     static_assert(FORM == 0 || KID == KMB_KERNEL_GAUSSIAN, "product form is Gaussian-only");
@@ -89,6 +94,24 @@ struct DirectCfg {
 // owner CTA of unit u when U units are cut into G ranges [U*c/G, U*(c+1)/G)
 __device__ __forceinline__ int unit_owner(long long u, long long U, int G) {
     return static_cast<int>(((u + 1) * G - 1) / U);
+}
+
+// 2^s for two packed exponents, |s| < 2^22, entirely on the FMA/ALU pipes: round-to-nearest split
+// s = n + r (magic-number add), degree-5 minimax polynomial of 2^r on [-0.5, 0.5] (max relative
+// error 7.5e-8 before rounding, 2.3e-7 in FP32 Horner form -- the same class as MUFU.EX2's 2 ulp),
+// then n is added straight into the exponent field.
+__device__ __forceinline__ float2 ex2_poly2(float2 s) {
+    const float2 magic = make_float2(12582912.f, 12582912.f);   // 1.5 * 2^23
+    const float2 t = add2(s, magic);                            // low mantissa bits = round(s)
+    const float2 n = add2(t, make_float2(-12582912.f, -12582912.f));
+    const float2 r = add2(s, make_float2(-n.x, -n.y));
+    float2 q = fma2(r, make_float2(1.327647129e-03f, 1.327647129e-03f), make_float2(9.675540961e-03f, 9.675540961e-03f));
+    q = fma2(q, r, make_float2(5.550713092e-02f, 5.550713092e-02f));
+    q = fma2(q, r, make_float2(2.402212024e-01f, 2.402212024e-01f));
+    q = fma2(q, r, make_float2(6.931469440e-01f, 6.931469440e-01f));
+    q = fma2(q, r, make_float2(1.000000119e+00f, 1.000000119e+00f));
+    return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+                       __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
 }
 
 template <int KID>
@@ -224,7 +247,12 @@ kprod_direct_kernel(const DirectParams P) {
                             // 2 u.v, then k' = 2^(2 u.v); 2^(-|v|^2) rides in the signal, 2^(-|u|^2) in the store
 #pragma unroll
                             for (int d = 0; d < DP; ++d) s = (d == 0) ? mul2(xr[d][p], pr[d]) : fma2(xr[d][p], pr[d], s);
-                            kv = make_float2(ex2_approx(s.x), ex2_approx(s.y));
+                            // a fixed share of the exponentials goes to the FMA pipe (see DirectCfg::POLY)
+                            constexpr int kPairsPerStep = RP * C::UNROLL;
+                            const bool poly = C::POLY > 0 && kPairsPerStep % C::POLY == 0 &&
+                                              ((j % C::UNROLL) * RP + p) % C::POLY == C::POLY - 1;
+                            if (poly) kv = ex2_poly2(s);
+                            else kv = make_float2(ex2_approx(s.x), ex2_approx(s.y));
                         } else {
 #pragma unroll
                             for (int d = 0; d < DP; ++d) {

@@ -69,25 +69,23 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(b, hb.data(), M * 4, cudaMemcpyHostToDevice));
     printf("N=M=%lld on %s (%d SMs)\n", N, p.name, p.multiProcessorCount);
     const int sms = p.multiProcessorCount;
-    //   DP EP R KID NORM FORM CONS UNR MINB STAGES
+    //   DP EP R KID NORM FORM CONS UNR MINB STAGES POLY
 #define RUN(...) run<DirectCfg<__VA_ARGS__>>(#__VA_ARGS__, N, M, y, y, b, out, sms)
-    RUN(3, 1, 8, 0, false, 0, 256, 4, 2, 4);
-    RUN(3, 1, 8, 0, false, 0, 256, 2, 2, 4);
-    RUN(3, 1, 8, 0, false, 1, 256, 2, 2, 4);
-    RUN(3, 1, 8, 0, false, 1, 256, 4, 2, 4);
-    RUN(3, 1, 8, 0, false, 1, 256, 8, 2, 4);
-    RUN(3, 1, 8, 0, false, 1, 256, 4, 1, 4);
-    RUN(3, 1, 8, 0, false, 1, 256, 2, 3, 3);
-    RUN(3, 1, 8, 0, false, 1, 128, 4, 4, 3);
-    RUN(3, 1, 4, 0, false, 1, 256, 4, 3, 3);
-    RUN(3, 1, 4, 0, false, 1, 256, 4, 4, 2);
-    RUN(3, 1, 6, 0, false, 1, 256, 4, 3, 3);
-    RUN(3, 1, 12, 0, false, 1, 256, 2, 2, 4);
-    RUN(3, 1, 16, 0, false, 1, 256, 2, 1, 4);
-    RUN(3, 1, 16, 0, false, 1, 128, 2, 2, 4);
-    RUN(3, 1, 16, 0, false, 1, 128, 4, 3, 3);
-    RUN(3, 1, 12, 0, false, 1, 128, 4, 4, 3);
-    RUN(3, 1, 8, 0, false, 1, 512, 4, 1, 4);
-    RUN(3, 1, 4, 0, false, 1, 512, 4, 2, 4);
+    RUN(3, 1, 4, 0, false, 1, 512, 4, 2, 4, 0);
+    RUN(3, 1, 4, 0, false, 1, 512, 4, 2, 4, 8);
+    RUN(3, 1, 4, 0, false, 1, 512, 4, 2, 4, 4);
+    RUN(3, 1, 4, 0, false, 1, 512, 2, 2, 4, 4);
+    RUN(3, 1, 4, 0, false, 1, 512, 4, 2, 4, 2);
+    RUN(3, 1, 4, 0, false, 1, 512, 4, 1, 4, 4);
+    RUN(3, 1, 8, 0, false, 1, 512, 4, 1, 4, 4);
+    RUN(3, 1, 8, 0, false, 1, 512, 2, 1, 4, 4);
+    RUN(3, 1, 8, 0, false, 1, 512, 2, 1, 4, 8);
+    RUN(3, 1, 8, 0, false, 1, 256, 4, 2, 4, 4);
+    RUN(3, 1, 6, 0, false, 1, 512, 4, 1, 4, 4);
+    RUN(3, 1, 6, 0, false, 1, 512, 4, 1, 4, 3);
+    RUN(3, 1, 4, 0, false, 1, 768, 4, 1, 4, 4);
+    RUN(3, 1, 4, 0, false, 1, 992, 4, 1, 4, 4);
+    RUN(3, 1, 4, 0, false, 1, 512, 8, 2, 4, 4);
+    RUN(3, 1, 4, 0, false, 1, 512, 8, 2, 4, 16);
     return 0;
 }
