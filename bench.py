@@ -316,7 +316,7 @@ def run_b200_arm(args):
             "unit": UNIT,
             "frac": achieved / peak,
             "traffic": None,
-            "kernel": "kprod_direct_kernel<D=3,E=1,R=8,gaussian>",
+            "kernel": "kprod_direct_kernel<D=3,E=1,R=4,gaussian,product form,512 thr>",
             "kernel_ms": main_ms,
             "peak_basis": f"16 pairs/clk/SM x {info['sm_count']} SMs x {sm_max:.0f} MHz (clocks.max.sm); "
                           f"MEASURED_PEAKS.json {peaks_src}: hbm {peaks.get('hbm_gbs')} GB/s not binding "

@@ -578,9 +578,12 @@ constexpr int direct_rows(int DP, int EP, bool online_max) {
     return r < 2 ? 2 : r;
 }
 
+// product form: unroll 8 sources and send every 16th exponential to the FMA pipe (tools/tune_direct.cu:
+// 14.71 -> 15.08 pairs/clk/SM; larger shares co-saturate the FMA and MUFU pipes and lose throughput)
 #define KMB_DIRECT_ENTRY(DP, EP, KID, NORM, FORM)                                                        \
     kmb::make_direct_entry<kmb::DirectCfg<DP, EP,                                                          \
-        kmb::direct_rows(DP, EP, (NORM) && (KID) != KMB_KERNEL_INVERSE_DISTANCE && (FORM) == 0), KID, NORM, FORM>>()
+        kmb::direct_rows(DP, EP, (NORM) && (KID) != KMB_KERNEL_INVERSE_DISTANCE && (FORM) == 0), KID, NORM, FORM, \
+        512, ((FORM) == 1 ? 8 : 4), 0, 4, ((FORM) == 1 ? 16 : 0)>>()
 #define KMB_DIRECT_ENTRIES_FOR_DP(DP, KID, NORM, FORM)                                  \
     KMB_DIRECT_ENTRY(DP, 1, KID, NORM, FORM), KMB_DIRECT_ENTRY(DP, 2, KID, NORM, FORM), \
         KMB_DIRECT_ENTRY(DP, 4, KID, NORM, FORM)
