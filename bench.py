@@ -72,6 +72,19 @@ def read_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def measured_traffic(n, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the main kernel from the committed ncu capture
+    (profiles/r1_traffic_main_kernel.json); only valid for the workload it was captured on."""
+    try:
+        with open(os.path.join(REPO, "profiles", "r1_traffic_main_kernel.json")) as f:
+            t = json.load(f)
+        if t["N"] == n and world == 1:
+            return t["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------ CPU arm
 
 
@@ -315,7 +328,7 @@ def run_b200_arm(args):
             "peak": peak,
             "unit": UNIT,
             "frac": achieved / peak,
-            "traffic": None,
+            "traffic": measured_traffic(args.n, world),
             "kernel": "kprod_direct_kernel<D=3,E=1,R=4,gaussian,product form,512 thr>",
             "kernel_ms": main_ms,
             "peak_basis": f"16 pairs/clk/SM x {info['sm_count']} SMs x {sm_max:.0f} MHz (clocks.max.sm); "

@@ -179,9 +179,13 @@ class B200Solver(BaseSolver):
             raise RuntimeError("B200Solver needs a CUDA device; there is no CPU fallback.")
         self.lam, self.rtol, self.max_iter, self.path = float(lam), float(rtol), int(max_iter), path
         self.device = torch.device("cuda", int(device))
-        self.name = f"B200Solver({np.dtype(precision).name}, lam={lam:g}, rtol={rtol:g})"
+        self.precision_name = np.dtype(precision).name
+        self._set_name()
         self.info = None
         self.res = None
+
+    def _set_name(self):
+        self.name = f"B200Solver({self.precision_name}, lam={self.lam:g}, rtol={self.rtol:g})"
 
     def set_query_arguments(self, **kwargs):
         """``query-args`` of algos.yaml (runner.py:123): rtol / max_iter / lam can be swept without refitting."""
@@ -190,6 +194,7 @@ class B200Solver(BaseSolver):
                 setattr(self, k, float(kwargs[k]))
         if "max_iter" in kwargs:
             self.max_iter = int(kwargs["max_iter"])
+        self._set_name()  # the name labels the result (runner.py:155)
 
     def prepare_data(self, *, source_points):
         self.source_points = _to_device(source_points, self.device)

@@ -1,0 +1,59 @@
+"""The B200 plugin driven by the reference's own runner.run / results / metrics on a B200
+(the drop-in claim of BASELINE.json's north star).  Needs the staged reference tree
+(baseline/_ref, written by ``__graft_entry__.build()`` where /root/reference exists); skips otherwise."""
+import os
+
+import numpy as np
+import pytest
+
+from kernel_matrix_benchmarks_b200.harness import bootstrap
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(bootstrap.find_reference() is None, reason="reference harness not staged")]
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(dataset, task, dim, hardware="GPU", normalize_rows=False, kernel="gaussian"):
+    bootstrap.activate()
+    from kernel_matrix_benchmarks.datasets import get_dataset
+    from kernel_matrix_benchmarks.definitions import get_definitions
+    from kernel_matrix_benchmarks.plotting.utils import compute_all_metrics
+    from kernel_matrix_benchmarks.results import load_all_results
+    from kernel_matrix_benchmarks.runner import run
+
+    defs = get_definitions(definition_file=os.path.join(REPO, "algos.yaml"), dimension=dim, dataset=dataset, task=task,
+                           hardware=hardware, kernel=kernel, normalize_rows=normalize_rows)
+    assert defs
+    for d in defs:
+        run(definition=d, dataset=dataset, runs=2)
+    ds, _ = get_dataset(dataset)
+    rows = []
+    for props, f in load_all_results(dataset):
+        m = compute_all_metrics(dataset=ds, run=f, properties=props)["metrics"]
+        result, error = f["result"][:], f["error"][:]
+        m["rel-l2"] = float(np.linalg.norm(error) / np.linalg.norm(result - error))
+        m["props"] = props
+        rows.append(m)
+    ds.close()
+    return rows
+
+
+def test_product_through_runner(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    rows = _run("product-ucube-D3-E1-M1000-N1000-gaussian", "product", 3)
+    assert len(rows) == 2  # path=auto and path=direct_diff
+    for m in rows:
+        assert m["rel-l2"] <= 1e-5, m  # BASELINE.json: FP32 direct path
+        assert m["props"]["algo"] == "b200-product" and m["props"]["gpu_launches"] > 0
+        assert m["query-time"] > 0 and m["build-time"] >= 0
+
+
+def test_solver_through_runner(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    rows = _run("solver-ucubelam1-D3-E1-M2000-N2000-gaussian", "solver", 3)
+    assert len(rows) == 2  # two query-arg groups (rtol 1e-4, 1e-6)
+    best = min(m["rel-l2"] for m in rows)
+    assert best <= 1e-4, rows
+    assert all(m["props"]["cg_converged"] for m in rows)
+    assert len({m["props"]["name"] for m in rows}) == 2  # the name carries the swept rtol
