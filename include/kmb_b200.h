@@ -63,7 +63,12 @@ enum {
                                   the device) the algebraically equal product form
                                   2^(-|u|^2) 2^(2u.v) 2^(-|v|^2) is used instead (4 FMA slots per pair, not 7) */
     KMB_PATH_TENSOR_3XTF32 = 2, /* |x|^2+|y|^2-2x.y (bruteforce.py:36-49) on tcgen05, 3xTF32 split, D >= 32 */
-    KMB_PATH_DIRECT_DIFF = 3   /* KMB_PATH_DIRECT_F32 restricted to the difference form */
+    KMB_PATH_DIRECT_DIFF = 3,  /* KMB_PATH_DIRECT_F32 restricted to the difference form */
+    KMB_PATH_DIRECT_SYM = 4    /* targets == sources (the reference's same_points, base.py:56-79): x must be the
+                                  same pointer as y.  Plain Gaussian product, D <= 3, E == 1: every kernel
+                                  value is evaluated once and feeds a_i += k b_j and a_j += k b_i (K is
+                                  symmetric), see kmb_product_sym_f32.  Never chosen by KMB_PATH_AUTO (the
+                                  library cannot see aliasing in kmb_product_workspace_bytes) */
 };
 
 typedef struct {
@@ -100,6 +105,24 @@ int kmb_product_workspace_bytes(int64_t n_targets, int64_t n_sources, int D, int
 int kmb_product_f32(const float* x, const float* y, const float* b, float* out, int64_t n_targets,
                     int64_t n_sources, int D, int E, int kernel_id, int flags, int path,
                     int64_t row_offset, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Symmetric Gaussian product for targets == sources (same_points):
+ *     out[i] = this part's share of  sum_j exp(-|y_i - y_j|^2) b[j]        (E == 1, D <= 3)
+ *
+ * Same arithmetic as kmb_product_f32(y, y, b, ...) -- kernel_matrix + K @ b of bruteforce.py:25-58,
+ * 153 with target_points = None (:27-28, :113-120) -- but K's symmetry is used: the n x n pair matrix
+ * is cut into (2048 rows x 512 sources) units, only units on or above the block diagonal are
+ * evaluated, and each kernel value is added to both its row's and its column's sum.  The unit list is
+ * split into `n_parts` equal contiguous ranges; this call evaluates range `part` and writes the sums it
+ * produced to ALL n entries of out (zero where it contributed nothing).  With n_parts > 1 (one part
+ * per GPU) the caller adds the parts' outputs -- one all-reduce of n floats; with n_parts == 1 out is
+ * the product.  Deterministic for a given (n, n_parts, device).  If the data are too spread out for the
+ * product form (see KMB_PATH_DIRECT_F32; decided on the device) the difference-form kernel computes
+ * rows [n*part/n_parts, n*(part+1)/n_parts) instead and the other rows of out are zero.
+ */
+int kmb_product_sym_workspace_bytes(int64_t n, int D, int part, int n_parts, size_t* bytes);
+int kmb_product_sym_f32(const float* y, const float* b, float* out, int64_t n, int D, int kernel_id,
+                        int part, int n_parts, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Number of this library's kernels the last kmb_product_f32 / kmb_cg_* call on this
  * thread launched (bench.py's gpu_launches). */

@@ -17,7 +17,7 @@ KMB_OK, KMB_ERR_INVALID, KMB_ERR_UNSUPPORTED, KMB_ERR_WORKSPACE, KMB_ERR_CUDA = 
 
 KERNEL_IDS = {"gaussian": 0, "absolute-exponential": 1, "inverse-distance": 2}
 FLAG_NORMALIZE_ROWS, FLAG_DENSITY = 1, 2
-PATH_IDS = {"auto": 0, "direct": 1, "tensor": 2, "direct_diff": 3}
+PATH_IDS = {"auto": 0, "direct": 1, "tensor": 2, "direct_diff": 3, "direct_sym": 4}
 
 
 class DeviceInfo(ctypes.Structure):
@@ -43,6 +43,11 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int64,
          c_void_p, c_size_t, c_void_p],
+    ),
+    "kmb_product_sym_workspace_bytes": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_size_t)]),
+    "kmb_product_sym_f32": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p],
     ),
     "kmb_set_profiling": (c_int, [c_int]),
     "kmb_last_main_kernel_ms": (c_int, [POINTER(c_float)]),

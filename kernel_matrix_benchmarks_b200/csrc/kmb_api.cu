@@ -6,6 +6,7 @@
 #include <algorithm>
 
 #include "kprod_direct.cuh"
+#include "kprod_sym.cuh"
 #include "kprod_tensor.cuh"
 
 namespace kmb {
@@ -37,6 +38,14 @@ KMB_DECLARE_TABLE(kDirect_invdist_n0)
 KMB_DECLARE_TABLE(kDirect_invdist_n1)
 KMB_DECLARE_TABLE(kDirect_gaussprod_n0)
 KMB_DECLARE_TABLE(kDirect_gaussprod_n1)
+
+// kprod_sym.cu
+bool sym_supported(int D);
+int sym_tile_rows();
+int sym_block_sources();
+long long sym_total_units(long long n_tiles, long long nsb);
+int sym_grid(int D, int sms, int* grid);
+int sym_launch(int D, const SymParams& P, cudaStream_t stream);
 
 static const DirectEntry* find_direct(int D, int e_chunk, int kid, bool norm, int form) {
     const DirectEntry* tab = nullptr;
@@ -119,6 +128,39 @@ static int plan_direct(int64_t N, int64_t M, int D, int E, int kid, int flags, i
     return KMB_OK;
 }
 
+// Symmetric (same_points) Gaussian product: the difference-form plan of this part's row shard (the
+// fallback when the data rule out the product form) + the buffers of kprod_sym.
+struct SymPlan {
+    DirectPlan direct;          // rows [lo, hi) x all sources, difference form + product-form record layout
+    int64_t lo, hi;
+    long long n_tiles, nsb, N_pad, units;
+    int grid;
+    size_t rowsum_bytes, rowpart_bytes, colpart_bytes, total_bytes;
+};
+
+static int plan_sym(int64_t n, int D, int part, int n_parts, SymPlan* sp) {
+    if (!sym_supported(D)) return set_error(KMB_ERR_UNSUPPORTED, "symmetric path supports D <= 3 (got D=%d)", D);
+    if (n_parts < 1 || part < 0 || part >= n_parts) return set_error(KMB_ERR_INVALID, "bad part %d of %d", part, n_parts);
+    sp->lo = n * part / n_parts;
+    sp->hi = n * (part + 1) / n_parts;
+    if (int rc = plan_direct(std::max<int64_t>(sp->hi - sp->lo, 1), n, D, 1, KMB_KERNEL_GAUSSIAN, 0, KMB_PATH_DIRECT_F32, &sp->direct)) return rc;
+    const DirectEntry* pe = sp->direct.form[1].ent;
+    if (!pe || pe->SB != sym_block_sources() || pe->RECV != 2)
+        return set_error(KMB_ERR_UNSUPPORTED, "no product-form record layout for D=%d", D);
+    sp->nsb = (n + sym_block_sources() - 1) / sym_block_sources();
+    sp->N_pad = sp->nsb * sym_block_sources();
+    sp->n_tiles = (n + sym_tile_rows() - 1) / sym_tile_rows();
+    sp->units = sym_total_units(sp->n_tiles, sp->nsb);
+    int sms = 0;
+    if (int rc = device_sm_count(&sms)) return rc;
+    if (int rc = sym_grid(D, sms, &sp->grid)) return rc;
+    sp->rowsum_bytes = align_up(static_cast<size_t>(sp->n_tiles) * sym_tile_rows() * 4, 256);
+    sp->rowpart_bytes = align_up(static_cast<size_t>(sp->grid) * 2 * sym_tile_rows() * 4, 256);
+    sp->colpart_bytes = align_up(static_cast<size_t>(sp->n_tiles) * sp->N_pad * 4, 256);
+    sp->total_bytes = sp->direct.total_bytes + sp->rowsum_bytes + sp->rowpart_bytes + sp->colpart_bytes;
+    return KMB_OK;
+}
+
 __global__ void fill_kernel(float* out, long long n, float v) {
     const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (i < n) out[i] = v;
@@ -129,7 +171,12 @@ static int check_product_args(int64_t N, int64_t M, int D, int E, int kid, int f
     if (kid < 0 || kid > KMB_KERNEL_INVERSE_DISTANCE) return set_error(KMB_ERR_UNSUPPORTED, "unknown kernel id %d", kid);
     if (flags & ~(KMB_FLAG_NORMALIZE_ROWS | KMB_FLAG_DENSITY)) return set_error(KMB_ERR_INVALID, "unknown flags 0x%x", flags);
     if ((flags & KMB_FLAG_DENSITY) && E != 1) return set_error(KMB_ERR_INVALID, "density estimation implies E == 1 (got %d)", E);
-    if (path < KMB_PATH_AUTO || path > KMB_PATH_DIRECT_DIFF) return set_error(KMB_ERR_INVALID, "unknown path %d", path);
+    if (path < KMB_PATH_AUTO || path > KMB_PATH_DIRECT_SYM) return set_error(KMB_ERR_INVALID, "unknown path %d", path);
+    if (path == KMB_PATH_DIRECT_SYM) {
+        if (N != M) return set_error(KMB_ERR_INVALID, "the symmetric path needs targets == sources (N=%lld, M=%lld)", (long long)N, (long long)M);
+        if (kid != KMB_KERNEL_GAUSSIAN || flags != 0 || E != 1 || !sym_supported(D))
+            return set_error(KMB_ERR_UNSUPPORTED, "the symmetric path covers the plain Gaussian product with D <= 3, E = 1");
+    }
     return KMB_OK;
 }
 
@@ -138,97 +185,18 @@ static int resolve_path(int D, int path) {
     return D <= 16 ? KMB_PATH_DIRECT_F32 : KMB_PATH_TENSOR_3XTF32;
 }
 
-}  // namespace kmb
-
-using namespace kmb;
-
-extern "C" {
-
-int kmb_abi_version(void) { return KMB_ABI_VERSION; }
-const char* kmb_last_error(void) { return g_err; }
-int kmb_last_launch_count(void) { return g_launches; }
-
-int kmb_set_profiling(int enabled) {
-    g_profile = enabled != 0;
-    g_ev_valid = false;
-    return KMB_OK;
-}
-int kmb_last_main_kernel_ms(float* ms) {
-    if (!ms) return set_error(KMB_ERR_INVALID, "ms is NULL");
-    if (!g_ev_valid) return set_error(KMB_ERR_INVALID, "no profiled product call on this thread");
-    KMB_CUDA_CHECK(cudaEventSynchronize(g_ev1));
-    KMB_CUDA_CHECK(cudaEventElapsedTime(ms, g_ev0, g_ev1));
-    return KMB_OK;
-}
-
-int kmb_get_device_info(int device, kmb_device_info* info) {
-    if (!info) return set_error(KMB_ERR_INVALID, "info is NULL");
-    cudaDeviceProp p;
-    KMB_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
-    info->sm_count = p.multiProcessorCount;
-    info->cc_major = p.major;
-    info->cc_minor = p.minor;
-    KMB_CUDA_CHECK(cudaDeviceGetAttribute(&info->clock_khz, cudaDevAttrClockRate, device));
-    info->l2_bytes = p.l2CacheSize;
-    info->smem_per_block_optin = static_cast<int>(p.sharedMemPerBlockOptin);
-    info->total_mem = p.totalGlobalMem;
-    return KMB_OK;
-}
-
-int kmb_product_workspace_bytes(int64_t N, int64_t M, int D, int E, int kernel_id, int flags, int path,
-                                size_t* bytes) {
-    if (!bytes) return set_error(KMB_ERR_INVALID, "bytes is NULL");
-    if (int rc = check_product_args(N, M, D, E, kernel_id, flags, path)) return rc;
-    *bytes = 256;
-    if ((flags & KMB_FLAG_NORMALIZE_ROWS) && (flags & KMB_FLAG_DENSITY)) return KMB_OK;
-    const int p = resolve_path(D, path);
-    if (p == KMB_PATH_DIRECT_F32 || p == KMB_PATH_DIRECT_DIFF) {
-        DirectPlan pl;
-        if (int rc = plan_direct(N, M, D, E, kernel_id, flags, p, &pl)) return rc;
-        *bytes = pl.total_bytes;
-        return KMB_OK;
-    }
-    return tensor_workspace_bytes(N, M, D, E, kernel_id, flags, bytes);
-}
-
-int kmb_product_f32(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D,
-                    int E, int kernel_id, int flags, int path, int64_t row_offset, void* workspace,
-                    size_t workspace_bytes, void* stream_) {
-    g_launches = 0;
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (int rc = check_product_args(N, M, D, E, kernel_id, flags, path)) return rc;
-    if (!x || !y || !out) return set_error(KMB_ERR_INVALID, "x, y and out must not be NULL");
-    const bool density = flags & KMB_FLAG_DENSITY;
-    if (!density && !b) return set_error(KMB_ERR_INVALID, "b is NULL without KMB_FLAG_DENSITY");
-    if (N == 0) return KMB_OK;
-
-    if ((flags & KMB_FLAG_NORMALIZE_ROWS) && density) {  // bruteforce.py:134-138
-        fill_kernel<<<static_cast<unsigned>((N + 255) / 256), 256, 0, stream>>>(out, N, 1.0f);
-        KMB_CUDA_CHECK(cudaGetLastError());
-        count_launch();
-        return KMB_OK;
-    }
-    const int p = resolve_path(D, path);
-    if (reinterpret_cast<uintptr_t>(workspace) % 256)
-        return set_error(KMB_ERR_INVALID, "workspace must be 256-byte aligned");
-    if (p == KMB_PATH_TENSOR_3XTF32) {
-        if (g_profile && !g_ev0) {
-            KMB_CUDA_CHECK(cudaEventCreate(&g_ev0));
-            KMB_CUDA_CHECK(cudaEventCreate(&g_ev1));
-        }
-        const int rc = tensor_product(x, y, density ? nullptr : b, out, N, M, D, E, kernel_id, flags, row_offset, workspace,
-                                      workspace_bytes, stream, g_profile ? g_ev0 : nullptr, g_profile ? g_ev1 : nullptr);
-        if (rc == KMB_OK && g_profile) g_ev_valid = true;
-        return rc;
-    }
-
-    DirectPlan pl;
-    if (int rc = plan_direct(N, M, D, E, kernel_id, flags, p, &pl)) return rc;
-    if (!workspace || workspace_bytes < pl.total_bytes)
-        return set_error(KMB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total_bytes, workspace_bytes);
-    if (reinterpret_cast<uintptr_t>(workspace) % 256)
-        return set_error(KMB_ERR_INVALID, "workspace must be 256-byte aligned");
-    char* ws = static_cast<char*>(workspace);
+// Enqueue the direct pipeline on `stream`: bounding-box statistics -> source packing -> main kernels.
+//   sym == nullptr  out (N x E) = product of the N targets x with all M sources.
+//   sym != nullptr  targets == sources == y (x is y, N == M, E == 1).  The product form runs as the
+//                   symmetric kernel over this part's share of the unit list and writes this part's
+//                   contribution to all N rows of out; if the data rule the product form out, the
+//                   difference form writes rows [lo, hi) of out and the other rows stay zero.  Either
+//                   way the parts' outputs add up to the product.
+static int run_direct(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D, int E,
+                      int kernel_id, int flags, int64_t row_offset, const DirectPlan& pl, const SymPlan* sym, int part,
+                      int n_parts, char* ws, cudaStream_t stream) {
+    const bool density = b == nullptr;
+    (void)flags;
     DirectStats* stats = reinterpret_cast<DirectStats*>(ws);
     float* block_box = reinterpret_cast<float*>(ws + align_up(sizeof(DirectStats), 256));
     float2* rec = reinterpret_cast<float2*>(ws + pl.stats_bytes);
@@ -236,6 +204,7 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
     int* counters = reinterpret_cast<int*>(ws + pl.stats_bytes + pl.rec_bytes + pl.partial_bytes);
     KMB_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(DirectStats), stream));
     KMB_CUDA_CHECK(cudaMemsetAsync(counters, 0, pl.counter_bytes, stream));
+    if (sym) KMB_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * N, stream));
 
     // bounding box -> centre, radius, evaluation form (stays on the device)
     {
@@ -286,9 +255,29 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
             }
             KMB_CUDA_CHECK(cudaEventRecord(g_ev0, stream));
         }
+        if (sym) {
+            // this part's share of the triangular unit list -> kprod_sym + combine (product form only)
+            char* sb = ws + pl.total_bytes;
+            SymParams S;
+            S.stats = stats;
+            S.rec = reinterpret_cast<const float4*>(rec);
+            S.rowsum = reinterpret_cast<float*>(sb);
+            S.rowpart = reinterpret_cast<float*>(sb + sym->rowsum_bytes);
+            S.colpart = reinterpret_cast<float*>(sb + sym->rowsum_bytes + sym->rowpart_bytes);
+            S.out = out;
+            S.N = N;
+            S.N_pad = sym->N_pad;
+            S.unit_begin = sym->units * part / n_parts;
+            S.unit_end = sym->units * (part + 1) / n_parts;
+            S.n_tiles = static_cast<int>(sym->n_tiles);
+            S.nsb = static_cast<int>(sym->nsb);
+            S.grid = sym->grid;
+            if (int rc = sym_launch(D, S, stream)) return rc;
+        }
         // both forms are enqueued; the one the data did not select returns at once
         for (int f = 1; f >= 0; --f) {
             if (!pl.form[f].ent) continue;
+            if (sym && (f == 1 || sym->hi == sym->lo)) continue;
             const DirectEntry& ent = *pl.form[f].ent;
             int per_sm = 0;
             if (int rc = resident(ent, &per_sm)) return rc;
@@ -296,15 +285,15 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
             long long grid = static_cast<long long>(pl.grid_max / 2) * per_sm;
             if (grid > units) grid = units;
             DirectParams P;
-            P.x = x;
+            P.x = sym ? y + sym->lo * D : x;
             P.stats = stats;
             P.rec = reinterpret_cast<const float4*>(rec);
-            P.out = out;
+            P.out = sym ? out + sym->lo : out;
             P.partial = partial;
             P.tile_counter = counters;
-            P.N = N;
+            P.N = sym ? sym->hi - sym->lo : N;
             P.M = M;
-            P.row_offset = row_offset;
+            P.row_offset = sym ? sym->lo : row_offset;
             P.D = D;
             P.E = E;
             P.e0 = e0;
@@ -320,6 +309,128 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
         }
     }
     return KMB_OK;
+}
+
+}  // namespace kmb
+
+using namespace kmb;
+
+extern "C" {
+
+int kmb_abi_version(void) { return KMB_ABI_VERSION; }
+const char* kmb_last_error(void) { return g_err; }
+int kmb_last_launch_count(void) { return g_launches; }
+
+int kmb_set_profiling(int enabled) {
+    g_profile = enabled != 0;
+    g_ev_valid = false;
+    return KMB_OK;
+}
+int kmb_last_main_kernel_ms(float* ms) {
+    if (!ms) return set_error(KMB_ERR_INVALID, "ms is NULL");
+    if (!g_ev_valid) return set_error(KMB_ERR_INVALID, "no profiled product call on this thread");
+    KMB_CUDA_CHECK(cudaEventSynchronize(g_ev1));
+    KMB_CUDA_CHECK(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+    return KMB_OK;
+}
+
+int kmb_get_device_info(int device, kmb_device_info* info) {
+    if (!info) return set_error(KMB_ERR_INVALID, "info is NULL");
+    cudaDeviceProp p;
+    KMB_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    info->sm_count = p.multiProcessorCount;
+    info->cc_major = p.major;
+    info->cc_minor = p.minor;
+    KMB_CUDA_CHECK(cudaDeviceGetAttribute(&info->clock_khz, cudaDevAttrClockRate, device));
+    info->l2_bytes = p.l2CacheSize;
+    info->smem_per_block_optin = static_cast<int>(p.sharedMemPerBlockOptin);
+    info->total_mem = p.totalGlobalMem;
+    return KMB_OK;
+}
+
+int kmb_product_workspace_bytes(int64_t N, int64_t M, int D, int E, int kernel_id, int flags, int path,
+                                size_t* bytes) {
+    if (!bytes) return set_error(KMB_ERR_INVALID, "bytes is NULL");
+    if (int rc = check_product_args(N, M, D, E, kernel_id, flags, path)) return rc;
+    *bytes = 256;
+    if ((flags & KMB_FLAG_NORMALIZE_ROWS) && (flags & KMB_FLAG_DENSITY)) return KMB_OK;
+    const int p = resolve_path(D, path);
+    if (p == KMB_PATH_DIRECT_SYM) return kmb_product_sym_workspace_bytes(N, D, 0, 1, bytes);
+    if (p == KMB_PATH_DIRECT_F32 || p == KMB_PATH_DIRECT_DIFF) {
+        DirectPlan pl;
+        if (int rc = plan_direct(N, M, D, E, kernel_id, flags, p, &pl)) return rc;
+        *bytes = pl.total_bytes;
+        return KMB_OK;
+    }
+    return tensor_workspace_bytes(N, M, D, E, kernel_id, flags, bytes);
+}
+
+int kmb_product_f32(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D,
+                    int E, int kernel_id, int flags, int path, int64_t row_offset, void* workspace,
+                    size_t workspace_bytes, void* stream_) {
+    g_launches = 0;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_product_args(N, M, D, E, kernel_id, flags, path)) return rc;
+    if (!x || !y || !out) return set_error(KMB_ERR_INVALID, "x, y and out must not be NULL");
+    const bool density = flags & KMB_FLAG_DENSITY;
+    if (!density && !b) return set_error(KMB_ERR_INVALID, "b is NULL without KMB_FLAG_DENSITY");
+    if (N == 0) return KMB_OK;
+
+    if ((flags & KMB_FLAG_NORMALIZE_ROWS) && density) {  // bruteforce.py:134-138
+        fill_kernel<<<static_cast<unsigned>((N + 255) / 256), 256, 0, stream>>>(out, N, 1.0f);
+        KMB_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+        return KMB_OK;
+    }
+    const int p = resolve_path(D, path);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256)
+        return set_error(KMB_ERR_INVALID, "workspace must be 256-byte aligned");
+    if (p == KMB_PATH_TENSOR_3XTF32) {
+        if (g_profile && !g_ev0) {
+            KMB_CUDA_CHECK(cudaEventCreate(&g_ev0));
+            KMB_CUDA_CHECK(cudaEventCreate(&g_ev1));
+        }
+        const int rc = tensor_product(x, y, density ? nullptr : b, out, N, M, D, E, kernel_id, flags, row_offset, workspace,
+                                      workspace_bytes, stream, g_profile ? g_ev0 : nullptr, g_profile ? g_ev1 : nullptr);
+        if (rc == KMB_OK && g_profile) g_ev_valid = true;
+        return rc;
+    }
+
+    if (p == KMB_PATH_DIRECT_SYM) {
+        if (x != y) return set_error(KMB_ERR_INVALID, "the symmetric path needs x == y (same_points)");
+        return kmb_product_sym_f32(y, b, out, N, D, kernel_id, 0, 1, workspace, workspace_bytes, stream_);
+    }
+    DirectPlan pl;
+    if (int rc = plan_direct(N, M, D, E, kernel_id, flags, p, &pl)) return rc;
+    if (!workspace || workspace_bytes < pl.total_bytes)
+        return set_error(KMB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total_bytes, workspace_bytes);
+    return run_direct(x, y, density ? nullptr : b, out, N, M, D, E, kernel_id, flags, row_offset, pl, nullptr, 0, 1,
+                      static_cast<char*>(workspace), stream);
+}
+
+int kmb_product_sym_workspace_bytes(int64_t n, int D, int part, int n_parts, size_t* bytes) {
+    if (!bytes) return set_error(KMB_ERR_INVALID, "bytes is NULL");
+    if (n < 1) return set_error(KMB_ERR_INVALID, "bad size n=%lld", (long long)n);
+    SymPlan sp;
+    if (int rc = plan_sym(n, D, part, n_parts, &sp)) return rc;
+    *bytes = sp.total_bytes;
+    return KMB_OK;
+}
+
+int kmb_product_sym_f32(const float* y, const float* b, float* out, int64_t n, int D, int kernel_id, int part, int n_parts,
+                        void* workspace, size_t workspace_bytes, void* stream_) {
+    g_launches = 0;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n < 1 || D < 1) return set_error(KMB_ERR_INVALID, "bad sizes n=%lld D=%d", (long long)n, D);
+    if (kernel_id != KMB_KERNEL_GAUSSIAN) return set_error(KMB_ERR_UNSUPPORTED, "the symmetric path covers the Gaussian kernel only");
+    if (!y || !b || !out) return set_error(KMB_ERR_INVALID, "y, b and out must not be NULL");
+    SymPlan sp;
+    if (int rc = plan_sym(n, D, part, n_parts, &sp)) return rc;
+    if (!workspace || workspace_bytes < sp.total_bytes)
+        return set_error(KMB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", sp.total_bytes, workspace_bytes);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256)
+        return set_error(KMB_ERR_INVALID, "workspace must be 256-byte aligned");
+    return run_direct(y, y, b, out, n, n, D, 1, kernel_id, 0, 0, sp.direct, &sp, part, n_parts, static_cast<char*>(workspace), stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,58 @@
+// Instantiations and launchers of the symmetric (same_points) Gaussian product, D <= 3, E = 1.
+#include "kprod_sym.cuh"
+
+namespace kmb {
+
+namespace {
+
+template <class C>
+int sym_grid_of(int sms, int* grid) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        KMB_CUDA_CHECK(cudaFuncSetAttribute(kprod_sym_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        int n = 0;
+        KMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kprod_sym_kernel<C>, C::THREADS, C::SMEM_BYTES));
+        if (n < 1) return set_error(KMB_ERR_CUDA, "symmetric kernel does not fit on an SM (smem %d B)", C::SMEM_BYTES);
+        per_sm = n > 2 ? 2 : n;
+    }
+    *grid = sms * per_sm;
+    return KMB_OK;
+}
+
+template <class C>
+int sym_launch_of(SymParams P, cudaStream_t stream) {
+    const long long units = P.unit_end - P.unit_begin;
+    if (units > 0) {
+        const int grid = static_cast<int>(std::min<long long>(P.grid, units));
+        P.grid = grid;
+        kprod_sym_kernel<C><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(P);
+        KMB_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+    }
+    sym_combine_kernel<C><<<static_cast<unsigned>((P.N + 255) / 256), 256, 0, stream>>>(P);
+    KMB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return KMB_OK;
+}
+
+using Sym2 = SymCfg<2>;
+using Sym3 = SymCfg<3>;
+
+}  // namespace
+
+bool sym_supported(int D) { return D >= 1 && D <= 3; }
+int sym_padded_dim(int D) { return D <= 2 ? 2 : 3; }
+int sym_tile_rows() { return Sym3::TILE_ROWS; }
+int sym_block_sources() { return Sym3::SB; }
+long long sym_total_units(long long n_tiles, long long nsb) { return sym_prefix<Sym3::TB>(n_tiles, nsb); }
+
+int sym_grid(int D, int sms, int* grid) {
+    return sym_padded_dim(D) == 2 ? sym_grid_of<Sym2>(sms, grid) : sym_grid_of<Sym3>(sms, grid);
+}
+
+// the main kernel over P.unit_begin .. P.unit_end on P.grid CTAs, then the combine kernel
+int sym_launch(int D, const SymParams& P, cudaStream_t stream) {
+    return sym_padded_dim(D) == 2 ? sym_launch_of<Sym2>(P, stream) : sym_launch_of<Sym3>(P, stream);
+}
+
+}  // namespace kmb

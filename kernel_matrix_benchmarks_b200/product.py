@@ -41,6 +41,16 @@ class Workspace:
 
 _default_ws = {}
 
+# below this many points the symmetric kernel's extra passes (column-sum buffers, combine kernel) cost
+# more than the exponentials it saves
+SYM_MIN_POINTS = 16384
+
+
+def _symmetric_applies(x, y, kernel, normalize_rows, density_estimation, E):
+    """targets *are* the sources (same tensor), plain Gaussian product, D <= 3, E == 1."""
+    return (x.data_ptr() == y.data_ptr() and x.shape == y.shape and kernel == "gaussian" and not normalize_rows
+            and not density_estimation and E == 1 and x.shape[1] <= 3)
+
 
 def kernel_product(x, y, b, *, kernel="gaussian", normalize_rows=False, density_estimation=False, path="auto",
                    row_offset=0, out=None, workspace=None):
@@ -68,6 +78,8 @@ def kernel_product(x, y, b, *, kernel="gaussian", normalize_rows=False, density_
         out = torch.empty((N, E), dtype=torch.float32, device=x.device)
     else:
         _check_f32("out", out, E)
+    if path == "auto" and N >= SYM_MIN_POINTS and _symmetric_applies(x, y, kernel, normalize_rows, density_estimation, E):
+        path = "direct_sym"  # same_points: each kernel value serves its row and its column (kprod_sym.cuh)
     kid, pid = _lib.KERNEL_IDS[kernel], _lib.PATH_IDS[path]
     need = ctypes.c_size_t(0)
     _lib.check(lib.kmb_product_workspace_bytes(N, M, D, E, kid, flags, pid, ctypes.byref(need)))
@@ -77,6 +89,33 @@ def kernel_product(x, y, b, *, kernel="gaussian", normalize_rows=False, density_
     with torch.cuda.device(x.device):
         _lib.check(lib.kmb_product_f32(_ptr(x), _ptr(y), _ptr(b), _ptr(out), N, M, D, E, kid, flags, pid, int(row_offset),
                                        _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
+def kernel_product_sym_part(y, b, part, n_parts, *, out=None, workspace=None):
+    """This part's share of the Gaussian product with targets == sources (kmb_product_sym_f32).
+
+    Returns an (n, 1) tensor; the shares of all ``n_parts`` parts add up to K b (the caller
+    all-reduces them when every part runs on its own GPU).  Asynchronous on the current stream.
+    """
+    lib = _lib.load()
+    _check_f32("points", y)
+    _check_f32("signal", b, 1)
+    n, D = y.shape
+    if b.shape[0] != n:
+        raise ValueError("signal and points disagree on n")
+    if out is None:
+        out = torch.empty((n, 1), dtype=torch.float32, device=y.device)
+    else:
+        _check_f32("out", out, 1)
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.kmb_product_sym_workspace_bytes(n, D, int(part), int(n_parts), ctypes.byref(need)))
+    if workspace is None:
+        workspace = _default_ws.setdefault(y.device, Workspace())
+    ws = workspace.get(need.value, y.device)
+    with torch.cuda.device(y.device):
+        _lib.check(lib.kmb_product_sym_f32(_ptr(y), _ptr(b), _ptr(out), n, D, _lib.KERNEL_IDS["gaussian"], int(part),
+                                           int(n_parts), _ptr(ws), ws.numel(), _stream()))
     return out
 
 
