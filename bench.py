@@ -6,15 +6,21 @@
         --master-port P bench.py --gpus N --steps K --warmup W
 
 A step is one pass of the hot path over the whole synthetic problem: a_i = sum_j exp(-|x_i-y_j|^2) b_j
-for all N targets.  With N > 1 GPUs the target rows are sharded (strong scaling: the problem is
-fixed), sources are replicated, no collective sits on the data path.  Rank 0 prints ONE JSON line.
+for all N targets.  The C2 dataset has targets == sources (datasets.uniform_cube, same_points), so the
+default path is the symmetric kernel (kprod_sym: every kernel value feeds its row and its column).
+With G > 1 GPUs the problem stays fixed (strong scaling): the triangular unit list is cut into G equal
+ranges, one per rank, and the ranks' partial results are summed with one NCCL all-reduce of N floats
+inside the timed step.  `--path direct` times the general (x != y) kernel instead, target rows sharded,
+no collective.  Rank 0 prints ONE JSON line.
 
   value     Gpairs/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e       same metric through the plugin call sequence (runner.py:73-143) with HOST float64
             arrays: cast + H2D of points and signal, query, D2H of the result inside the timer
   roofline  the dominant kernel against the FP32/MUFU pipe roofline of SURVEY.md section 8(d):
-            16 pairs/clk/SM x SMs x clocks.max.sm (this path is compute bound: its compulsory
-            HBM traffic is 32 MB per 10^12 pairs)
+            16 kernel evaluations/clk/SM x SMs x clocks.max.sm (this path is compute bound: its
+            compulsory HBM traffic is 32 MB per 10^12 pairs).  The symmetric kernel needs one
+            evaluation per TWO pairs, so its peak is 32 pairs/clk/SM; `frac` is against that and
+            `frac_vs_one_eval_per_pair` against the 16 pairs/clk/SM figure of the general kernel
   cpu_baseline / --impl reference
             the reference algorithm (NumPy port in oracle/, the reference itself is pure Python
             and does not travel to the GPU box) on a bounded row sample, all host cores
@@ -47,10 +53,16 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = sized for ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--path", default="auto", choices=["auto", "direct"],
+                    help="auto: symmetric kernel (targets == sources); direct: general kernel, rows sharded")
     return ap.parse_args()
 
 
-def workload_config(n, n_gpus):
+def workload_config(n, n_gpus, path="auto"):
+    sharding = (f"symmetric unit list over {n_gpus} GPU(s), points replicated, one all-reduce of N floats per step"
+                if path == "auto" else f"target rows over {n_gpus} GPU(s), sources replicated, no collective")
+    if path == "auto" and n_gpus == 1:
+        sharding = "1 GPU, symmetric kernel (same_points), no collective"
     return {
         "workload": f"C2: gaussian kernel product N=M={n}, D=3, E=1 (datasets.uniform_cube semantics)",
         "kernel": "gaussian",
@@ -58,7 +70,8 @@ def workload_config(n, n_gpus):
         "M": n,
         "D": 3,
         "E": 1,
-        "sharding": f"target rows over {n_gpus} GPU(s), sources replicated, no collective",
+        "path": "symmetric (kprod_sym)" if path == "auto" else "general (kprod_direct)",
+        "sharding": sharding,
         "l2": "flushed between timed steps (256 MiB write)",
     }
 
@@ -72,11 +85,12 @@ def read_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def measured_traffic(n, world):
+def measured_traffic(n, world, sym):
     """dram__bytes_read.sum + dram__bytes_write.sum of the main kernel from the committed ncu capture
-    (profiles/r1_traffic_main_kernel.json); only valid for the workload it was captured on."""
+    (profiles/r1_traffic_*.json); only valid for the workload it was captured on."""
     try:
-        with open(os.path.join(REPO, "profiles", "r1_traffic_main_kernel.json")) as f:
+        name = "r1_traffic_sym_kernel.json" if sym else "r1_traffic_main_kernel.json"
+        with open(os.path.join(REPO, "profiles", name)) as f:
             t = json.load(f)
         if t["N"] == n and world == 1:
             return t["dram_bytes_per_launch"]
@@ -143,7 +157,7 @@ def run_reference_arm(args):
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args.n, args.gpus),
+        "data": "synthetic", "config": workload_config(args.n, args.gpus, args.path),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -244,13 +258,22 @@ def run_b200_arm(args):
     # ---- device-resident arm ---------------------------------------------------------------
     y = torch.from_numpy(ds.source_points.astype(np.float32)).to(dev)
     b = torch.from_numpy(ds.source_signal.astype(np.float32)).to(dev)
+    sym = args.path == "auto"
+    if sym and not product.symmetric_applies(y, y, "gaussian"):
+        raise SystemExit("the symmetric path does not apply to this workload")
     x = y[lo:hi]
-    out = torch.empty((hi - lo, 1), dtype=torch.float32, device=dev)
+    out = torch.empty((N if sym else hi - lo, 1), dtype=torch.float32, device=dev)
     ws = product.Workspace()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step():
-        product.kernel_product(x, y, b, kernel="gaussian", path="direct", row_offset=lo, out=out, workspace=ws)
+        if not sym:
+            product.kernel_product(x, y, b, kernel="gaussian", path="direct", row_offset=lo, out=out, workspace=ws)
+        elif world == 1:
+            product.kernel_product(y, y, b, kernel="gaussian", path="direct_sym", out=out, workspace=ws)
+        else:
+            product.kernel_product_sym_part(y, b, rank, world, out=out, workspace=ws)
+            dist.all_reduce(out)   # the exchange step of the symmetric split: N floats
 
     product.set_profiling(True)
     for _ in range(args.warmup):
@@ -275,15 +298,35 @@ def run_b200_arm(args):
     main_ms = max_over_ranks(sum(kernel_ms) / len(kernel_ms))
     value = pairs_total / (step_ms * 1e-3) / 1e9
 
+    # the general (x != y) kernel on the same data, rows sharded: what a caller without same_points gets
+    general = None
+    if sym:
+        out_g = torch.empty((hi - lo, 1), dtype=torch.float32, device=dev)
+        for _ in range(2):
+            product.kernel_product(x, y, b, kernel="gaussian", path="direct", row_offset=lo, out=out_g, workspace=ws)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(2):
+            product.kernel_product(x, y, b, kernel="gaussian", path="direct", row_offset=lo, out=out_g, workspace=ws)
+        g1.record()
+        barrier()
+        g_ms = max_over_ranks(g0.elapsed_time(g1) / 2)
+        general = {"value": pairs_total / (g_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": g_ms,
+                   "kernel": "kprod_direct_kernel<D=3,E=1,R=4,gaussian,product form,512 thr>, target rows sharded"}
+        # parity of the two kernels on this rank's rows (the tests hold both to the oracle)
+        diff = (out[lo:hi] - out_g).double().norm() / out_g.double().norm()
+        general["rel_l2_symmetric_vs_general"] = float(diff)
+
     # ---- end-to-end arm: plugin API, host float64 arrays in, host float64 result out ------------
     e2e = None
     if not args.no_e2e:
         xs_host = ds.source_points[lo:hi]
 
         def e2e_step():
-            algo = B200Product(kernel="gaussian", dimension=3, normalize_rows=False, precision="float32", path="direct",
-                               device=local_rank)
-            if world == 1:
+            algo = B200Product(kernel="gaussian", dimension=3, normalize_rows=False, precision="float32", path=args.path,
+                               device=local_rank, distributed=(sym and world > 1))
+            if world == 1 or sym:
                 algo.prepare_data(source_points=ds.source_points, target_points=ds.source_points, same_points=True)
             else:
                 algo.prepare_data(source_points=ds.source_points, target_points=xs_host, same_points=False)
@@ -304,46 +347,55 @@ def run_b200_arm(args):
         dt = time.perf_counter() - t0
         barrier()
         e2e_ms = max_over_ranks(1e3 * dt / args.steps)
-        n_x = 0 if world == 1 else (hi - lo) * 3
+        n_x = 0 if (world == 1 or sym) else (hi - lo) * 3
+        n_out = N if sym else hi - lo
         e2e = {
             "value": pairs_total / (e2e_ms * 1e-3) / 1e9,
             "unit": UNIT,
             "ms_per_step": e2e_ms,
             "h2d_bytes_per_step": int(4 * (n_x + M * 3 + M * 1)),
-            "d2h_bytes_per_step": int(4 * (hi - lo)),
+            "d2h_bytes_per_step": int(4 * n_out),
             "api": "B200Product.prepare_data/fit/prepare_query/query/get_result, host float64 in/out",
         }
-        assert res.shape == (hi - lo, 1)
+        assert res.shape == (n_out, 1)
 
     if rank == 0:
         peaks, peaks_src = read_peaks()
         info = product.device_info(local_rank)
         sm_max = float(clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or info["clock_khz"] / 1e3)
-        peak = PAIRS_PER_CLK_PER_SM * info["sm_count"] * sm_max * 1e6 / 1e9  # Gpairs/s per GPU
-        pairs_per_launch = float(hi - lo) * M  # rank 0's shard (the largest)
+        evals_per_pair = 0.5 if sym else 1.0   # the symmetric kernel evaluates k once per two pairs
+        peak_evals = PAIRS_PER_CLK_PER_SM * info["sm_count"] * sm_max * 1e6 / 1e9   # G kernel evaluations/s per GPU
+        peak = peak_evals / evals_per_pair                                           # Gpairs/s per GPU
+        pairs_per_launch = pairs_total / world  # every rank evaluates an equal share
         achieved = pairs_per_launch / (main_ms * 1e-3) / 1e9
+        kernel_name = ("kprod_sym_kernel<D=3,512 thr x 8 rows,butterfly 16> + sym_combine_kernel" if sym
+                       else "kprod_direct_kernel<D=3,E=1,R=4,gaussian,product form,512 thr>")
         roofline = {
             "bound": "fp32_mufu",
             "achieved": achieved,
             "peak": peak,
             "unit": UNIT,
             "frac": achieved / peak,
-            "traffic": measured_traffic(args.n, world),
-            "kernel": "kprod_direct_kernel<D=3,E=1,R=4,gaussian,product form,512 thr>",
+            "frac_vs_one_eval_per_pair": achieved / peak_evals,
+            "kernel_evals_per_pair": evals_per_pair,
+            "traffic": measured_traffic(args.n, world, sym),
+            "kernel": kernel_name,
             "kernel_ms": main_ms,
-            "peak_basis": f"16 pairs/clk/SM x {info['sm_count']} SMs x {sm_max:.0f} MHz (clocks.max.sm); "
-                          f"MEASURED_PEAKS.json {peaks_src}: hbm {peaks.get('hbm_gbs')} GB/s not binding "
-                          f"(algorithmic HBM bytes/launch = {4 * ((hi - lo) * 3 + M * 4 + (hi - lo))})",
-            "frac_at_sampled_clock": (achieved / (PAIRS_PER_CLK_PER_SM * info["sm_count"] * clocks["sm_mhz"] * 1e-3)
+            "peak_basis": f"16 kernel evaluations (MUFU.EX2)/clk/SM x {info['sm_count']} SMs x {sm_max:.0f} MHz (clocks.max.sm) "
+                          f"/ {evals_per_pair} evaluations per pair; MEASURED_PEAKS.json {peaks_src}: hbm {peaks.get('hbm_gbs')} GB/s "
+                          f"not binding (algorithmic HBM bytes/launch = {4 * (N * 3 + M * 4 + N)})",
+            "frac_at_sampled_clock": (achieved * evals_per_pair / (PAIRS_PER_CLK_PER_SM * info["sm_count"] * clocks["sm_mhz"] * 1e-3)
                                       if clocks.get("sm_mhz") else None),
         }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args.n, world),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.n, world, args.path),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roofline,
         }
+        if general is not None:
+            line["general_kernel"] = general
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(ds, pick_cpu_rows(ds, args.cpu_rows))
         print(json.dumps(line))

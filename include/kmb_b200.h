@@ -65,7 +65,7 @@ enum {
     KMB_PATH_TENSOR_3XTF32 = 2, /* |x|^2+|y|^2-2x.y (bruteforce.py:36-49) on tcgen05, 3xTF32 split, D >= 32 */
     KMB_PATH_DIRECT_DIFF = 3,  /* KMB_PATH_DIRECT_F32 restricted to the difference form */
     KMB_PATH_DIRECT_SYM = 4    /* targets == sources (the reference's same_points, base.py:56-79): x must be the
-                                  same pointer as y.  Plain Gaussian product, D <= 3, E == 1: every kernel
+                                  same pointer as y.  Plain Gaussian product or density, D <= 3, E == 1: every kernel
                                   value is evaluated once and feeds a_i += k b_j and a_j += k b_i (K is
                                   symmetric), see kmb_product_sym_f32.  Never chosen by KMB_PATH_AUTO (the
                                   library cannot see aliasing in kmb_product_workspace_bytes) */
@@ -119,6 +119,7 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
  * the product.  Deterministic for a given (n, n_parts, device).  If the data are too spread out for the
  * product form (see KMB_PATH_DIRECT_F32; decided on the device) the difference-form kernel computes
  * rows [n*part/n_parts, n*(part+1)/n_parts) instead and the other rows of out are zero.
+ * b == NULL means b == 1 (density estimation, bruteforce.py:150).
  */
 int kmb_product_sym_workspace_bytes(int64_t n, int D, int part, int n_parts, size_t* bytes);
 int kmb_product_sym_f32(const float* y, const float* b, float* out, int64_t n, int D, int kernel_id,

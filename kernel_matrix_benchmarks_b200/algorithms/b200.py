@@ -24,8 +24,9 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..product import Workspace, device_info, kernel_product, last_launch_count
-from ..solver import CudaShardOps, LocalComm, cg_solve
+from .. import product as _product
+from ..product import Workspace, device_info, kernel_product, kernel_product_sym_part, last_launch_count
+from ..solver import CudaShardOps, CudaSymmetricOps, LocalComm, TorchDistComm, cg_solve, shard_bounds
 from .base import BaseProduct, BaseSolver
 
 
@@ -64,7 +65,12 @@ class _GpuTimer:
 class B200Product(BaseProduct):
     """On-the-fly kernel product / density / attention on one B200."""
 
-    def __init__(self, *, kernel, dimension, normalize_rows=False, precision="float32", path="auto", device=0):
+    def __init__(self, *, kernel, dimension, normalize_rows=False, precision="float32", path="auto", device=0,
+                 distributed=False):
+        """``distributed=True``: one process per GPU under torch.distributed (NCCL).  Every rank is handed
+        the same arrays; with ``same_points`` data the ranks split the symmetric unit list and all-reduce
+        the result, otherwise they split the target rows and ``get_result`` gathers them.  Every rank
+        returns the whole (N, E) result."""
         super().__init__(kernel=kernel, dimension=dimension, normalize_rows=normalize_rows, precision=precision)
         if kernel not in _lib.KERNEL_IDS:
             raise NotImplementedError(f"B200Product doesn't support kernel {kernel}.")
@@ -77,6 +83,10 @@ class B200Product(BaseProduct):
         self.path = path
         self.device = torch.device("cuda", int(device))
         self.name = f"B200Product({np.dtype(precision).name}, path={path})"
+        self.comm = TorchDistComm() if distributed else LocalComm()
+        if self.comm.world > 1:
+            self.name = f"B200Product({np.dtype(precision).name}, path={path}, gpus={self.comm.world})"
+        self.path_used = None
         self.workspace = Workspace()
         self.query_ms = None
         self.launches = 0
@@ -105,19 +115,45 @@ class B200Product(BaseProduct):
         """Timed: the whole product, ending with a device synchronise."""
         with torch.cuda.device(self.device):
             with _GpuTimer() as t:
-                self.res_device = kernel_product(
-                    self.target_points,
-                    self.source_points,
-                    self.source_signal,
-                    kernel=self.kernel,
-                    normalize_rows=bool(self.normalize_rows),
-                    density_estimation=self.density_estimation,
-                    path=self.path,
-                    workspace=self.workspace,
-                )
-            self.launches = last_launch_count()
+                if self.comm.world > 1:
+                    self._query_distributed()
+                else:
+                    self.res_device = kernel_product(
+                        self.target_points,
+                        self.source_points,
+                        self.source_signal,
+                        kernel=self.kernel,
+                        normalize_rows=bool(self.normalize_rows),
+                        density_estimation=self.density_estimation,
+                        path=self.path,
+                        workspace=self.workspace,
+                    )
+                    self.path_used = _product.last_path
+                    self.launches = last_launch_count()
             torch.cuda.synchronize(self.device)
         self.query_ms = t.ms()
+
+    def _query_distributed(self):
+        """world > 1.  same_points + Gaussian + D <= 3: this rank's range of the symmetric unit list, then
+        one all-reduce of N floats.  Otherwise: this rank's block of target rows, gathered afterwards."""
+        rank, world = self.comm.rank, self.comm.world
+        y, b = self.source_points, self.source_signal
+        E = 1 if self.density_estimation else b.shape[1]
+        sym = (self.path == "auto" and self.same_points and y.shape[0] >= _product.SYM_MIN_POINTS and
+               _product.symmetric_applies(y, y, self.kernel, bool(self.normalize_rows), self.density_estimation, E))
+        if sym:
+            self.res_device = kernel_product_sym_part(y, b, rank, world, workspace=self.workspace)
+            self.launches = last_launch_count()
+            self.comm.all_reduce(self.res_device)
+            self.path_used = "direct_sym"
+            return
+        lo, hi, _ = shard_bounds(self.target_points.shape[0], rank, world)
+        mine = kernel_product(self.target_points[lo:hi], y, b, kernel=self.kernel, normalize_rows=bool(self.normalize_rows),
+                              density_estimation=self.density_estimation, path=self.path, row_offset=lo,
+                              workspace=self.workspace)
+        self.launches = last_launch_count()
+        self.path_used = _product.last_path
+        self.res_device = self.comm.all_gather(mine, self.target_points.shape[0])
 
     def get_result(self):
         """Untimed device->host copy; float64 contiguous as base.py:116."""
@@ -134,6 +170,7 @@ class B200Product(BaseProduct):
             "gpairs_per_s": pairs / (self.query_ms * 1e-3) / 1e9,
             "gpu_launches": int(self.launches),
             "path": self.path,
+            "path_used": str(self.path_used),
             "form": self._form(),
         }
 
@@ -169,7 +206,7 @@ class B200Solver(BaseSolver):
     """
 
     def __init__(self, *, kernel, dimension, normalize_rows=False, precision="float32", lam=0.0, rtol=1e-6,
-                 max_iter=500, path="auto", device=0):
+                 max_iter=500, path="auto", device=0, distributed=False):
         super().__init__(kernel=kernel, dimension=dimension, normalize_rows=normalize_rows, precision=precision)
         if kernel not in _lib.KERNEL_IDS:
             raise NotImplementedError(f"B200Solver doesn't support kernel {kernel}.")
@@ -178,6 +215,7 @@ class B200Solver(BaseSolver):
         if not torch.cuda.is_available():
             raise RuntimeError("B200Solver needs a CUDA device; there is no CPU fallback.")
         self.lam, self.rtol, self.max_iter, self.path = float(lam), float(rtol), int(max_iter), path
+        self.comm = TorchDistComm() if distributed else LocalComm()
         self.device = torch.device("cuda", int(device))
         self.precision_name = np.dtype(precision).name
         self._set_name()
@@ -201,24 +239,50 @@ class B200Solver(BaseSolver):
         torch.cuda.synchronize(self.device)
 
     def fit(self):
-        n = self.source_points.shape[0]
-        self.ops = CudaShardOps(self.source_points, self.kernel, 0, n, path=self.path)
+        """Timed.  Nothing to factorise: the system is applied through the on-the-fly product."""
+        self._ops = {}
         torch.cuda.synchronize(self.device)
+
+    def _ops_for(self, E):
+        """The matvec of the solve always has targets == sources: the symmetric product applies whenever
+        the kernel is Gaussian, D <= 3 and there is one right-hand side (every rank then holds all CG
+        vectors and the ranks share the unit list); otherwise the rows of the system are sharded."""
+        n = self.source_points.shape[0]
+        symmetric = self.path == "auto" and CudaSymmetricOps.applies(self.source_points, self.kernel, E)
+        key = "symmetric" if symmetric else "rows"
+        if key not in self._ops:
+            if symmetric:
+                self._ops[key] = CudaSymmetricOps(self.source_points, self.kernel, self.comm)
+            else:
+                lo, hi, _ = shard_bounds(n, self.comm.rank, self.comm.world)
+                self.rows = (lo, hi)
+                self._ops[key] = CudaShardOps(self.source_points, self.kernel, lo, hi, path=self.path)
+        self.symmetric, self.ops = symmetric, self._ops[key]
+        return self.ops
 
     def prepare_query(self, *, target_signal):
         self.target_signal = _to_device(target_signal, self.device)
         torch.cuda.synchronize(self.device)
 
     def query(self):
+        n = self.source_points.shape[0]
         with torch.cuda.device(self.device):
             with _GpuTimer() as t:
-                self.info = cg_solve(self.ops, LocalComm(), self.target_signal, self.source_points.shape[0],
-                                     lam=self.lam, rtol=self.rtol, max_iter=self.max_iter)
+                self._ops_for(self.target_signal.shape[1])
+                if self.symmetric:  # replicated vectors; the only collective is inside ops.matvec
+                    self.info = cg_solve(self.ops, LocalComm(), self.target_signal, n, lam=self.lam, rtol=self.rtol,
+                                         max_iter=self.max_iter)
+                    self.x_full = self.info.x
+                else:
+                    lo, hi = self.rows
+                    self.info = cg_solve(self.ops, self.comm, self.target_signal[lo:hi].contiguous(), n, lam=self.lam,
+                                         rtol=self.rtol, max_iter=self.max_iter)
+                    self.x_full = self.comm.all_gather(self.info.x, n)
             torch.cuda.synchronize(self.device)
         self.query_ms = t.ms()
 
     def get_result(self):
-        self.res = self.info.x.cpu().numpy()
+        self.res = self.x_full.cpu().numpy()
         return np.ascontiguousarray(self.res, dtype=np.float64)
 
     def get_additional(self):
@@ -229,6 +293,7 @@ class B200Solver(BaseSolver):
             "cg_iterations": int(self.info.iterations),
             "cg_rel_residual": float(self.info.rel_residual),
             "cg_converged": bool(self.info.converged),
+            "matvec": "symmetric" if self.symmetric else "rows",
             "gpu_launches": int(self.ops.launches),
         }
 
@@ -236,7 +301,7 @@ class B200Solver(BaseSolver):
         return super().get_memory_usage() + torch.cuda.memory_allocated(self.device) / 1024
 
     def done(self):
-        for k in ("source_points", "target_signal", "ops"):
+        for k in ("source_points", "target_signal", "ops", "_ops", "x_full"):
             self.__dict__.pop(k, None)
 
     def __del__(self):

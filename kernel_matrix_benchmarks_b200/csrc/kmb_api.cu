@@ -174,8 +174,8 @@ static int check_product_args(int64_t N, int64_t M, int D, int E, int kid, int f
     if (path < KMB_PATH_AUTO || path > KMB_PATH_DIRECT_SYM) return set_error(KMB_ERR_INVALID, "unknown path %d", path);
     if (path == KMB_PATH_DIRECT_SYM) {
         if (N != M) return set_error(KMB_ERR_INVALID, "the symmetric path needs targets == sources (N=%lld, M=%lld)", (long long)N, (long long)M);
-        if (kid != KMB_KERNEL_GAUSSIAN || flags != 0 || E != 1 || !sym_supported(D))
-            return set_error(KMB_ERR_UNSUPPORTED, "the symmetric path covers the plain Gaussian product with D <= 3, E = 1");
+        if (kid != KMB_KERNEL_GAUSSIAN || (flags & KMB_FLAG_NORMALIZE_ROWS) || E != 1 || !sym_supported(D))
+            return set_error(KMB_ERR_UNSUPPORTED, "the symmetric path covers the plain Gaussian product / density with D <= 3, E = 1");
     }
     return KMB_OK;
 }
@@ -398,7 +398,7 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
 
     if (p == KMB_PATH_DIRECT_SYM) {
         if (x != y) return set_error(KMB_ERR_INVALID, "the symmetric path needs x == y (same_points)");
-        return kmb_product_sym_f32(y, b, out, N, D, kernel_id, 0, 1, workspace, workspace_bytes, stream_);
+        return kmb_product_sym_f32(y, density ? nullptr : b, out, N, D, kernel_id, 0, 1, workspace, workspace_bytes, stream_);
     }
     DirectPlan pl;
     if (int rc = plan_direct(N, M, D, E, kernel_id, flags, p, &pl)) return rc;
@@ -423,7 +423,7 @@ int kmb_product_sym_f32(const float* y, const float* b, float* out, int64_t n, i
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (n < 1 || D < 1) return set_error(KMB_ERR_INVALID, "bad sizes n=%lld D=%d", (long long)n, D);
     if (kernel_id != KMB_KERNEL_GAUSSIAN) return set_error(KMB_ERR_UNSUPPORTED, "the symmetric path covers the Gaussian kernel only");
-    if (!y || !b || !out) return set_error(KMB_ERR_INVALID, "y, b and out must not be NULL");
+    if (!y || !out) return set_error(KMB_ERR_INVALID, "y and out must not be NULL");   // b == NULL: density (b == 1)
     SymPlan sp;
     if (int rc = plan_sym(n, D, part, n_parts, &sp)) return rc;
     if (!workspace || workspace_bytes < sp.total_bytes)

@@ -35,8 +35,12 @@ int sym_launch_of(SymParams P, cudaStream_t stream) {
     return KMB_OK;
 }
 
-using Sym2 = SymCfg<2>;
-using Sym3 = SymCfg<3>;
+// Production shape (tools/tune_sym.cu on B200, profiles/r1_tune_sym.log): 512 consumer threads x 8 rows,
+// one CTA per SM, butterflies of 16 sources, every exponential on the MUFU pipe -- 13.1 kernel
+// evaluations/clk/SM = 26 pairs/clk/SM at N = 10^6 (4 rows x 2 CTAs/SM: 12.5; with 1/16 of the
+// exponentials on the FMA pipe: 12.0 -- here the FMA pipe and the issue slots are the scarce resource).
+using Sym2 = SymCfg<2, 0, 1, 16, 512, 8, 4>;
+using Sym3 = SymCfg<3, 0, 1, 16, 512, 8, 4>;
 
 }  // namespace
 

@@ -56,21 +56,22 @@ __host__ __device__ __forceinline__ int sym_tile_of(long long u, long long nsb, 
     return static_cast<int>(I);
 }
 
-template <int DP_, int POLY_ = 16, int MINB_ = 2>
+// POLY_: every POLY_-th exponential on the FMA pipe (see DirectCfg); CH_: sources per shuffle butterfly
+template <int DP_, int POLY_ = 16, int MINB_ = 2, int CH_ = 8, int CONSUMERS_ = 512, int R_ = 4, int STAGES_ = 4>
 struct SymCfg {
-    static constexpr int DP = DP_, POLY = POLY_, MINB = MINB_;
-    static constexpr int R = 4, RP = 2, CONSUMERS = 512, THREADS = CONSUMERS + 32, WARPS = CONSUMERS / 32;
+    static constexpr int DP = DP_, POLY = POLY_, MINB = MINB_, CH = CH_;
+    static constexpr int R = R_, RP = R_ / 2, CONSUMERS = CONSUMERS_, THREADS = CONSUMERS + 32, WARPS = CONSUMERS / 32;
+    static_assert(R % 2 == 0 && (CH == 8 || CH == 16), "rows are processed as packed pairs; butterflies of 8 or 16 sources");
     static constexpr int TILE_ROWS = CONSUMERS * R;
-    static constexpr int STAGES = 4;
+    static constexpr int STAGES = STAGES_;
     static constexpr int PAIRS = DP + 1, RECV = (PAIRS + 1) / 2;
     static_assert(RECV == 2, "32-byte records (D <= 3, E = 1)");
     static constexpr int SB = 512;
-    static_assert(SB == CONSUMERS, "one thread per source when the warps' column sums are combined");
+    static_assert(SB % CONSUMERS == 0 && TILE_ROWS % SB == 0, "whole sources per thread when the warps' column sums are combined");
     static constexpr int TB = TILE_ROWS / SB;
     static constexpr int STAGE_BYTES = SB * RECV * 16;
     static constexpr int COLBUF_BYTES = WARPS * SB * 4;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + COLBUF_BYTES + 2 * STAGES * 8 + 16;
-    static constexpr int CH = 8;   // sources per shuffle butterfly
 };
 
 template <class C>
@@ -124,10 +125,11 @@ kprod_sym_kernel(const SymParams P) {
 
     // -------------------------------- consumers --------------------------------
     const int lane = tid & 31, warp = tid >> 5;
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-    const int jl = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);   // the source of a chunk this lane ends up holding
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+    // the source of a chunk this lane ends up holding, and whether it is the lane that stores it
+    const int jl = CH == 16 ? (h16 ? 8 : 0) + (h8 ? 4 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0) : (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
     float* my_col = colbuf + warp * SB + jl;
-    const bool col_writer = (lane & 3) == 0;
+    const bool col_writer = CH == 16 ? (lane & 1) == 0 : (lane & 3) == 0;
 
     uint32_t it = 0;
     long long u = u0;
@@ -208,22 +210,45 @@ kprod_sym_kernel(const SymParams P) {
                         for (int p = 1; p < RP; ++p) tt = fma2(kv[p], w[p], tt);
                         t[c] = tt.x + tt.y;
                     }
-                    // transposing butterfly: after the xor-16/8/4 steps each lane keeps one of the CH columns
-                    float s4[4], s2[2];
+                    // transposing butterfly: each xor step halves the columns a lane carries, until one is left
+                    float cs;
+                    if constexpr (CH == 16) {
+                        float s8[8], s4[4], s2[2];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float send = h16 ? t[q] : t[q + 4], keep = h16 ? t[q + 4] : t[q];
-                        s4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
+                        for (int q = 0; q < 8; ++q) {
+                            const float send = h16 ? t[q] : t[q + 8], keep = h16 ? t[q + 8] : t[q];
+                            s8[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const float send = h8 ? s4[q] : s4[q + 2], keep = h8 ? s4[q + 2] : s4[q];
-                        s2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        for (int q = 0; q < 4; ++q) {
+                            const float send = h8 ? s8[q] : s8[q + 4], keep = h8 ? s8[q + 4] : s8[q];
+                            s4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const float send = h4 ? s4[q] : s4[q + 2], keep = h4 ? s4[q + 2] : s4[q];
+                            s2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        }
+                        const float send = h2 ? s2[0] : s2[1], keep = h2 ? s2[1] : s2[0];
+                        cs = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                        cs += __shfl_xor_sync(0xffffffffu, cs, 1);
+                    } else {
+                        float s4[4], s2[2];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float send = h16 ? t[q] : t[q + 4], keep = h16 ? t[q + 4] : t[q];
+                            s4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const float send = h8 ? s4[q] : s4[q + 2], keep = h8 ? s4[q + 2] : s4[q];
+                            s2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        }
+                        const float send = h4 ? s2[0] : s2[1], keep = h4 ? s2[1] : s2[0];
+                        cs = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        cs += __shfl_xor_sync(0xffffffffu, cs, 2);
+                        cs += __shfl_xor_sync(0xffffffffu, cs, 1);
                     }
-                    const float send = h4 ? s2[0] : s2[1], keep = h4 ? s2[1] : s2[0];
-                    float cs = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    cs += __shfl_xor_sync(0xffffffffu, cs, 2);
-                    cs += __shfl_xor_sync(0xffffffffu, cs, 1);
                     if (col_writer) my_col[j] = cs;
                 }
             }
@@ -238,10 +263,13 @@ kprod_sym_kernel(const SymParams P) {
             if (off_diagonal) {
                 // the 16 warps' column sums of this unit -> one value per source -> colpart[tile][source]
                 named_bar_sync(1, C::CONSUMERS);
-                float cs = 0.f;
 #pragma unroll
-                for (int wv = 0; wv < C::WARPS; ++wv) cs += colbuf[wv * SB + tid];
-                P.colpart[static_cast<size_t>(tile) * P.N_pad + jb * SB + tid] = cs;
+                for (int sidx = tid; sidx < SB; sidx += C::CONSUMERS) {
+                    float cs = 0.f;
+#pragma unroll
+                    for (int wv = 0; wv < C::WARPS; ++wv) cs += colbuf[wv * SB + sidx];
+                    P.colpart[static_cast<size_t>(tile) * P.N_pad + jb * SB + sidx] = cs;
+                }
                 named_bar_sync(1, C::CONSUMERS);
             }
         }

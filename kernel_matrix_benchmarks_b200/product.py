@@ -43,13 +43,16 @@ _default_ws = {}
 
 # below this many points the symmetric kernel's extra passes (column-sum buffers, combine kernel) cost
 # more than the exponentials it saves
-SYM_MIN_POINTS = 16384
+SYM_MIN_POINTS = 32768
 
 
-def _symmetric_applies(x, y, kernel, normalize_rows, density_estimation, E):
-    """targets *are* the sources (same tensor), plain Gaussian product, D <= 3, E == 1."""
+last_path = None  # the path the last kernel_product call asked the library for ("auto" resolved to "direct_sym" or left to C)
+
+
+def symmetric_applies(x, y, kernel, normalize_rows=False, density_estimation=False, E=1):
+    """targets *are* the sources (same tensor), plain Gaussian product or density, D <= 3, E == 1."""
     return (x.data_ptr() == y.data_ptr() and x.shape == y.shape and kernel == "gaussian" and not normalize_rows
-            and not density_estimation and E == 1 and x.shape[1] <= 3)
+            and E == 1 and x.shape[1] <= 3)
 
 
 def kernel_product(x, y, b, *, kernel="gaussian", normalize_rows=False, density_estimation=False, path="auto",
@@ -78,8 +81,10 @@ def kernel_product(x, y, b, *, kernel="gaussian", normalize_rows=False, density_
         out = torch.empty((N, E), dtype=torch.float32, device=x.device)
     else:
         _check_f32("out", out, E)
-    if path == "auto" and N >= SYM_MIN_POINTS and _symmetric_applies(x, y, kernel, normalize_rows, density_estimation, E):
+    if path == "auto" and N >= SYM_MIN_POINTS and symmetric_applies(x, y, kernel, normalize_rows, density_estimation, E):
         path = "direct_sym"  # same_points: each kernel value serves its row and its column (kprod_sym.cuh)
+    global last_path
+    last_path = path
     kid, pid = _lib.KERNEL_IDS[kernel], _lib.PATH_IDS[path]
     need = ctypes.c_size_t(0)
     _lib.check(lib.kmb_product_workspace_bytes(N, M, D, E, kid, flags, pid, ctypes.byref(need)))
@@ -100,10 +105,11 @@ def kernel_product_sym_part(y, b, part, n_parts, *, out=None, workspace=None):
     """
     lib = _lib.load()
     _check_f32("points", y)
-    _check_f32("signal", b, 1)
     n, D = y.shape
-    if b.shape[0] != n:
-        raise ValueError("signal and points disagree on n")
+    if b is not None:  # None: density estimation (b == 1)
+        _check_f32("signal", b, 1)
+        if b.shape[0] != n:
+            raise ValueError("signal and points disagree on n")
     if out is None:
         out = torch.empty((n, 1), dtype=torch.float32, device=y.device)
     else:

@@ -30,7 +30,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from .product import Workspace, _ptr, _stream, kernel_product
+from .product import SYM_MIN_POINTS, Workspace, _ptr, _stream, kernel_product, kernel_product_sym_part, symmetric_applies
 
 
 def shard_bounds(n, rank, world):
@@ -128,6 +128,36 @@ class CudaShardOps:
         _lib.check(self.lib.kmb_cg_direction_f32(_ptr(p), _ptr(r), _ptr(rs_new), _ptr(rs), self.n_local, p.shape[1],
                                                  _stream()))
         self.launches += 1
+
+
+class CudaSymmetricOps(CudaShardOps):
+    """CG on the symmetric product (kprod_sym): the kernel solve always has targets == sources, so
+    every kernel value can serve its row and its column.  The work of one matvec is the triangular
+    unit list, cut into ``world`` equal ranges; rank r evaluates range r and the ranks' partial
+    results are summed with ONE all-reduce of N floats -- that is the exchange step of this mode
+    (instead of the all-gather of p of the row-sharded mode).  All CG vectors are replicated (N floats
+    each: their updates cost microseconds), so no other collective is needed and every rank holds the
+    whole solution.  Use with ``LocalComm`` in ``cg_solve``: ``dist_comm`` is only used inside matvec.
+    """
+
+    def __init__(self, points, kernel, dist_comm=None):
+        n = points.shape[0]
+        super().__init__(points, kernel, 0, n)
+        if not self.applies(points, kernel):
+            raise NotImplementedError("the symmetric matvec covers the Gaussian kernel with D <= 3")
+        self.dist_comm = dist_comm if dist_comm is not None else LocalComm()
+
+    @staticmethod
+    def applies(points, kernel, E=1):
+        return points.shape[0] >= SYM_MIN_POINTS and symmetric_applies(points, points, kernel, E=E)
+
+    def matvec(self, p_full):
+        if p_full.shape[1] != 1:
+            raise NotImplementedError("the symmetric matvec takes one right-hand side")
+        kernel_product_sym_part(self.y, p_full, self.dist_comm.rank, self.dist_comm.world, out=self.Ap, workspace=self.ws)
+        self.launches += int(self.lib.kmb_last_launch_count())
+        self.dist_comm.all_reduce(self.Ap)
+        return self.Ap
 
 
 @dataclass

@@ -324,3 +324,92 @@ def test_tensor_pv_lazy_rescale(kernel):
     want = orc.kernel_product(kernel, y, x, b, normalize_rows=True)
     assert np.isfinite(out).all()
     assert orc.rel_l2(out, want) <= 5e-4  # |u||v| ~ 1e4 here: the 3xTF32 cancellation error of d^2 is ~1e-2
+
+
+# ---- symmetric (same_points) Gaussian product: kprod_sym --------------------------------------------
+
+def _sym_case(n, D, radius=1.0):
+    from kernel_matrix_benchmarks_b200 import datasets
+
+    ds = datasets.uniform_cube(n, D, radius, "gaussian")
+    rows = np.unique(np.concatenate([np.arange(0, n, max(1, n // 192)), [0, n - 1, n // 2]]))
+    want = orc.kernel_product("gaussian", ds.source_points, None, ds.source_signal, rows=rows)
+    return ds, rows, want
+
+
+@pytest.mark.parametrize("n, D", [(300, 3), (4096, 2), (5000, 1), (40000, 3), (65553, 2), (131072 + 5, 3)])
+def test_symmetric_product_matches_oracle(n, D):
+    """kmb_product_f32(path=DIRECT_SYM) == K b of bruteforce.py:25-58,153 with target_points=None."""
+    import torch
+    from kernel_matrix_benchmarks_b200 import product
+
+    ds, rows, want = _sym_case(n, D)
+    y = torch.tensor(ds.source_points, dtype=torch.float32, device="cuda")
+    b = torch.tensor(ds.source_signal, dtype=torch.float32, device="cuda")
+    got = product.kernel_product(y, y, b, path="direct_sym").cpu().numpy().astype(np.float64)
+    assert got.shape == (n, 1)
+    assert orc.rel_l2(got[rows], want) <= TOL_DIRECT
+    # row-by-row against the general kernel on all rows (catches a wrong tile / column block)
+    ref = product.kernel_product(y, y, b, path="direct").cpu().numpy().astype(np.float64)
+    assert np.max(np.abs(got - ref)) <= 2e-5 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("n_parts", [2, 3, 8])
+def test_symmetric_parts_add_up(n_parts):
+    """The unit list cut into n_parts ranges (one per GPU): the partial outputs sum to the product."""
+    import torch
+    from kernel_matrix_benchmarks_b200 import product
+
+    ds, rows, want = _sym_case(50000, 3)
+    y = torch.tensor(ds.source_points, dtype=torch.float32, device="cuda")
+    b = torch.tensor(ds.source_signal, dtype=torch.float32, device="cuda")
+    total = torch.zeros((ds.N, 1), dtype=torch.float64, device="cuda")
+    for part in range(n_parts):
+        total += product.kernel_product_sym_part(y, b, part, n_parts).double()
+    assert orc.rel_l2(total.cpu().numpy()[rows], want) <= TOL_DIRECT
+
+
+def test_symmetric_falls_back_to_difference_form_on_spread_data():
+    import torch
+    from kernel_matrix_benchmarks_b200 import product
+
+    ds, rows, want = _sym_case(20000, 3, radius=6.0)
+    y = torch.tensor(ds.source_points, dtype=torch.float32, device="cuda")
+    b = torch.tensor(ds.source_signal, dtype=torch.float32, device="cuda")
+    got = product.kernel_product(y, y, b, path="direct_sym").cpu().numpy().astype(np.float64)
+    assert product.direct_stats()["form"] == "difference"
+    assert orc.rel_l2(got[rows], want) <= TOL_DIRECT
+    parts = sum(product.kernel_product_sym_part(y, b, p, 3).double() for p in range(3)).cpu().numpy()
+    assert orc.rel_l2(parts[rows], want) <= TOL_DIRECT
+
+
+def test_symmetric_is_deterministic_and_checks_its_arguments():
+    import torch
+    from kernel_matrix_benchmarks_b200 import _lib, product
+
+    ds, _, _ = _sym_case(40000, 3)
+    y = torch.tensor(ds.source_points, dtype=torch.float32, device="cuda")
+    b = torch.tensor(ds.source_signal, dtype=torch.float32, device="cuda")
+    a1 = product.kernel_product(y, y, b, path="direct_sym").clone()
+    a2 = product.kernel_product(y, y, b, path="direct_sym").clone()
+    assert torch.equal(a1, a2)
+    with pytest.raises(ValueError):  # a copy of the points is not "the same points"
+        product.kernel_product(y.clone(), y, b, path="direct_sym")
+    with pytest.raises(NotImplementedError):
+        product.kernel_product(y, y, b, kernel="absolute-exponential", path="direct_sym")
+    need = ctypes.c_size_t(0)
+    lib = _lib.load()
+    assert lib.kmb_product_sym_workspace_bytes(40000, 4, 0, 1, ctypes.byref(need)) == _lib.KMB_ERR_UNSUPPORTED
+    assert lib.kmb_product_sym_workspace_bytes(40000, 3, 2, 2, ctypes.byref(need)) == _lib.KMB_ERR_INVALID
+
+
+def test_plugin_takes_the_symmetric_path_for_same_points():
+    """runner.py passes same_points=True together with target_points == source_points (runner.py:77-84)."""
+    ds, rows, want = _sym_case(40000, 3)
+    out, extra = run_plugin("gaussian", ds.source_points, ds.source_points, ds.source_signal, same_points=True)
+    assert extra["path_used"] == "direct_sym" and extra["form"] == "product"
+    assert orc.rel_l2(out[rows], want) <= TOL_DIRECT
+    # without the flag the arrays are copied separately and the general kernel runs
+    out2, extra2 = run_plugin("gaussian", ds.source_points, ds.source_points.copy(), ds.source_signal, same_points=False)
+    assert extra2["path_used"] != "direct_sym"
+    assert orc.rel_l2(out2[rows], want) <= TOL_DIRECT

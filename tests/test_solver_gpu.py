@@ -63,3 +63,28 @@ def test_cg_zero_rhs_returns_zero():
     pts = np.random.RandomState(0).rand(500, 3)
     x, extra = run_solver("gaussian", pts, np.zeros((500, 1)), lam=1.0)
     assert np.array_equal(x, np.zeros((500, 1))) and extra["cg_iterations"] == 0
+
+
+def test_cg_symmetric_matvec_agrees_with_row_matvec():
+    """N >= 32768, Gaussian, D = 3: the solver takes the symmetric product (kprod_sym) as its matvec."""
+    from kernel_matrix_benchmarks_b200 import datasets
+
+    n, lam = 40000, 1.0
+    ds = datasets.uniform_cube(n, 3, 1.0, "gaussian", "solver")
+    rows = np.arange(0, n, 200)
+    import torch
+    from kernel_matrix_benchmarks_b200 import product
+
+    y = torch.tensor(ds.source_points, dtype=torch.float32, device="cuda")
+    b = torch.tensor(ds.source_signal, dtype=torch.float32, device="cuda")
+    rhs = (product.kernel_product(y, y, b, path="direct") + lam * b).cpu().numpy().astype(np.float64)
+    x_sym, e_sym = run_solver("gaussian", ds.source_points, rhs, lam=lam, rtol=1e-6)
+    x_row, e_row = run_solver("gaussian", ds.source_points, rhs, lam=lam, rtol=1e-6, path="direct")
+    assert e_sym["matvec"] == "symmetric" and e_row["matvec"] == "rows"
+    assert e_sym["cg_converged"] and e_row["cg_converged"]
+    assert abs(e_sym["cg_iterations"] - e_row["cg_iterations"]) <= 2
+    assert orc.rel_l2(x_sym, x_row) <= 1e-4
+    assert orc.rel_l2(x_sym, ds.source_signal) <= 5e-4
+    # residual on sampled rows with the float64 oracle product
+    want = orc.kernel_product("gaussian", ds.source_points, None, x_sym, rows=rows) + lam * x_sym[rows]
+    assert orc.rel_l2(want, rhs[rows]) <= 2e-5

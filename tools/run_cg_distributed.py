@@ -2,11 +2,14 @@
 """Sharded CG solve under torchrun (one process per GPU, NCCL): config C5 semantics at a chosen N.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P \
-        tools/run_cg_distributed.py [N] [lam]
+        tools/run_cg_distributed.py [N] [lam] [rows|symmetric]
 
-Every rank owns a contiguous block of rows of x, r, p, Ap; each iteration all-gathers p and all-reduces
-two scalars (kernel_matrix_benchmarks_b200/solver.py).  Rank 0 prints one JSON line with the iteration
-count, the device time per iteration (max over ranks) and the error against the generating signal.
+rows:      every rank owns a contiguous block of rows of x, r, p, Ap; each iteration all-gathers p and
+           all-reduces two scalars (solver.CudaShardOps + TorchDistComm).
+symmetric: (default) the matvec is the symmetric product -- the ranks split its triangular unit list and
+           all-reduce the N-float result; the CG vectors are replicated (solver.CudaSymmetricOps).
+Rank 0 prints one JSON line with the iteration count, the device time per iteration (max over ranks)
+and the error against the generating signal.
 """
 import json
 import os
@@ -20,12 +23,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from kernel_matrix_benchmarks_b200 import datasets  # noqa: E402
 from kernel_matrix_benchmarks_b200.product import kernel_product  # noqa: E402
-from kernel_matrix_benchmarks_b200.solver import CudaShardOps, LocalComm, TorchDistComm, cg_solve, shard_bounds  # noqa: E402
+from kernel_matrix_benchmarks_b200.solver import (CudaShardOps, CudaSymmetricOps, LocalComm, TorchDistComm, cg_solve,  # noqa: E402
+                                                  shard_bounds)
 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
     lam = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+    mode = sys.argv[3] if len(sys.argv) > 3 else "symmetric"
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -39,23 +44,29 @@ def main():
     lo, hi, _ = shard_bounds(n, rank, world)
     # this rank's rows of the right-hand side a = K b + lam b
     rhs = kernel_product(y[lo:hi], y, b, row_offset=lo) + lam * b[lo:hi]
-    ops = CudaShardOps(y, "gaussian", lo, hi)
+    if mode == "symmetric":
+        rhs = comm.all_gather(rhs, n).clone()   # replicated right-hand side
+        ops, loop_comm = CudaSymmetricOps(y, "gaussian", comm), LocalComm()
+        lo, hi = 0, n
+    else:
+        ops, loop_comm = CudaShardOps(y, "gaussian", lo, hi, path="direct"), comm
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    res = cg_solve(ops, comm, rhs, n, lam=lam, rtol=1e-6, max_iter=500)
+    res = cg_solve(ops, loop_comm, rhs, n, lam=lam, rtol=1e-6, max_iter=500)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     err2 = ((res.x - b[lo:hi]) ** 2).sum().double().reshape(1)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(err2)
+        if mode != "symmetric":
+            dist.all_reduce(err2)
     if rank == 0:
         it = max(1, res.iterations)
-        print(json.dumps({"config": "C5-sharded", "N": n, "n_gpus": world, "lam": lam, "cg_iterations": res.iterations,
+        print(json.dumps({"config": "C5-sharded", "matvec": mode, "N": n, "n_gpus": world, "lam": lam, "cg_iterations": res.iterations,
                           "converged": res.converged, "rel_residual": res.rel_residual, "total_ms": float(ms),
                           "ms_per_iteration": float(ms) / it,
                           "matvec_gpairs_per_s": float(n) * n * it / (float(ms) * 1e-3) / 1e9,
