@@ -107,7 +107,8 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
         }
     } else if (warp == 1) {
         // ------------------------------------- MMA issuer -------------------------------------
-        if (lane == 0) {
+        // all 32 lanes walk the loop and wait on the barriers; one elected lane issues (see elect_one)
+        {
             uint32_t it = 0, unit = 0;
             for (long long u = u0; u < u1; ++u, ++unit) {
                 const int a = unit % ACC_STAGES;
@@ -119,20 +120,24 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
                     mbar_wait(&full_bar[stage], (it / STAGES) & 1);
                     tc_fence_after();
                     const unsigned char* st = stages + stage * STAGE_BYTES;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < TK / UMMA_K; ++k) {
-                        const uint64_t ah = umma_desc_sw128(st + 0 * TILE_BYTES, k * UMMA_K * 4);
-                        const uint64_t al = umma_desc_sw128(st + 1 * TILE_BYTES, k * UMMA_K * 4);
-                        const uint64_t bh = umma_desc_sw128(st + 2 * TILE_BYTES, k * UMMA_K * 4);
-                        const uint64_t bl = umma_desc_sw128(st + 3 * TILE_BYTES, k * UMMA_K * 4);
-                        // 3xTF32: the two small cross terms first, then hi.hi
-                        umma_tf32(d_tmem, al, bh, idesc_tf32(TN), (kb | k) != 0);
-                        umma_tf32(d_tmem, ah, bl, idesc_tf32(TN), 1);
-                        umma_tf32(d_tmem, ah, bh, idesc_tf32(TN), 1);
+                        for (int k = 0; k < TK / UMMA_K; ++k) {
+                            const uint64_t ah = umma_desc_sw128(st + 0 * TILE_BYTES, k * UMMA_K * 4);
+                            const uint64_t al = umma_desc_sw128(st + 1 * TILE_BYTES, k * UMMA_K * 4);
+                            const uint64_t bh = umma_desc_sw128(st + 2 * TILE_BYTES, k * UMMA_K * 4);
+                            const uint64_t bl = umma_desc_sw128(st + 3 * TILE_BYTES, k * UMMA_K * 4);
+                            // 3xTF32: the two small cross terms first, then hi.hi
+                            umma_tf32(d_tmem, al, bh, idesc_tf32(TN), (kb | k) != 0);
+                            umma_tf32(d_tmem, ah, bl, idesc_tf32(TN), 1);
+                            umma_tf32(d_tmem, ah, bh, idesc_tf32(TN), 1);
+                        }
+                        umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
                     }
-                    umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+                    __syncwarp();
                 }
-                umma_commit(&acc_full[a]);           // accumulator complete
+                if (elect_one()) umma_commit(&acc_full[a]);   // accumulator complete
+                __syncwarp();
             }
         }
     } else {

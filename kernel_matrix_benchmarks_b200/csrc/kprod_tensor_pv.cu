@@ -8,6 +8,11 @@
 //   O += P.B      tcgen05.mma with A = P from TMEM (hi, lo), B = transposed signal tile (hi, lo) from
 //                 shared memory, accumulator O (128 x E) in TMEM; read once per row tile
 //
+// The epilogue is the critical resource (MUFU + the hi/lo split, ~12 instructions per kernel value against
+// 48 MMAs of 32 cycles per 128 x 64 tile), so it is spread over NG groups of four warps: group g owns
+// columns [g TN/NG, (g+1) TN/NG) of every S tile (all 128 rows: TMEM lane quarter = warp % 4), the groups
+// agree on the row maximum through shared memory, and each one rescales / stores its own share of O.
+//
 // TMEM columns: S stage 0 [0,64) | S stage 1 [64,128) | P hi [128,192) | P lo [192,256) | O [256,256+E).
 // Warp roles and the stream-K work split are those of kprod_tensor.cu.
 #include <algorithm>
@@ -23,16 +28,25 @@ constexpr int TN = 64;                 // sources per S tile
 constexpr int SLOT_BYTES = 16384;      // ring slot: v tile hi+lo of one K block, or one half (hi / lo) of a signal tile
 constexpr int HALF_SLOT = SLOT_BYTES / 2;
 constexpr int A_TILE_BYTES = TM * TK * 4;   // 16 KB
-constexpr int EPI_THREADS = 128;
+constexpr int NG = 4;                  // epilogue column groups (4 warps each)
+constexpr int CPT = TN / NG;           // S columns per epilogue thread
+constexpr int EPI_WARPS = 4 * NG;
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
 constexpr int THREADS = 64 + EPI_THREADS;
+static_assert(CPT % 16 == 0, "tcgen05.ld/st in 16-column chunks");
 constexpr int TMEM_COLS = 512;
 constexpr int COL_S = 0, COL_PH = 128, COL_PL = 192, COL_O = 256;
+constexpr int COL_UH = 320, COL_UL = 384;   // u tile (hi, lo) when D <= 64: A operand of the S MMAs from tensor memory
+constexpr int U_TMEM_MAX_D = 0;   // 64 enables the TMEM-resident u tile (experimental: not faster on B200 yet, one parity failure)
 constexpr int MAX_EB = 64;             // signal columns per pass
 constexpr float kLazyRescale = 64.f;   // rescale O only when the row maximum grows by more than 2^64
 
 struct Params {
     const float* un;
     const float* vn;
+    const float* uh;          // (N, Dp) TF32 hi / lo of the scaled targets (prepass), for the TMEM-resident u tile
+    const float* ul;
+    int Dp, u_in_tmem;
     float* out;
     float* partial;
     int* tile_counter;
@@ -58,9 +72,11 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char* u_region = smem;                                   // kblocks x [A hi 16 KB | A lo 16 KB]
-    unsigned char* ring = u_region + P.kblocks * 2 * A_TILE_BYTES;    // stages x 16 KB
+    unsigned char* ring = u_region + (P.u_in_tmem ? 0 : P.kblocks * 2 * A_TILE_BYTES);    // stages x 16 KB
     float* aux = reinterpret_cast<float*>(ring + P.stages * SLOT_BYTES);   // 2 x TN floats (|v|^2)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux + 2 * TN);
+    float* cmbuf = aux + 2 * TN;                                            // 2 x NG x TM: per-group row maxima of a tile
+    float* ksbuf = cmbuf + 2 * NG * TM;                                     // NG x TM: per-group sums of weights
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ksbuf + NG * TM);
     uint64_t* empty_bar = full_bar + P.stages;
     uint64_t* acc_full = empty_bar + P.stages;
     uint64_t* acc_empty = acc_full + 2;
@@ -68,7 +84,8 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
     uint64_t* u_free = u_full + 1;
     uint64_t* p_ready = u_free + 1;
     uint64_t* p_free = p_ready + 1;
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(p_free + 1);
+    uint64_t* utm_full = p_free + 1;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(utm_full + 1);
     int* s_flag = reinterpret_cast<int*>(tmem_base_smem + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -80,11 +97,12 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
 
     if (tid == 0) {
         for (int s = 0; s < ST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_THREADS / 32); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
         mbar_init(u_full, 1);
         mbar_init(u_free, 1);
-        mbar_init(p_ready, EPI_THREADS / 32);
+        mbar_init(p_ready, EPI_WARPS);
         mbar_init(p_free, 1);
+        mbar_init(utm_full, 4);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
@@ -113,7 +131,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
             long long prev = -1;
             for (long long u = u0; u < u1; ++u) {
                 const int tile = static_cast<int>(u / nsb);
-                if (u == u0 || u % nsb == 0) {   // new row tile: (re)load the resident u tile
+                if (!P.u_in_tmem && (u == u0 || u % nsb == 0)) {   // new row tile: (re)load the resident u tile
                     mbar_wait(u_free, (seg & 1) ^ 1);
                     mbar_arrive_expect_tx(u_full, P.kblocks * 2 * A_TILE_BYTES);
                     for (int kb = 0; kb < P.kblocks; ++kb) {
@@ -138,11 +156,15 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
         }
     } else if (warp == 1) {
         // ------------------------------------- MMA issuer -------------------------------------
-        if (lane == 0) {
+        // All 32 lanes walk the loop and wait on the barriers; one elected lane issues (see elect_one).
+        // Order: S(0), S(1), PV(0), S(2), PV(1), ...; at the first tile of a row segment whose u tile lives
+        // in TMEM the pending PV goes first (the epilogue writes the new u tile only after it has finished
+        // the previous segment, which needs that PV).
+        {
             uint32_t it = 0, n = 0, seg = 0;
+            const uint32_t d_o = tmem_base + COL_O;
             auto issue_pv = [&](uint32_t m, bool first_of_segment) {
                 mbar_wait(p_ready, m & 1);
-                tc_fence_after();
                 const int slot_h = it % ST;
                 mbar_wait(&full_bar[slot_h], (it / ST) & 1);
                 ++it;
@@ -152,26 +174,36 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                 tc_fence_after();
                 const unsigned char* sh = ring + slot_h * SLOT_BYTES;
                 const unsigned char* sl = ring + slot_l * SLOT_BYTES;
-                const uint32_t d_o = tmem_base + COL_O;
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < TN / UMMA_K; ++k) {
-                    const int panel = k >> 2, koff = (k & 3) * UMMA_K * 4;
-                    const uint64_t bh = umma_desc_sw128(sh + panel * HALF_SLOT, koff);
-                    const uint64_t bl = umma_desc_sw128(sl + panel * HALF_SLOT, koff);
-                    const uint32_t a_hi = tmem_base + COL_PH + k * UMMA_K, a_lo = tmem_base + COL_PL + k * UMMA_K;
-                    umma_tf32_ts(d_o, a_lo, bh, idesc_o, !(first_of_segment && k == 0));
-                    umma_tf32_ts(d_o, a_hi, bl, idesc_o, 1);
-                    umma_tf32_ts(d_o, a_hi, bh, idesc_o, 1);
+                    for (int k = 0; k < TN / UMMA_K; ++k) {
+                        const int panel = k >> 2, koff = (k & 3) * UMMA_K * 4;
+                        const uint64_t bh = umma_desc_sw128(sh + panel * HALF_SLOT, koff);
+                        const uint64_t bl = umma_desc_sw128(sl + panel * HALF_SLOT, koff);
+                        const uint32_t a_hi = tmem_base + COL_PH + k * UMMA_K, a_lo = tmem_base + COL_PL + k * UMMA_K;
+                        umma_tf32_ts(d_o, a_lo, bh, idesc_o, !(first_of_segment && k == 0));
+                        umma_tf32_ts(d_o, a_hi, bl, idesc_o, 1);
+                        umma_tf32_ts(d_o, a_hi, bh, idesc_o, 1);
+                    }
+                    umma_commit(&empty_bar[slot_h]);
+                    umma_commit(&empty_bar[slot_l]);
+                    umma_commit(p_free);
                 }
-                umma_commit(&empty_bar[slot_h]);
-                umma_commit(&empty_bar[slot_l]);
-                umma_commit(p_free);
+                __syncwarp();
             };
-            bool prev_first = false;
+            bool prev_first = false, pv_pending = false;
             for (long long u = u0; u < u1; ++u, ++n) {
                 const bool first = (u == u0) || (u % nsb == 0);
                 if (first) {
-                    mbar_wait(u_full, seg & 1);
+                    if (P.u_in_tmem) {
+                        if (pv_pending) {
+                            issue_pv(n - 1, prev_first);
+                            pv_pending = false;
+                        }
+                        mbar_wait(utm_full, seg & 1);
+                    } else {
+                        mbar_wait(u_full, seg & 1);
+                    }
                     ++seg;
                 }
                 const int a = n & 1;
@@ -184,32 +216,63 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                     tc_fence_after();
                     const unsigned char* bt = ring + slot * SLOT_BYTES;
                     const unsigned char* at = u_region + kb * 2 * A_TILE_BYTES;
+                    if (elect_one()) {
+                        if (P.u_in_tmem) {
+                            // A = u tile from tensor memory: only the 2 KB v slice comes from shared memory.
+                            // (An SS tcgen05.mma here fetches 6 KB per 32-cycle MMA and runs at ~107 cycles.)
 #pragma unroll
-                    for (int k = 0; k < TK / UMMA_K; ++k) {
-                        const uint64_t ah = umma_desc_sw128(at, k * UMMA_K * 4);
-                        const uint64_t al = umma_desc_sw128(at + A_TILE_BYTES, k * UMMA_K * 4);
-                        const uint64_t bh = umma_desc_sw128(bt, k * UMMA_K * 4);
-                        const uint64_t bl = umma_desc_sw128(bt + HALF_SLOT, k * UMMA_K * 4);
-                        umma_tf32(d_s, al, bh, idesc_s, (kb | k) != 0);
-                        umma_tf32(d_s, ah, bl, idesc_s, 1);
-                        umma_tf32(d_s, ah, bh, idesc_s, 1);
+                            for (int k = 0; k < TK / UMMA_K; ++k) {
+                                const uint64_t bh = umma_desc_sw128(bt, k * UMMA_K * 4);
+                                const uint64_t bl = umma_desc_sw128(bt + HALF_SLOT, k * UMMA_K * 4);
+                                const uint32_t a_hi = tmem_base + COL_UH + kb * TK + k * UMMA_K;
+                                const uint32_t a_lo = tmem_base + COL_UL + kb * TK + k * UMMA_K;
+                                umma_tf32_ts(d_s, a_lo, bh, idesc_s, (kb | k) != 0);
+                                umma_tf32_ts(d_s, a_hi, bl, idesc_s, 1);
+                                umma_tf32_ts(d_s, a_hi, bh, idesc_s, 1);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < TK / UMMA_K; ++k) {
+                                const uint64_t ah = umma_desc_sw128(at, k * UMMA_K * 4);
+                                const uint64_t al = umma_desc_sw128(at + A_TILE_BYTES, k * UMMA_K * 4);
+                                const uint64_t bh = umma_desc_sw128(bt, k * UMMA_K * 4);
+                                const uint64_t bl = umma_desc_sw128(bt + HALF_SLOT, k * UMMA_K * 4);
+                                umma_tf32(d_s, al, bh, idesc_s, (kb | k) != 0);
+                                umma_tf32(d_s, ah, bl, idesc_s, 1);
+                                umma_tf32(d_s, ah, bh, idesc_s, 1);
+                            }
+                        }
+                        umma_commit(&empty_bar[slot]);
                     }
-                    umma_commit(&empty_bar[slot]);
+                    __syncwarp();
                 }
-                umma_commit(&acc_full[a]);
-                if (u + 1 == u1 || (u + 1) % nsb == 0) umma_commit(u_free);   // last S of this row tile
-                if (n >= 1) issue_pv(n - 1, prev_first);
+                const bool last_of_tile = (u + 1 == u1 || (u + 1) % nsb == 0);
+                if (elect_one()) {
+                    umma_commit(&acc_full[a]);
+                    if (last_of_tile && !P.u_in_tmem) umma_commit(u_free);   // last S of this row tile
+                }
+                __syncwarp();
+                if (pv_pending) issue_pv(n - 1, prev_first);
+                pv_pending = true;
                 prev_first = first;
             }
-            if (n >= 1) issue_pv(n - 1, prev_first);
+            if (pv_pending) issue_pv(n - 1, prev_first);
         }
     } else {
         // -------------------------------------- epilogue --------------------------------------
         const int et = tid - 64;
-        const int lane_group = warp & 3;
+        const int lane_group = warp & 3;             // TMEM lane quarter this warp may touch
+        const int cg = (warp - 2) >> 2;              // column group
+        const int col0 = cg * CPT;                   // first S / P column of this thread
         const int row_in_tile = lane_group * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(lane_group * 32) << 16;
         uint32_t n = 0, pv_seen = 0;
+#ifdef KMB_PV_TIMING
+        long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define KMB_T(i) do { const long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } while (0)
+#else
+#define KMB_T(i) do { } while (0)
+#endif
         auto ensure_pv_done = [&](uint32_t count) {   // PV(0 .. count-1) have completed
             while (pv_seen < count) {
                 mbar_wait(p_free, pv_seen & 1);
@@ -218,6 +281,11 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
             tc_fence_after();
         };
         long long u = u0;
+        float vn_next = 1.0e30f;   // |v|^2 of source (next tile's block) + et, for the threads that stage it
+        if (et < TN && u0 < u1) {
+            const long long j = (u0 % nsb) * TN + et;
+            if (j < P.M) vn_next = __ldg(P.vn + j);
+        }
         while (u < u1) {
             const int tile = static_cast<int>(u / nsb);
             const long long sb0 = u - tile * nsb;
@@ -226,22 +294,45 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
             const bool row_ok = row < P.N;
             const float un = row_ok ? __ldg(P.un + row) : 0.f;
             [[maybe_unused]] const long long jz = (P.row_offset + row) % (P.M + 1);
-            float ksum = 0.f, ref = -INFINITY;
+            float ksum = 0.f, ref = -INFINITY;   // ksum: this group's columns only
+            if (P.u_in_tmem && cg == 0) {
+                // this row's u (hi, lo) -> TMEM lanes; every S MMA of the previous segment has completed
+                // (their tiles were consumed above), so the columns are free
+                for (int c0 = 0; c0 < P.Dp; c0 += 16) {
+                    float h[16], l[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        h[c] = row_ok ? __ldg(P.uh + row * P.Dp + c0 + c) : 0.f;
+                        l[c] = row_ok ? __ldg(P.ul + row * P.Dp + c0 + c) : 0.f;
+                    }
+                    tmem_st_cols<16>(tmem_base + COL_UH + c0 + lane_addr, h);
+                    tmem_st_cols<16>(tmem_base + COL_UL + c0 + lane_addr, l);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(utm_full);
+            }
 
             for (int k = 0; k < cnt; ++k, ++n) {
                 const long long j0 = (sb0 + k) * TN;
                 float* ax = aux + (n & 1) * TN;
                 if (et < TN) {
-                    const long long j = j0 + et;
-                    ax[et] = j < P.M ? __ldg(P.vn + j) : 1.0e30f;
+                    ax[et] = vn_next;   // loaded one tile ago: the global-load latency stays off the critical path
+                    const long long un1 = u + k + 1;
+                    const long long j = (un1 % nsb) * TN + et;
+                    vn_next = (un1 < u1 && j < P.M) ? __ldg(P.vn + j) : 1.0e30f;
                 }
+                KMB_T(0);
                 named_bar_sync(1, EPI_THREADS);
+                KMB_T(1);
                 const int a = n & 1;
                 mbar_wait(&acc_full[a], (n >> 1) & 1);
                 tc_fence_after();
-                float s0[32], s1[32];
-                tmem_ld_32x32(tmem_base + COL_S + a * TN + lane_addr, s0);
-                tmem_ld_32x32(tmem_base + COL_S + a * TN + 32 + lane_addr, s1);
+                KMB_T(2);
+                float s[CPT];
+                tmem_ld_cols<CPT>(tmem_base + COL_S + a * TN + col0 + lane_addr, s);
+                KMB_T(3);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[a]);   // S is in registers: the MMA warp may refill this stage
@@ -249,95 +340,107 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                 // kernel values (or their log2 under the online max)
                 float cm = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
+                for (int c = 0; c < CPT; ++c) {
                     if constexpr (C::ONLINE_MAX) {
-                        s0[c] = log2_kernel_from_parts<KID>(s0[c], un, ax[c]);
-                        s1[c] = log2_kernel_from_parts<KID>(s1[c], un, ax[32 + c]);
-                        cm = fmaxf(cm, fmaxf(s0[c], s1[c]));
+                        s[c] = log2_kernel_from_parts<KID>(s[c], un, ax[col0 + c]);
+                        cm = fmaxf(cm, s[c]);
                     } else {
-                        s0[c] = kernel_from_parts<KID>(s0[c], un, ax[c]);
-                        s1[c] = kernel_from_parts<KID>(s1[c], un, ax[32 + c]);
+                        s[c] = kernel_from_parts<KID>(s[c], un, ax[col0 + c]);
                         if constexpr (KID == KMB_KERNEL_INVERSE_DISTANCE) {
-                            if (j0 + c == jz || j0 + c >= P.M) s0[c] = 0.f;
-                            if (j0 + 32 + c == jz || j0 + 32 + c >= P.M) s1[c] = 0.f;
+                            if (j0 + col0 + c == jz || j0 + col0 + c >= P.M) s[c] = 0.f;
                         }
                     }
                 }
+                if constexpr (C::ONLINE_MAX) {
+                    // the groups agree on the row maximum of the tile (so that they take the same decisions)
+                    float* cmb = cmbuf + (n & 1) * (NG * TM);
+                    cmb[cg * TM + row_in_tile] = cm;
+                    named_bar_sync(3, EPI_THREADS);
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) cm = fmaxf(cm, cmb[g * TM + row_in_tile]);
+                }
+                KMB_T(4);
                 ensure_pv_done(n);   // PV(n-1) has read P and finished accumulating into O
+                KMB_T(5);
                 if constexpr (C::ONLINE_MAX) {
                     // lazy rescale: keep the reference exponent unless the row maximum outgrew it by 2^64
                     bool need = false;
                     if (ref == -INFINITY) ref = cm;   // first tile of the row (O is overwritten by its PV)
                     else need = cm > ref + kLazyRescale;
-                    if (__any_sync(0xffffffffu, need)) {
+                    if (__any_sync(0xffffffffu, need)) {   // same lanes, same data in every group: same branch
                         const float sc = need ? ex2_approx(ref - cm) : 1.f;
-                        for (int c0 = 0; c0 < P.ebp; c0 += 32) {
-                            float o[32];
-                            tmem_ld_32x32(tmem_base + COL_O + c0 + lane_addr, o);
+                        for (int c0 = cg * 16; c0 < P.ebp; c0 += NG * 16) {   // this group's 16-column chunks of O
+                            float o[16];
+                            tmem_ld_cols<16>(tmem_base + COL_O + c0 + lane_addr, o);
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) o[c] *= sc;
-                            tmem_st_32x32(tmem_base + COL_O + c0 + lane_addr, o);
+                            for (int c = 0; c < 16; ++c) o[c] *= sc;
+                            tmem_st_cols<16>(tmem_base + COL_O + c0 + lane_addr, o);
                         }
                         tmem_st_wait();
                         ksum *= sc;
                         if (need) ref = cm;
                     }
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        s0[c] = ex2_approx(s0[c] - ref);
-                        s1[c] = ex2_approx(s1[c] - ref);
-                    }
+                    for (int c = 0; c < CPT; ++c) s[c] = ex2_approx(s[c] - ref);
                 }
                 // TF32 hi / lo split of P -> TMEM; the weights summed for the normaliser are the split ones
                 {
-                    float hi[32], lo[32], kacc = 0.f;   // two-level sum of the weights (see kprod_direct.cuh)
+                    float lo[CPT], kacc = 0.f;   // two-level sum of the weights (see kprod_direct.cuh)
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        hi[c] = to_tf32(s0[c]);
-                        lo[c] = to_tf32(s0[c] - hi[c]);
-                        kacc += hi[c] + lo[c];
+                    for (int c = 0; c < CPT; ++c) {
+                        const float hi = to_tf32(s[c]);
+                        lo[c] = to_tf32(s[c] - hi);
+                        s[c] = hi;
+                        kacc += hi + lo[c];
                     }
-                    tmem_st_32x32(tmem_base + COL_PH + lane_addr, hi);
-                    tmem_st_32x32(tmem_base + COL_PL + lane_addr, lo);
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        hi[c] = to_tf32(s1[c]);
-                        lo[c] = to_tf32(s1[c] - hi[c]);
-                        kacc += hi[c] + lo[c];
-                    }
-                    tmem_st_32x32(tmem_base + COL_PH + 32 + lane_addr, hi);
-                    tmem_st_32x32(tmem_base + COL_PL + 32 + lane_addr, lo);
+                    tmem_st_cols<CPT>(tmem_base + COL_PH + col0 + lane_addr, s);
+                    tmem_st_cols<CPT>(tmem_base + COL_PL + col0 + lane_addr, lo);
                     ksum += kacc;
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_ready);
+                KMB_T(6);
             }
+#ifdef KMB_PV_TIMING
+            if (blockIdx.x == 0 && et == 0 && u + cnt >= u1) {
+                for (int i = 0; i < 7; ++i) P.out[i] = static_cast<float>(tacc[i]) / n;
+                P.out[7] = static_cast<float>(n);
+            }
+#endif
 
             // ------------------------------ row tile (segment) done ------------------------------
             ensure_pv_done(n);
+            // the row's sum of weights over all column groups, in a fixed order
+            ksbuf[cg * TM + row_in_tile] = ksum;
+            named_bar_sync(2, EPI_THREADS);
+            float ktot = 0.f;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) ktot += ksbuf[g * TM + row_in_tile];
             const bool complete = (cnt == nsb);
             const int slot = (u == u0) ? 0 : 1;
             float* mine = P.partial + (static_cast<size_t>(blockIdx.x) * 2 + slot) * (TM * C::PS);
-            for (int c0 = 0; c0 < P.ebp; c0 += 32) {
-                float o[32];
-                tmem_ld_32x32(tmem_base + COL_O + c0 + lane_addr, o);
+            for (int c0 = cg * 16; c0 < P.ebp; c0 += NG * 16) {   // this group's 16-column chunks of O
+                float o[16];
+                tmem_ld_cols<16>(tmem_base + COL_O + c0 + lane_addr, o);
                 if (complete) {
                     if (row_ok) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            if (c0 + c < P.eb) P.out[row * P.E + P.e0 + c0 + c] = NORM ? o[c] / ksum : o[c];
+                        for (int c = 0; c < 16; ++c)
+                            if (c0 + c < P.eb) P.out[row * P.E + P.e0 + c0 + c] = NORM ? o[c] / ktot : o[c];
                     }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) mine[(c0 + c) * TM + row_in_tile] = o[c];
+                    for (int c = 0; c < 16; ++c) mine[(c0 + c) * TM + row_in_tile] = o[c];
                 }
             }
             tc_fence_before();
             if (!complete) {
-                mine[MAX_EB * TM + row_in_tile] = ksum;
-                mine[(MAX_EB + 1) * TM + row_in_tile] = ref;
+                if (cg == 0) {
+                    mine[MAX_EB * TM + row_in_tile] = ktot;
+                    mine[(MAX_EB + 1) * TM + row_in_tile] = ref;
+                }
                 __threadfence();
                 named_bar_sync(2, EPI_THREADS);
                 const long long tile_u0 = static_cast<long long>(tile) * nsb;
@@ -362,7 +465,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                             mx = fmaxf(mx, __ldcg(ps + (MAX_EB + 1) * TM + row_in_tile));
                         }
                     }
-                    for (int e = 0; e < P.eb; ++e) {
+                    for (int e = cg; e < P.eb; e += NG) {   // the groups share the signal columns of the row
                         float sum = 0.f;
                         l = 0.f;
                         for (int c = c_first; c <= c_last; ++c) {
@@ -379,6 +482,8 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                         P.out[row * P.E + P.e0 + e] = NORM ? sum / l : sum;
                     }
                 }
+            } else {
+                named_bar_sync(2, EPI_THREADS);   // ksbuf is rewritten at the end of the next segment
             }
             u += cnt;
         }
@@ -426,9 +531,10 @@ int plan_pv(int64_t N, int64_t M, int D, int E, PvPlan* pl) {
     KMB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     KMB_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     pl->grid_max = sms;
-    const int fixed = 1024 + pl->kblocks * 2 * pv::A_TILE_BYTES + 2 * pv::TN * 4 + 512;
+    const int u_bytes = pl->Dp <= pv::U_TMEM_MAX_D ? 0 : pl->kblocks * 2 * pv::A_TILE_BYTES;   // u tile in TMEM when it fits
+    const int fixed = 1024 + u_bytes + 2 * pv::TN * 4 + 3 * pv::NG * tc::TM * 4 + 512;
     pl->stages = std::min(12, (smem_max - fixed) / pv::SLOT_BYTES);
-    if (pl->stages < pl->kblocks + 2) return set_error(KMB_ERR_UNSUPPORTED, "not enough shared memory for D=%d", D);
+    if (pl->stages < 4) return set_error(KMB_ERR_UNSUPPORTED, "not enough shared memory for D=%d", D);
     pl->smem = fixed + pl->stages * pv::SLOT_BYTES;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += align_up_pv(bytes, 256); return at; };
@@ -513,6 +619,10 @@ int tensor_pv_product(const float* x, const float* y, const float* b, float* out
         pv::Params P;
         P.un = F(pl.off_un);
         P.vn = F(pl.off_vn);
+        P.uh = uh;
+        P.ul = ul;
+        P.Dp = pl.Dp;
+        P.u_in_tmem = pl.Dp <= pv::U_TMEM_MAX_D ? 1 : 0;
         P.out = out;
         P.partial = F(pl.off_partial);
         P.tile_counter = counters;

@@ -28,6 +28,21 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// One lane of a converged warp.  The MMA-issuing warp walks its loop with all 32 lanes (uniform control
+// flow, so ptxas keeps descriptors and TMEM addresses in uniform registers) and issues tcgen05.mma /
+// tcgen05.commit under this predicate.  Wrapping the whole loop in `if (lane == 0)` instead makes every
+// UTCHMMA a waterfall loop (ELECT + 4 R2UR + BRA.U.ANY): ~125 cycles per MMA, measured.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -90,6 +105,38 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float (&r)[3
         "r"(u[19]), "r"(u[20]), "r"(u[21]), "r"(u[22]), "r"(u[23]), "r"(u[24]), "r"(u[25]), "r"(u[26]), "r"(u[27]),
         "r"(u[28]), "r"(u[29]), "r"(u[30]), "r"(u[31])
         : "memory");
+}
+// 16-column variants (column-split epilogues: each warp group owns a slice of the tile's columns)
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* r) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(r);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const float* r) {
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(r);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]),
+        "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+        : "memory");
+}
+// CPT (16 or 32) consecutive columns of this warp's 32 lanes <-> registers
+template <int CPT>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&r)[CPT]) {
+    static_assert(CPT % 16 == 0, "16-column chunks");
+#pragma unroll
+    for (int c = 0; c < CPT; c += 16) tmem_ld_32x16(taddr + c, r + c);
+    tmem_ld_wait();
+}
+template <int CPT>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const float (&r)[CPT]) {
+#pragma unroll
+    for (int c = 0; c < CPT; c += 16) tmem_st_32x16(taddr + c, r + c);
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float to_tf32(float x) {

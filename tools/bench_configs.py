@@ -83,8 +83,8 @@ def main():
     if "c4s" in which:
         run_product("C4-small(32k)", datasets.config_c4(n=32768), runs=2)
     if "c4" in which:
-        run_product("C4", datasets.config_c4(), runs=1)
-        run_product("C4-gaussian", datasets.config_c4(kernel="gaussian"), runs=1)
+        run_product("C4", datasets.config_c4(), runs=2)
+        run_product("C4-gaussian", datasets.config_c4(kernel="gaussian"), runs=2)
     if "c5s" in which:
         run_solver("C5-small(100k)", 100_000)
     if "c5" in which:
