@@ -22,7 +22,7 @@
 // triangular (targets == sources, see kprod_sym.cuh) unit list, first across `n_parts` GPUs, then across
 // the CTAs; mma_combine_kernel adds the row pieces (and column pieces) in a fixed order.
 #pragma once
-#include "kprod_direct.cuh"
+#include "../../kernel_matrix_benchmarks_b200/csrc/kprod_direct.cuh"
 
 namespace kmb {
 
@@ -81,11 +81,11 @@ struct UnitMap {
 };
 
 // POLY_: every POLY_-th pair of exponentials on the FMA pipe (0 = none).  WARPS_ consumer warps x 64 rows.
-template <bool SYM_, int POLY_ = 0, int WARPS_ = 16, int SB_ = 256, int STAGES_ = 4, int MINB_ = 1>
+template <bool SYM_, int POLY_ = 0, int WARPS_ = 16, int SB_ = 256, int STAGES_ = 4, int MINB_ = 1, int MT_ = 4>
 struct MmaCfg {
     static constexpr bool SYM = SYM_;
     static constexpr int POLY = POLY_, WARPS = WARPS_, SB = SB_, STAGES = STAGES_, MINB = MINB_;
-    static constexpr int MT = 4;                       // m16 tiles per warp
+    static constexpr int MT = MT_;                     // m16 tiles per warp
     static constexpr int ROWS_PER_WARP = 16 * MT;
     static constexpr int CONSUMERS = 32 * WARPS, THREADS = CONSUMERS + 32;
     static constexpr int TILE_ROWS = WARPS * ROWS_PER_WARP;

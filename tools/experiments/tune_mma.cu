@@ -1,11 +1,11 @@
 // Tuning harness for kprod_mma_kernel (exponent on mma.sync TF32): times configurations of the D = 3
 // Gaussian product (general and symmetric) on one GPU and prints one line each.
-//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tune_mma tools/tune_mma.cu
+//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tune_mma tools/experiments/tune_mma.cu
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 
-#include "../kernel_matrix_benchmarks_b200/csrc/kprod_mma.cuh"
+#include "kprod_mma.cuh"
 
 namespace kmb {
 int set_error(int code, const char*, ...) { return code; }
@@ -74,18 +74,20 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(b, hb.data(), N * 4, cudaMemcpyHostToDevice));
     printf("N=%lld on %s (%d SMs)   (reference checksums of tune_direct / tune_sym: -2.353711e+06 at 262144, -9.753223e+06 at 1000000)\n", N, p.name, p.multiProcessorCount);
     const int sms = p.multiProcessorCount;
-    //   SYM POLY WARPS SB STAGES MINB
+    //   SYM POLY WARPS SB STAGES MINB MT
 #define RUN(...) run<MmaCfg<__VA_ARGS__>>(#__VA_ARGS__, N, y, b, out, sms)
-    RUN(false, 0, 16, 256, 4, 1);
-    RUN(false, 0, 8, 256, 4, 2);
-    RUN(false, 4, 16, 256, 4, 1);
-    RUN(false, 4, 8, 256, 4, 2);
-    RUN(false, 2, 8, 256, 4, 2);
-    RUN(false, 8, 8, 256, 4, 2);
-    RUN(true, 0, 16, 256, 4, 1);
-    RUN(true, 4, 16, 256, 4, 1);
-    RUN(true, 8, 16, 256, 4, 1);
-    RUN(true, 0, 8, 256, 4, 2);
-    RUN(true, 4, 8, 256, 4, 2);
+    RUN(false, 0, 16, 256, 4, 1, 4);
+    RUN(false, 4, 16, 256, 4, 1, 4);
+    RUN(false, 0, 16, 256, 4, 2, 2);
+    RUN(false, 4, 16, 256, 4, 2, 2);
+    RUN(false, 2, 16, 256, 4, 2, 2);
+    RUN(false, 8, 16, 256, 4, 2, 2);
+    RUN(false, 4, 8, 256, 4, 4, 2);
+    RUN(false, 4, 16, 256, 3, 2, 2);
+    RUN(true, 0, 16, 256, 4, 2, 2);
+    RUN(true, 4, 16, 256, 4, 2, 2);
+    RUN(true, 8, 16, 256, 4, 2, 2);
+    RUN(true, 0, 8, 256, 4, 4, 2);
+    RUN(true, 8, 8, 256, 4, 4, 2);
     return 0;
 }
