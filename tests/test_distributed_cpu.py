@@ -110,3 +110,96 @@ def test_shard_bounds_cover_rows_exactly():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             per = shard_bounds(n, 0, world)[2]
             assert all(hi - lo <= per for lo, hi in spans)
+
+
+# ---- symmetric mode: the triangular unit list split across ranks + one all-reduce per matvec ----------
+# Host-level restatement of the partition of csrc/kprod_sym.cuh (sym_prefix / sym_tile_of / unit ranges)
+# with float64 oracle arithmetic, so the N > 1 logic of CudaSymmetricOps is exercised on CPU.
+
+def sym_prefix(I, nsb, TB):
+    """units of tiles 0 .. I-1: sum_{t<I} (nsb - TB t)   (kprod_sym.cuh: sym_prefix)"""
+    return I * nsb - (TB * I * (I - 1)) // 2
+
+
+def sym_tile_of(u, nsb, n_tiles, TB):
+    I = 0
+    while I + 1 < n_tiles and sym_prefix(I + 1, nsb, TB) <= u:
+        I += 1
+    return I
+
+
+def sym_part(pts, b, part, n_parts, tile_rows=8, sb=4):
+    """This part's share of K b for targets == sources: units on / above the block diagonal, each kernel
+    value used for its row sum and (off the diagonal blocks) its column sum."""
+    n = len(pts)
+    TB = tile_rows // sb
+    nsb, n_tiles = -(-n // sb), -(-n // tile_rows)
+    units = sym_prefix(n_tiles, nsb, TB)
+    ub, ue = units * part // n_parts, units * (part + 1) // n_parts
+    out = np.zeros((n, 1))
+    for u in range(ub, ue):
+        I = sym_tile_of(u, nsb, n_tiles, TB)
+        jb = TB * I + (u - sym_prefix(I, nsb, TB))
+        rows = np.arange(I * tile_rows, min(n, (I + 1) * tile_rows))
+        cols = np.arange(jb * sb, min(n, (jb + 1) * sb))
+        if len(rows) == 0 or len(cols) == 0:
+            continue
+        K = np.exp(-((pts[rows][:, None, :] - pts[cols][None, :, :]) ** 2).sum(-1))
+        out[rows] += K @ b[cols]
+        if jb >= TB * (I + 1):          # off the block diagonal: the same values feed the column sums
+            out[cols] += K.T @ b[rows]
+    return out, units
+
+
+@pytest.mark.parametrize("n,n_parts", [(50, 1), (50, 3), (37, 2), (8, 4), (5, 8)])
+def test_symmetric_partition_adds_up(n, n_parts):
+    rng = np.random.RandomState(n)
+    pts, b = rng.rand(n, 3), rng.randn(n, 1)
+    total = sum(sym_part(pts, b, p, n_parts)[0] for p in range(n_parts))
+    assert orc.rel_l2(total, orc.kernel_product("gaussian", pts, None, b)) <= 1e-13
+    # every unit is owned by exactly one part
+    units = sym_part(pts, b, 0, n_parts)[1]
+    owned = [units * (p + 1) // n_parts - units * p // n_parts for p in range(n_parts)]
+    assert sum(owned) == units and max(owned) - min(owned) <= 1
+
+
+class OracleSymmetricOps(OracleShardOps):
+    """Same role as solver.CudaSymmetricOps: replicated CG vectors, the matvec is this rank's range of the
+    symmetric unit list followed by one all-reduce."""
+
+    def __init__(self, points, kernel, dist_comm):
+        super().__init__(points, kernel, 0, len(points))
+        self.dist_comm = dist_comm
+
+    def matvec(self, p_full):
+        part, _ = sym_part(self.pts, p_full.numpy(), self.dist_comm.rank, self.dist_comm.world)
+        out = torch.from_numpy(part)
+        self.dist_comm.all_reduce(out)
+        return out
+
+
+def _sym_worker(rank, world, port, n, lam, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.RandomState(5)
+        pts, b = rng.rand(n, 3), rng.randn(n, 1)
+        rhs = orc.regularised_matvec("gaussian", pts, b, lam)
+        ops = OracleSymmetricOps(pts, "gaussian", TorchDistComm())
+        res = cg_solve(ops, LocalComm(), torch.from_numpy(rhs).clone(), n, lam=lam, rtol=1e-10, max_iter=200)
+        np.savez(os.path.join(out_dir, f"sym{rank}.npz"), x=res.x.numpy(), it=res.iterations, conv=res.converged)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 61), (3, 40)])
+def test_symmetric_cg_gloo(tmp_path, world, n):
+    lam = 1.0
+    mp.spawn(_sym_worker, args=(world, _free_port(), n, lam, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.RandomState(5)
+    pts, b = rng.rand(n, 3), rng.randn(n, 1)
+    parts = [np.load(tmp_path / f"sym{r}.npz") for r in range(world)]
+    assert all(bool(p["conv"]) for p in parts) and len({int(p["it"]) for p in parts}) == 1
+    for p in parts:  # every rank holds the whole solution
+        assert p["x"].shape == (n, 1) and orc.rel_l2(p["x"], b) <= 1e-8
+    assert all(np.array_equal(parts[0]["x"], p["x"]) for p in parts[1:]), "replicated vectors must stay bit-identical"
