@@ -125,6 +125,16 @@ int kmb_product_sym_workspace_bytes(int64_t n, int D, int part, int n_parts, siz
 int kmb_product_sym_f32(const float* y, const float* b, float* out, int64_t n, int D, int kernel_id,
                         int part, int n_parts, void* workspace, size_t workspace_bytes, void* stream);
 
+/* out[i, :] = sum_j k(x_i, y_j) b[j, :] in double precision: the `precision=float64` variant of the
+ * reference's plugin (bruteforce.py:64-87, 100-106; algos.yaml:156-162), same arithmetic as its float64
+ * difference-form path (bruteforce.py:53-54).  All pointers are float64 device arrays; D <= 16; flags and
+ * row_offset as kmb_product_f32.  No workspace.  Row normalisation divides by the plain row sum as the
+ * reference does (a row whose kernels all underflow is 0/0 = NaN there and here).
+ */
+int kmb_product_f64(const double* x, const double* y, const double* b, double* out, int64_t n_targets,
+                    int64_t n_sources, int D, int E, int kernel_id, int flags, int64_t row_offset,
+                    void* stream);
+
 /* Number of this library's kernels the last kmb_product_f32 / kmb_cg_* call on this
  * thread launched (bench.py's gpu_launches). */
 int kmb_last_launch_count(void);

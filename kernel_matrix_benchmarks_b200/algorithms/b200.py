@@ -30,17 +30,27 @@ from ..solver import CudaShardOps, CudaSymmetricOps, LocalComm, TorchDistComm, c
 from .base import BaseProduct, BaseSolver
 
 
-def _check_precision(precision, who):
+def _check_precision(precision, who, allowed=(np.float32,)):
     """The reference accepts a numpy dtype or its name (algos.yaml:156-162 passes strings)."""
     dt = np.dtype(precision)
-    if dt != np.float32:
-        raise NotImplementedError(f"{who} computes in float32 only (got precision={precision}).")
+    if dt not in [np.dtype(a) for a in allowed]:
+        names = ", ".join(np.dtype(a).name for a in allowed)
+        raise NotImplementedError(f"{who} supports precision in {{{names}}} (got precision={precision}).")
     return dt
 
 
-def _to_device(array, device):
-    """float64 host array (owned by the runner, never mutated) -> float32 device tensor."""
-    host = torch.from_numpy(np.ascontiguousarray(array, dtype=np.float32))
+def _to_device(array, device, precision=np.float32):
+    """float64 host array (owned by the runner, never mutated) -> device tensor in the working precision.
+
+    float32: cast as bruteforce.py:100-106 casts.  float64: kept.  float16: the inputs are rounded to half
+    precision exactly as the reference's ``astype(float16)`` rounds them, then widened to float32 -- the
+    arithmetic itself runs in FP32 (the reference's float16 run also accumulates in half precision, which
+    costs it another ~1e-3; this variant only carries the input rounding)."""
+    dt = np.dtype(precision)
+    a = np.asarray(array)
+    if dt == np.float16:
+        a = a.astype(np.float16).astype(np.float32)
+    host = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64 if dt == np.float64 else np.float32))
     if host.dim() == 1:
         host = host[:, None]
     return host.pin_memory().to(device, non_blocking=True)
@@ -76,7 +86,9 @@ class B200Product(BaseProduct):
             raise NotImplementedError(f"B200Product doesn't support kernel {kernel}.")
         if path not in _lib.PATH_IDS:
             raise ValueError(f"unknown path {path!r} (expected one of {sorted(_lib.PATH_IDS)})")
-        _check_precision(precision, "B200Product")
+        self.dtype = _check_precision(precision, "B200Product", (np.float32, np.float64, np.float16))
+        if self.dtype == np.float64 and dimension > 16:
+            raise NotImplementedError("B200Product float64 path supports dimension <= 16.")
         _lib.load()  # fail here, loudly, if the CUDA library is absent
         if not torch.cuda.is_available():
             raise RuntimeError("B200Product needs a CUDA device; there is no CPU fallback.")
@@ -94,9 +106,9 @@ class B200Product(BaseProduct):
 
     def prepare_data(self, *, source_points, target_points, same_points=False, density_estimation=False):
         """Untimed host->device copy (base.py:64-67), cast to float32 as bruteforce.py:100-106 casts."""
-        self.source_points = _to_device(source_points, self.device)
+        self.source_points = _to_device(source_points, self.device, self.dtype)
         self.same_points = bool(same_points)
-        self.target_points = self.source_points if self.same_points else _to_device(target_points, self.device)
+        self.target_points = self.source_points if self.same_points else _to_device(target_points, self.device, self.dtype)
         self.density_estimation = bool(density_estimation)
         torch.cuda.synchronize(self.device)
 
@@ -108,14 +120,22 @@ class B200Product(BaseProduct):
 
     def prepare_query(self, *, source_signal):
         """Untimed host->device copy of the signal (bruteforce.py:122-128)."""
-        self.source_signal = None if self.density_estimation else _to_device(source_signal, self.device)
+        self.source_signal = None if self.density_estimation else _to_device(source_signal, self.device, self.dtype)
         torch.cuda.synchronize(self.device)
 
     def query(self):
         """Timed: the whole product, ending with a device synchronise."""
         with torch.cuda.device(self.device):
             with _GpuTimer() as t:
-                if self.comm.world > 1:
+                if self.dtype == np.float64:
+                    lo, hi, _ = shard_bounds(self.target_points.shape[0], self.comm.rank, self.comm.world)
+                    mine = _product.kernel_product_f64(
+                        self.target_points[lo:hi], self.source_points, self.source_signal, kernel=self.kernel,
+                        normalize_rows=bool(self.normalize_rows), density_estimation=self.density_estimation, row_offset=lo)
+                    self.launches = last_launch_count()
+                    self.path_used = "direct_f64"
+                    self.res_device = mine if self.comm.world == 1 else self.comm.all_gather(mine, self.target_points.shape[0])
+                elif self.comm.world > 1:
                     self._query_distributed()
                 else:
                     self.res_device = kernel_product(
@@ -175,7 +195,7 @@ class B200Product(BaseProduct):
         }
 
     def _form(self):
-        if self.source_points.shape[1] > 16 or (self.normalize_rows and self.density_estimation):
+        if self.source_points.shape[1] > 16 or (self.normalize_rows and self.density_estimation) or self.dtype == np.float64:
             return "n/a"
         from ..product import direct_stats
 

@@ -39,6 +39,9 @@ KMB_DECLARE_TABLE(kDirect_invdist_n1)
 KMB_DECLARE_TABLE(kDirect_gaussprod_n0)
 KMB_DECLARE_TABLE(kDirect_gaussprod_n1)
 
+// kprod_f64.cu
+int product_f64(const double* x, const double* y, const double* b, double* out, int64_t N, int64_t M, int D, int E,
+                int kernel_id, int flags, int64_t row_offset, cudaStream_t stream);
 // kprod_sym.cu
 bool sym_supported(int D);
 int sym_tile_rows();
@@ -406,6 +409,16 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
         return set_error(KMB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total_bytes, workspace_bytes);
     return run_direct(x, y, density ? nullptr : b, out, N, M, D, E, kernel_id, flags, row_offset, pl, nullptr, 0, 1,
                       static_cast<char*>(workspace), stream);
+}
+
+int kmb_product_f64(const double* x, const double* y, const double* b, double* out, int64_t N, int64_t M, int D, int E,
+                    int kernel_id, int flags, int64_t row_offset, void* stream_) {
+    g_launches = 0;
+    if (int rc = check_product_args(N, M, D, E, kernel_id, flags, KMB_PATH_AUTO)) return rc;
+    if (!x || !y || !out) return set_error(KMB_ERR_INVALID, "x, y and out must not be NULL");
+    if (!(flags & KMB_FLAG_DENSITY) && !b) return set_error(KMB_ERR_INVALID, "b is NULL without KMB_FLAG_DENSITY");
+    if (N == 0) return KMB_OK;
+    return product_f64(x, y, b, out, N, M, D, E, kernel_id, flags, row_offset, static_cast<cudaStream_t>(stream_));
 }
 
 int kmb_product_sym_workspace_bytes(int64_t n, int D, int part, int n_parts, size_t* bytes) {

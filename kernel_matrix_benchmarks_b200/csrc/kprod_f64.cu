@@ -1,0 +1,124 @@
+// kprod_f64: a_i = sum_j k(x_i, y_j) b_j in double precision -- the `precision=float64` variant of the
+// reference (/root/reference/kernel_matrix_benchmarks/algorithms/bruteforce.py:64-87, 100-106; algos.yaml:156-162
+// sweeps float16 / float32 / float64).  Same arithmetic as the reference's float64 slow path
+// (bruteforce.py:53-54: sum of squared differences; :18-22 kernel functions; :130-153 query modes), K never
+// materialised.  This is the accuracy end of the Pareto front, not the headline path: one target row per
+// thread, sources staged through shared memory, FP64 pipe (64 DFMA/clk/SM) + libdevice exp.
+//
+// Row normalisation divides by the plain row sum like the reference does (no running maximum): a row
+// whose kernels all underflow in float64 is 0/0 = NaN there and here.
+#include "kmb_common.cuh"
+
+namespace kmb {
+
+namespace {
+
+constexpr int F64_THREADS = 128;
+constexpr int F64_SB = 256;        // sources per shared-memory stage
+constexpr int F64_MAX_D = 16, F64_MAX_E = 8;
+
+template <int KID>
+__device__ __forceinline__ double kernel_value_f64(double d2) {
+    if constexpr (KID == KMB_KERNEL_GAUSSIAN) return exp(-d2);
+    else if constexpr (KID == KMB_KERNEL_ABSOLUTE_EXPONENTIAL) return exp(-sqrt(fmax(d2, 0.0)));   // bruteforce.py:21
+    else return 1.0 / sqrt(fmax(d2, 0.0));                                                          // bruteforce.py:10-11
+}
+
+// E columns e0 .. e0+EC-1 of the signal per launch (EC <= F64_MAX_E)
+template <int KID, int EC>
+__global__ void __launch_bounds__(F64_THREADS)
+kprod_f64_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ b,
+                 double* __restrict__ out, long long N, long long M, int D, int E, int e0, int normalize,
+                 long long row_offset) {
+    extern __shared__ double sm[];
+    double* sy = sm;                        // F64_SB x D
+    double* sb = sm + F64_SB * D;           // F64_SB x EC
+    const long long row = blockIdx.x * static_cast<long long>(F64_THREADS) + threadIdx.x;
+    const bool ok = row < N;
+    double xr[F64_MAX_D];
+#pragma unroll
+    for (int d = 0; d < F64_MAX_D; ++d) xr[d] = (ok && d < D) ? x[row * D + d] : 0.0;
+    double acc[EC], ksum = 0.0;
+#pragma unroll
+    for (int e = 0; e < EC; ++e) acc[e] = 0.0;
+    [[maybe_unused]] const long long jz = (row_offset + row) % (M + 1);   // inverse-distance zeroing (bruteforce.py:12-14)
+
+    for (long long j0 = 0; j0 < M; j0 += F64_SB) {
+        const int cnt = static_cast<int>(min(static_cast<long long>(F64_SB), M - j0));
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * D; i += F64_THREADS) sy[i] = y[j0 * D + i];
+        for (int i = threadIdx.x; i < cnt * EC; i += F64_THREADS) {
+            const int j = i / EC, e = i % EC;
+            sb[i] = (e0 + e < E) ? (b ? b[(j0 + j) * E + e0 + e] : 1.0) : 0.0;
+        }
+        __syncthreads();
+        if (ok) {
+            for (int j = 0; j < cnt; ++j) {
+                double d2 = 0.0;
+#pragma unroll
+                for (int d = 0; d < F64_MAX_D; ++d) {
+                    if (d < D) {
+                        const double diff = xr[d] - sy[j * D + d];
+                        d2 = fma(diff, diff, d2);
+                    }
+                }
+                double k = kernel_value_f64<KID>(d2);
+                if constexpr (KID == KMB_KERNEL_INVERSE_DISTANCE) {
+                    if (j0 + j == jz) k = 0.0;
+                }
+                ksum += k;
+#pragma unroll
+                for (int e = 0; e < EC; ++e) acc[e] = fma(k, sb[j * EC + e], acc[e]);
+            }
+        }
+    }
+    if (ok) {
+#pragma unroll
+        for (int e = 0; e < EC; ++e)
+            if (e0 + e < E) out[row * E + e0 + e] = normalize ? acc[e] / ksum : acc[e];
+    }
+}
+
+__global__ void fill_f64_kernel(double* out, long long n, double v) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
+template <int KID>
+int launch_f64(const double* x, const double* y, const double* b, double* out, int64_t N, int64_t M, int D, int E, int flags,
+               int64_t row_offset, cudaStream_t stream) {
+    const int normalize = (flags & KMB_FLAG_NORMALIZE_ROWS) ? 1 : 0;
+    const unsigned grid = static_cast<unsigned>((N + F64_THREADS - 1) / F64_THREADS);
+    for (int e0 = 0; e0 < E; e0 += F64_MAX_E) {
+        const int ec = std::min(F64_MAX_E, E - e0);
+        const size_t smem = sizeof(double) * F64_SB * (D + (ec <= 1 ? 1 : ec <= 2 ? 2 : ec <= 4 ? 4 : 8));
+        if (ec <= 1) kprod_f64_kernel<KID, 1><<<grid, F64_THREADS, smem, stream>>>(x, y, b, out, N, M, D, E, e0, normalize, row_offset);
+        else if (ec <= 2) kprod_f64_kernel<KID, 2><<<grid, F64_THREADS, smem, stream>>>(x, y, b, out, N, M, D, E, e0, normalize, row_offset);
+        else if (ec <= 4) kprod_f64_kernel<KID, 4><<<grid, F64_THREADS, smem, stream>>>(x, y, b, out, N, M, D, E, e0, normalize, row_offset);
+        else kprod_f64_kernel<KID, 8><<<grid, F64_THREADS, smem, stream>>>(x, y, b, out, N, M, D, E, e0, normalize, row_offset);
+        KMB_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+    }
+    return KMB_OK;
+}
+
+}  // namespace
+
+int product_f64(const double* x, const double* y, const double* b, double* out, int64_t N, int64_t M, int D, int E,
+                int kernel_id, int flags, int64_t row_offset, cudaStream_t stream) {
+    if (D > F64_MAX_D) return set_error(KMB_ERR_UNSUPPORTED, "float64 path supports D <= %d (got D=%d)", F64_MAX_D, D);
+    if ((flags & KMB_FLAG_NORMALIZE_ROWS) && (flags & KMB_FLAG_DENSITY)) {   // bruteforce.py:134-138
+        fill_f64_kernel<<<static_cast<unsigned>((N + 255) / 256), 256, 0, stream>>>(out, N, 1.0);
+        KMB_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+        return KMB_OK;
+    }
+    const double* sig = (flags & KMB_FLAG_DENSITY) ? nullptr : b;
+    switch (kernel_id) {
+        case KMB_KERNEL_GAUSSIAN: return launch_f64<KMB_KERNEL_GAUSSIAN>(x, y, sig, out, N, M, D, E, flags, row_offset, stream);
+        case KMB_KERNEL_ABSOLUTE_EXPONENTIAL: return launch_f64<KMB_KERNEL_ABSOLUTE_EXPONENTIAL>(x, y, sig, out, N, M, D, E, flags, row_offset, stream);
+        default: return launch_f64<KMB_KERNEL_INVERSE_DISTANCE>(x, y, sig, out, N, M, D, E, flags, row_offset, stream);
+    }
+}
+
+}  // namespace kmb

@@ -125,6 +125,32 @@ def kernel_product_sym_part(y, b, part, n_parts, *, out=None, workspace=None):
     return out
 
 
+def kernel_product_f64(x, y, b, *, kernel="gaussian", normalize_rows=False, density_estimation=False, row_offset=0, out=None):
+    """The float64 variant (kmb_product_f64): x (N, D), y (M, D), b (M, E) float64 CUDA tensors, D <= 16."""
+    lib = _lib.load()
+    if kernel not in _lib.KERNEL_IDS:
+        raise NotImplementedError(f"B200 kernel product doesn't support kernel {kernel}.")
+    for name, t in (("target points", x), ("source points", y)) + ((("source signal", b),) if not density_estimation else ()):
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.dim() == 2):
+            raise ValueError(f"{name} must be a contiguous 2-D float64 CUDA tensor")
+    N, D = x.shape
+    M = y.shape[0]
+    if y.shape[1] != D:
+        raise ValueError("target and source points disagree on D")
+    E = 1 if density_estimation else b.shape[1]
+    if not density_estimation and b.shape[0] != M:
+        raise ValueError("source signal and source points disagree on M")
+    flags = (_lib.FLAG_NORMALIZE_ROWS if normalize_rows else 0) | (_lib.FLAG_DENSITY if density_estimation else 0)
+    if out is None:
+        out = torch.empty((N, E), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.kmb_product_f64(_ptr(x), _ptr(y), None if density_estimation else _ptr(b), _ptr(out), N, M, D, E,
+                                       _lib.KERNEL_IDS[kernel], flags, int(row_offset), _stream()))
+    global last_path
+    last_path = "direct_f64"
+    return out
+
+
 def direct_stats(workspace=None, device=None):
     """What the device-side statistics pass of the last direct-path product decided (synchronises):
     bounding-box centre, log2(e)*half-diagonal^2 and the evaluation form of the Gaussian kernel."""

@@ -71,7 +71,11 @@ def test_plugin_rejects_what_the_reference_rejects():
         with pytest.raises(NotImplementedError):  # bruteforce.py:82-85
             cls(kernel="laplace", dimension=3)
         with pytest.raises(NotImplementedError):
-            cls(kernel="gaussian", dimension=3, precision=np.float64)
+            cls(kernel="gaussian", dimension=3, precision=np.int32)
+    with pytest.raises(NotImplementedError):   # the solver iterates in float32 only
+        B200Solver(kernel="gaussian", dimension=3, precision=np.float64)
+    with pytest.raises(NotImplementedError):   # the float64 product kernel covers D <= 16
+        B200Product(kernel="gaussian", dimension=784, precision="float64")
 
 
 def test_no_cpu_fallback():

@@ -413,3 +413,65 @@ def test_plugin_takes_the_symmetric_path_for_same_points():
     out2, extra2 = run_plugin("gaussian", ds.source_points, ds.source_points.copy(), ds.source_signal, same_points=False)
     assert extra2["path_used"] != "direct_sym"
     assert orc.rel_l2(out2[rows], want) <= TOL_DIRECT
+
+
+# ---- precision variants of the plugin (bruteforce.py:64-87; algos.yaml:156-162 sweeps float16/32/64) -----
+
+def run_plugin_precision(precision, g, **kw):
+    from kernel_matrix_benchmarks_b200.algorithms.b200 import B200Product
+
+    algo = B200Product(kernel=g["kernel"], dimension=g["source_points"].shape[1], normalize_rows=g["normalize_rows"],
+                       precision=precision, **kw)
+    try:
+        algo.prepare_data(source_points=g["source_points"], target_points=g["target_points"], same_points=g["same_points"],
+                          density_estimation=g["density_estimation"])
+        algo.fit()
+        algo.prepare_query(source_signal=g["source_signal"])
+        algo.query()
+        return algo.get_result(), algo.get_additional(), str(algo)
+    finally:
+        algo.done()
+
+
+@pytest.mark.parametrize("name", [n for n in PRODUCT_CASES if load_golden(n)["source_points"].shape[1] <= 16])
+def test_float64_precision_matches_reference_float64(name):
+    """precision=float64: the reference's own float64 outputs (tests/golden) to round-off."""
+    g = load_golden(name)
+    out, extra, label = run_plugin_precision("float64", g)
+    assert out.dtype == np.float64 and out.shape == g["truth"].shape and "float64" in label
+    assert extra["path_used"] in ("direct_f64", "None") or g["normalize_rows"] and g["density_estimation"]
+    if np.isnan(g["truth"]).any():
+        assert np.array_equal(np.isnan(out), np.isnan(g["truth"]))
+    else:
+        assert orc.rel_l2(out, g["truth"]) <= 1e-12
+
+
+def test_float64_precision_properties_at_size():
+    from kernel_matrix_benchmarks_b200 import datasets
+
+    ds = datasets.uniform_cube(20000, 3, 1.0, "gaussian")
+    g = dict(kernel="gaussian", source_points=ds.source_points, target_points=ds.source_points, source_signal=ds.source_signal,
+             same_points=True, normalize_rows=False, density_estimation=False)
+    out, _, _ = run_plugin_precision(np.float64, g)
+    rows = np.arange(0, 20000, 100)
+    want = orc.kernel_product("gaussian", ds.source_points, None, ds.source_signal, rows=rows)
+    assert orc.rel_l2(out[rows], want) <= 1e-13
+
+
+def test_float16_precision_rounds_the_inputs_like_the_reference():
+    """precision=float16: inputs go through half precision (bruteforce.py:100-106 astype), arithmetic in FP32."""
+    g = load_golden(PRODUCT_CASES[0]) if False else None
+    from kernel_matrix_benchmarks_b200 import datasets
+
+    ds = datasets.uniform_cube(4096, 3, 1.0, "gaussian")
+    g = dict(kernel="gaussian", source_points=ds.source_points, target_points=ds.source_points, source_signal=ds.source_signal,
+             same_points=True, normalize_rows=False, density_estimation=False)
+    out, _, label = run_plugin_precision("float16", g)
+    y16 = ds.source_points.astype(np.float16).astype(np.float64)
+    b16 = ds.source_signal.astype(np.float16).astype(np.float64)
+    want = orc.kernel_product("gaussian", y16, None, b16)
+    assert "float16" in label
+    assert orc.rel_l2(out, want) <= TOL_DIRECT
+    # and it is a float16-class result w.r.t. the unrounded problem (the reference's own float16 run: ~1e-3)
+    exact = orc.kernel_product("gaussian", ds.source_points, None, ds.source_signal)
+    assert 1e-5 < orc.rel_l2(out, exact) < 5e-3
