@@ -50,10 +50,29 @@ def _to_device(array, device, precision=np.float32):
     a = np.asarray(array)
     if dt == np.float16:
         a = a.astype(np.float16).astype(np.float32)
-    host = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64 if dt == np.float64 else np.float32))
-    if host.dim() == 1:
-        host = host[:, None]
-    return host.pin_memory().to(device, non_blocking=True)
+    work = np.float64 if dt == np.float64 else np.float32
+    if a.ndim == 1:
+        a = a[:, None]
+    # cast straight into a cached pinned staging buffer (one pass over the data, no per-call pinning)
+    stage = _staging(a.shape, work)
+    np.copyto(stage.numpy(), a, casting="unsafe")
+    out = stage.to(device, non_blocking=True)
+    torch.cuda.current_stream(device).synchronize()   # the staging buffer is reused by the next call
+    return out
+
+
+_STAGING = {}
+
+
+def _staging(shape, dtype):
+    key = (tuple(shape), np.dtype(dtype).str)
+    buf = _STAGING.get(key)
+    if buf is None:
+        if len(_STAGING) > 16:
+            _STAGING.clear()
+        buf = torch.empty(tuple(shape), dtype=torch.float64 if np.dtype(dtype) == np.float64 else torch.float32).pin_memory()
+        _STAGING[key] = buf
+    return buf
 
 
 class _GpuTimer:

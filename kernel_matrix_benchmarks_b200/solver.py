@@ -168,24 +168,79 @@ class CgResult:
     converged: bool
 
 
-def cg_solve(ops, comm, a_local, n_total, *, lam=0.0, rtol=1e-6, max_iter=500, check_every=1):
-    """Solve (K + lam I) x = a for the rows this rank owns.  Every rank runs the same loop."""
+class _LaggedFlag:
+    """Convergence test without stalling the device: the flag of iteration k is copied to pinned host memory
+    asynchronously and read while iteration k+1 is already enqueued, so the host stays one iteration ahead of
+    the GPU (the solve then runs at most one iteration past convergence).  CPU tensors: read at once."""
+
+    def __init__(self, device):
+        self.cuda = device.type == "cuda"
+        if self.cuda:
+            self.host = [torch.zeros(1, dtype=torch.bool).pin_memory() for _ in range(2)]
+            self.event = [torch.cuda.Event() for _ in range(2)]
+        self.pending = None
+        self.k = 0
+
+    def push(self, flag):
+        """Returns the value of the PREVIOUS flag (None if there is none yet)."""
+        previous = self.wait()
+        if not self.cuda:
+            self.pending = bool(flag)
+            return previous
+        slot = self.k & 1
+        self.host[slot].copy_(flag.reshape(1), non_blocking=True)
+        self.event[slot].record()
+        self.pending = slot
+        self.k += 1
+        return previous
+
+    def wait(self):
+        if self.pending is None:
+            return None
+        if not self.cuda:
+            value, self.pending = self.pending, None
+            return value
+        slot, self.pending = self.pending, None
+        self.event[slot].synchronize()
+        return bool(self.host[slot].item())
+
+
+def cg_solve(ops, comm, a_local, n_total, *, lam=0.0, rtol=1e-6, max_iter=500, check_every=1, lagged_check=True):
+    """Solve (K + lam I) x = a for the rows this rank owns.  Every rank runs the same loop.
+
+    ``lagged_check`` (CUDA only, check_every == 1): test convergence on the flag of the previous iteration so
+    that enqueuing iteration k+1 overlaps the device work of iteration k (see _LaggedFlag); the iterate
+    returned is the one the blocking check would have returned."""
+    if check_every != 1:
+        lagged_check = False
     x, r, p, rs = ops.init(a_local)
     comm.all_reduce(rs)
     rs0 = rs.clone()
     pAp, rs_new = torch.empty_like(rs), torch.empty_like(rs)
     tol2 = float(rtol) ** 2
     it, done = 0, bool((rs0 <= 0).all())
+    lag = _LaggedFlag(rs.device) if (lagged_check and rs.device.type == "cuda") else None
+    x_prev = torch.empty_like(x) if lag is not None else None
     while not done and it < max_iter:
         p_full = comm.all_gather(p, n_total)
         Ap = ops.matvec(p_full)
         comm.all_reduce(ops.shift_dot(Ap, p, float(lam), pAp))
+        if lag is not None:
+            x_prev.copy_(x)   # the iterate the previous flag speaks about (N floats: microseconds)
         comm.all_reduce(ops.update(x, r, p, Ap, rs, pAp, rs_new))
         ops.direction(p, r, rs_new, rs)
-        rs, rs_new = rs_new, rs
+        rs, rs_new = rs_new, rs   # rs: residual norms after this iteration, rs_new: those before it
         it += 1
         if it % check_every == 0 or it == max_iter:
-            done = bool((rs <= tol2 * rs0).all())  # the only host synchronisation in the loop
+            flag = (rs <= tol2 * rs0).all()
+            if lag is None:
+                done = bool(flag)  # the only host synchronisation in the loop
+            elif lag.push(flag):
+                # the PREVIOUS iterate had already converged: return exactly that one (same result as the
+                # blocking check; the extra iteration only cost device time that overlapped the host)
+                x, rs, it, done = x_prev, rs_new, it - 1, True
+    if lag is not None and not done and lag.wait():
+        done = True   # the last pushed flag (iteration max_iter) was true
     safe = torch.where(rs0 > 0, rs0, torch.ones_like(rs0))
     rel = float(torch.sqrt(rs / safe).max()) if rs0.numel() else 0.0
     return CgResult(x=x, iterations=it, rel_residual=rel, converged=bool((rs <= tol2 * rs0).all()))
