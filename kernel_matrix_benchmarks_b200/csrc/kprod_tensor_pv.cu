@@ -36,17 +36,12 @@ constexpr int THREADS = 64 + EPI_THREADS;
 static_assert(CPT % 16 == 0, "tcgen05.ld/st in 16-column chunks");
 constexpr int TMEM_COLS = 512;
 constexpr int COL_S = 0, COL_PH = 128, COL_PL = 192, COL_O = 256;
-constexpr int COL_UH = 320, COL_UL = 384;   // u tile (hi, lo) when D <= 64: A operand of the S MMAs from tensor memory
-constexpr int U_TMEM_MAX_D = 0;   // 64 enables the TMEM-resident u tile (experimental: not faster on B200 yet, one parity failure)
 constexpr int MAX_EB = 64;             // signal columns per pass
 constexpr float kLazyRescale = 64.f;   // rescale O only when the row maximum grows by more than 2^64
 
 struct Params {
     const float* un;
     const float* vn;
-    const float* uh;          // (N, Dp) TF32 hi / lo of the scaled targets (prepass), for the TMEM-resident u tile
-    const float* ul;
-    int Dp, u_in_tmem;
     float* out;
     float* partial;
     int* tile_counter;
@@ -72,7 +67,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char* u_region = smem;                                   // kblocks x [A hi 16 KB | A lo 16 KB]
-    unsigned char* ring = u_region + (P.u_in_tmem ? 0 : P.kblocks * 2 * A_TILE_BYTES);    // stages x 16 KB
+    unsigned char* ring = u_region + P.kblocks * 2 * A_TILE_BYTES;    // stages x 16 KB
     float* aux = reinterpret_cast<float*>(ring + P.stages * SLOT_BYTES);   // 2 x TN floats (|v|^2)
     float* cmbuf = aux + 2 * TN;                                            // 2 x NG x TM: per-group row maxima of a tile
     float* ksbuf = cmbuf + 2 * NG * TM;                                     // NG x TM: per-group sums of weights
@@ -84,8 +79,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
     uint64_t* u_free = u_full + 1;
     uint64_t* p_ready = u_free + 1;
     uint64_t* p_free = p_ready + 1;
-    uint64_t* utm_full = p_free + 1;
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(utm_full + 1);
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(p_free + 1);
     int* s_flag = reinterpret_cast<int*>(tmem_base_smem + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -102,7 +96,6 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
         mbar_init(u_free, 1);
         mbar_init(p_ready, EPI_WARPS);
         mbar_init(p_free, 1);
-        mbar_init(utm_full, 4);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
@@ -131,7 +124,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
             long long prev = -1;
             for (long long u = u0; u < u1; ++u) {
                 const int tile = static_cast<int>(u / nsb);
-                if (!P.u_in_tmem && (u == u0 || u % nsb == 0)) {   // new row tile: (re)load the resident u tile
+                if (u == u0 || u % nsb == 0) {   // new row tile: (re)load the resident u tile
                     mbar_wait(u_free, (seg & 1) ^ 1);
                     mbar_arrive_expect_tx(u_full, P.kblocks * 2 * A_TILE_BYTES);
                     for (int kb = 0; kb < P.kblocks; ++kb) {
@@ -157,9 +150,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
     } else if (warp == 1) {
         // ------------------------------------- MMA issuer -------------------------------------
         // All 32 lanes walk the loop and wait on the barriers; one elected lane issues (see elect_one).
-        // Order: S(0), S(1), PV(0), S(2), PV(1), ...; at the first tile of a row segment whose u tile lives
-        // in TMEM the pending PV goes first (the epilogue writes the new u tile only after it has finished
-        // the previous segment, which needs that PV).
+        // Order: S(0), S(1), PV(0), S(2), PV(1), ...
         {
             uint32_t it = 0, n = 0, seg = 0;
             const uint32_t d_o = tmem_base + COL_O;
@@ -195,15 +186,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
             for (long long u = u0; u < u1; ++u, ++n) {
                 const bool first = (u == u0) || (u % nsb == 0);
                 if (first) {
-                    if (P.u_in_tmem) {
-                        if (pv_pending) {
-                            issue_pv(n - 1, prev_first);
-                            pv_pending = false;
-                        }
-                        mbar_wait(utm_full, seg & 1);
-                    } else {
-                        mbar_wait(u_full, seg & 1);
-                    }
+                    mbar_wait(u_full, seg & 1);
                     ++seg;
                 }
                 const int a = n & 1;
@@ -217,30 +200,15 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                     const unsigned char* bt = ring + slot * SLOT_BYTES;
                     const unsigned char* at = u_region + kb * 2 * A_TILE_BYTES;
                     if (elect_one()) {
-                        if (P.u_in_tmem) {
-                            // A = u tile from tensor memory: only the 2 KB v slice comes from shared memory.
-                            // (An SS tcgen05.mma here fetches 6 KB per 32-cycle MMA and runs at ~107 cycles.)
 #pragma unroll
-                            for (int k = 0; k < TK / UMMA_K; ++k) {
-                                const uint64_t bh = umma_desc_sw128(bt, k * UMMA_K * 4);
-                                const uint64_t bl = umma_desc_sw128(bt + HALF_SLOT, k * UMMA_K * 4);
-                                const uint32_t a_hi = tmem_base + COL_UH + kb * TK + k * UMMA_K;
-                                const uint32_t a_lo = tmem_base + COL_UL + kb * TK + k * UMMA_K;
-                                umma_tf32_ts(d_s, a_lo, bh, idesc_s, (kb | k) != 0);
-                                umma_tf32_ts(d_s, a_hi, bl, idesc_s, 1);
-                                umma_tf32_ts(d_s, a_hi, bh, idesc_s, 1);
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < TK / UMMA_K; ++k) {
-                                const uint64_t ah = umma_desc_sw128(at, k * UMMA_K * 4);
-                                const uint64_t al = umma_desc_sw128(at + A_TILE_BYTES, k * UMMA_K * 4);
-                                const uint64_t bh = umma_desc_sw128(bt, k * UMMA_K * 4);
-                                const uint64_t bl = umma_desc_sw128(bt + HALF_SLOT, k * UMMA_K * 4);
-                                umma_tf32(d_s, al, bh, idesc_s, (kb | k) != 0);
-                                umma_tf32(d_s, ah, bl, idesc_s, 1);
-                                umma_tf32(d_s, ah, bh, idesc_s, 1);
-                            }
+                        for (int k = 0; k < TK / UMMA_K; ++k) {
+                            const uint64_t ah = umma_desc_sw128(at, k * UMMA_K * 4);
+                            const uint64_t al = umma_desc_sw128(at + A_TILE_BYTES, k * UMMA_K * 4);
+                            const uint64_t bh = umma_desc_sw128(bt, k * UMMA_K * 4);
+                            const uint64_t bl = umma_desc_sw128(bt + HALF_SLOT, k * UMMA_K * 4);
+                            umma_tf32(d_s, al, bh, idesc_s, (kb | k) != 0);
+                            umma_tf32(d_s, ah, bl, idesc_s, 1);
+                            umma_tf32(d_s, ah, bh, idesc_s, 1);
                         }
                         umma_commit(&empty_bar[slot]);
                     }
@@ -249,7 +217,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                 const bool last_of_tile = (u + 1 == u1 || (u + 1) % nsb == 0);
                 if (elect_one()) {
                     umma_commit(&acc_full[a]);
-                    if (last_of_tile && !P.u_in_tmem) umma_commit(u_free);   // last S of this row tile
+                    if (last_of_tile) umma_commit(u_free);   // last S of this row tile
                 }
                 __syncwarp();
                 if (pv_pending) issue_pv(n - 1, prev_first);
@@ -295,24 +263,6 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
             const float un = row_ok ? __ldg(P.un + row) : 0.f;
             [[maybe_unused]] const long long jz = (P.row_offset + row) % (P.M + 1);
             float ksum = 0.f, ref = -INFINITY;   // ksum: this group's columns only
-            if (P.u_in_tmem && cg == 0) {
-                // this row's u (hi, lo) -> TMEM lanes; every S MMA of the previous segment has completed
-                // (their tiles were consumed above), so the columns are free
-                for (int c0 = 0; c0 < P.Dp; c0 += 16) {
-                    float h[16], l[16];
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        h[c] = row_ok ? __ldg(P.uh + row * P.Dp + c0 + c) : 0.f;
-                        l[c] = row_ok ? __ldg(P.ul + row * P.Dp + c0 + c) : 0.f;
-                    }
-                    tmem_st_cols<16>(tmem_base + COL_UH + c0 + lane_addr, h);
-                    tmem_st_cols<16>(tmem_base + COL_UL + c0 + lane_addr, l);
-                }
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(utm_full);
-            }
 
             for (int k = 0; k < cnt; ++k, ++n) {
                 const long long j0 = (sb0 + k) * TN;
@@ -531,8 +481,7 @@ int plan_pv(int64_t N, int64_t M, int D, int E, PvPlan* pl) {
     KMB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     KMB_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     pl->grid_max = sms;
-    const int u_bytes = pl->Dp <= pv::U_TMEM_MAX_D ? 0 : pl->kblocks * 2 * pv::A_TILE_BYTES;   // u tile in TMEM when it fits
-    const int fixed = 1024 + u_bytes + 2 * pv::TN * 4 + 3 * pv::NG * tc::TM * 4 + 512;
+    const int fixed = 1024 + pl->kblocks * 2 * pv::A_TILE_BYTES + 2 * pv::TN * 4 + 3 * pv::NG * tc::TM * 4 + 512;
     pl->stages = std::min(12, (smem_max - fixed) / pv::SLOT_BYTES);
     if (pl->stages < 4) return set_error(KMB_ERR_UNSUPPORTED, "not enough shared memory for D=%d", D);
     pl->smem = fixed + pl->stages * pv::SLOT_BYTES;
@@ -619,10 +568,6 @@ int tensor_pv_product(const float* x, const float* y, const float* b, float* out
         pv::Params P;
         P.un = F(pl.off_un);
         P.vn = F(pl.off_vn);
-        P.uh = uh;
-        P.ul = ul;
-        P.Dp = pl.Dp;
-        P.u_in_tmem = pl.Dp <= pv::U_TMEM_MAX_D ? 1 : 0;
         P.out = out;
         P.partial = F(pl.off_partial);
         P.tile_counter = counters;
