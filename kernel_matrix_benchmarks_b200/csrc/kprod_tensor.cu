@@ -3,14 +3,14 @@
 //   prepass   u = s (x - c), v = s (y - c)  (c = column means of y, s folds log2 e into the data),
 //             split into TF32 hi / lo parts (3xTF32: hi.hi + hi.lo + lo.hi), squared norms in FP32.
 //   main      persistent CTAs, warp-specialised:
-//               warp 0      TMA producer: 128 x 32-float tiles of A = 2u (hi, lo) and B = v (hi, lo),
-//                           SWIZZLE_128B, 3-stage mbarrier ring
-//               warp 1      MMA issuer: tcgen05.mma kind::tf32, M = 128, N = 128, K = 8 per instruction,
+//               warp 0      TMA producer: 128 x 32-float tiles of A = 2u (hi, lo), 256 x 32 of B = v (hi, lo),
+//                           SWIZZLE_128B, 2-stage mbarrier ring of 96 KB stages
+//               warp 1      MMA issuer: tcgen05.mma kind::tf32, M = 128, N = 256, K = 8 per instruction,
 //                           S = 2 u.v accumulated in TMEM (two accumulator stages)
 //               warps 2-5   epilogue: tcgen05.ld the S tile (one target row per thread), d2 = |u|^2 + |v|^2 - S,
 //                           kernel function (MUFU), reduce against b in registers; online max-rescale for
 //                           the row-normalised variant
-//   work      stream-K over (128-row tile x 128-source block) units, as in the direct kernel: equal
+//   work      stream-K over (128-row tile x 256-source block) units, as in the direct kernel: equal
 //             contiguous unit ranges per CTA, split tiles combined in CTA order by the last CTA to arrive.
 #include <algorithm>
 
@@ -21,10 +21,15 @@ namespace kmb {
 
 namespace tc {
 
-constexpr int TN = 128;            // sources per tile      (UMMA N, one TMEM column per source)
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = TM * TK * 4;        // 16 KB
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A hi, A lo, B hi, B lo
+#ifndef KMB_TC_TN
+#define KMB_TC_TN 256
+#endif
+constexpr int TN = KMB_TC_TN;      // sources per tile      (UMMA N, one TMEM column per source): 128 or 256
+static_assert(TN == 128 || TN == 256, "TN");
+constexpr int STAGES = TN == 256 ? 2 : 3;
+constexpr int TILE_BYTES = TM * TK * 4;        // 16 KB: one 128 x 32-float A tile
+constexpr int B_TILE_BYTES = TN * TK * 4;      // one TN x 32-float B tile
+constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;    // A hi, A lo, B hi, B lo
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * TN;     // 256 columns of 32-bit
 constexpr int EPI_THREADS = 128;
@@ -101,7 +106,7 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
                     tma_load_2d(st + 0 * TILE_BYTES, &map_ah, kb * TK, row0, &full_bar[stage]);
                     tma_load_2d(st + 1 * TILE_BYTES, &map_al, kb * TK, row0, &full_bar[stage]);
                     tma_load_2d(st + 2 * TILE_BYTES, &map_bh, kb * TK, src0, &full_bar[stage]);
-                    tma_load_2d(st + 3 * TILE_BYTES, &map_bl, kb * TK, src0, &full_bar[stage]);
+                    tma_load_2d(st + 2 * TILE_BYTES + B_TILE_BYTES, &map_bl, kb * TK, src0, &full_bar[stage]);
                 }
             }
         }
@@ -126,7 +131,7 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
                             const uint64_t ah = umma_desc_sw128(st + 0 * TILE_BYTES, k * UMMA_K * 4);
                             const uint64_t al = umma_desc_sw128(st + 1 * TILE_BYTES, k * UMMA_K * 4);
                             const uint64_t bh = umma_desc_sw128(st + 2 * TILE_BYTES, k * UMMA_K * 4);
-                            const uint64_t bl = umma_desc_sw128(st + 3 * TILE_BYTES, k * UMMA_K * 4);
+                            const uint64_t bl = umma_desc_sw128(st + 2 * TILE_BYTES + B_TILE_BYTES, k * UMMA_K * 4);
                             // 3xTF32: the two small cross terms first, then hi.hi
                             umma_tf32(d_tmem, al, bh, idesc_tf32(TN), (kb | k) != 0);
                             umma_tf32(d_tmem, ah, bl, idesc_tf32(TN), 1);
@@ -164,15 +169,16 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
                 const long long j0 = (sb0 + k) * TN;
                 // stage |v|^2 and the signal of this source block in shared memory (double buffered)
                 float* ax = aux + (unit & 1) * C::AUX_FLOATS;
-                {
-                    const long long j = j0 + et;
+#pragma unroll
+                for (int jt = et; jt < TN; jt += EPI_THREADS) {
+                    const long long j = j0 + jt;
                     const bool live = j < P.M;
-                    ax[et] = live ? __ldg(P.vn + j) : 1.0e30f;   // padded sources: k underflows to 0
+                    ax[jt] = live ? __ldg(P.vn + j) : 1.0e30f;   // padded sources: k underflows to 0
 #pragma unroll
                     for (int e = 0; e < EP; ++e) {
                         float v = 0.f;
                         if (live && P.e0 + e < P.E) v = P.b ? __ldg(P.b + j * P.E + P.e0 + e) : 1.f;
-                        ax[TN + et * EP + e] = v;
+                        ax[TN + jt * EP + e] = v;
                     }
                 }
                 named_bar_sync(1, EPI_THREADS);
