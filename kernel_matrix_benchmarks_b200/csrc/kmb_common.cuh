@@ -92,10 +92,12 @@ __device__ __forceinline__ float rsqrt_approx(float x) {  // one MUFU.RSQ
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float sqrt_approx(float x) {  // one MUFU.SQRT
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
+__device__ __forceinline__ float sqrt_approx(float x) {  // one MUFU.RSQ + one FMUL, x >= 0
+    // sqrt.approx.ftz expands to MUFU.RSQ + FMUL + two FSETP/SEL fix-ups for 0 and inf; clamping the
+    // argument away from zero keeps rsqrt finite and needs no fix-up (sqrt(1e-30) = 1e-15 is below FP32
+    // resolution of the exponents it feeds)
+    const float c = fminf(fmaxf(x, 1.0e-30f), 3.0e38f);   // one FMNMX3; inf would give inf * 0
+    return c * rsqrt_approx(c);
 }
 
 // Packed FP32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: two lanes of work per issue slot).
