@@ -93,7 +93,8 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
 
     if (warp == 0) {
         // ------------------------------------ TMA producer ------------------------------------
-        if (lane == 0) {
+        // all 32 lanes walk the loop (uniform control flow); one elected lane issues (see elect_one)
+        {
             uint32_t it = 0;
             for (long long u = u0; u < u1; ++u) {
                 const int row0 = static_cast<int>(u / nsb) * TM;
@@ -101,12 +102,15 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
                 for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
                     const int stage = it % STAGES;
                     mbar_wait(&empty_bar[stage], ((it / STAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
                     unsigned char* st = stages + stage * STAGE_BYTES;
-                    tma_load_2d(st + 0 * TILE_BYTES, &map_ah, kb * TK, row0, &full_bar[stage]);
-                    tma_load_2d(st + 1 * TILE_BYTES, &map_al, kb * TK, row0, &full_bar[stage]);
-                    tma_load_2d(st + 2 * TILE_BYTES, &map_bh, kb * TK, src0, &full_bar[stage]);
-                    tma_load_2d(st + 2 * TILE_BYTES + B_TILE_BYTES, &map_bl, kb * TK, src0, &full_bar[stage]);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_2d(st + 0 * TILE_BYTES, &map_ah, kb * TK, row0, &full_bar[stage]);
+                        tma_load_2d(st + 1 * TILE_BYTES, &map_al, kb * TK, row0, &full_bar[stage]);
+                        tma_load_2d(st + 2 * TILE_BYTES, &map_bh, kb * TK, src0, &full_bar[stage]);
+                        tma_load_2d(st + 2 * TILE_BYTES + B_TILE_BYTES, &map_bl, kb * TK, src0, &full_bar[stage]);
+                    }
+                    __syncwarp();
                 }
             }
         }

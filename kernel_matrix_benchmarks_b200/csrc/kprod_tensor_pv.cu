@@ -107,18 +107,22 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
 
     if (warp == 0) {
         // ------------------------------------ TMA producer ------------------------------------
-        if (lane == 0) {
+        // all 32 lanes walk the loop (uniform control flow); one elected lane issues (see elect_one)
+        {
             uint32_t it = 0, seg = 0;
             auto emit_signal = [&](long long u) {
                 const int src0 = static_cast<int>(u % nsb) * TN;
                 for (int h = 0; h < 2; ++h, ++it) {
                     const int slot = it % ST;
                     mbar_wait(&empty_bar[slot], ((it / ST) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[slot], SLOT_BYTES);
                     unsigned char* dst = ring + slot * SLOT_BYTES;
                     const CUtensorMap* m = h == 0 ? &map_sh : &map_sl;
-                    tma_load_2d(dst, m, src0, P.e0, &full_bar[slot]);                  // K columns src0 .. +31
-                    tma_load_2d(dst + HALF_SLOT, m, src0 + TK, P.e0, &full_bar[slot]); // K columns src0+32 .. +63
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&full_bar[slot], SLOT_BYTES);
+                        tma_load_2d(dst, m, src0, P.e0, &full_bar[slot]);                  // K columns src0 .. +31
+                        tma_load_2d(dst + HALF_SLOT, m, src0 + TK, P.e0, &full_bar[slot]); // K columns src0+32 .. +63
+                    }
+                    __syncwarp();
                 }
             };
             long long prev = -1;
@@ -126,21 +130,27 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                 const int tile = static_cast<int>(u / nsb);
                 if (u == u0 || u % nsb == 0) {   // new row tile: (re)load the resident u tile
                     mbar_wait(u_free, (seg & 1) ^ 1);
-                    mbar_arrive_expect_tx(u_full, P.kblocks * 2 * A_TILE_BYTES);
-                    for (int kb = 0; kb < P.kblocks; ++kb) {
-                        tma_load_2d(u_region + (kb * 2 + 0) * A_TILE_BYTES, &map_ah, kb * TK, tile * TM, u_full);
-                        tma_load_2d(u_region + (kb * 2 + 1) * A_TILE_BYTES, &map_al, kb * TK, tile * TM, u_full);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(u_full, P.kblocks * 2 * A_TILE_BYTES);
+                        for (int kb = 0; kb < P.kblocks; ++kb) {
+                            tma_load_2d(u_region + (kb * 2 + 0) * A_TILE_BYTES, &map_ah, kb * TK, tile * TM, u_full);
+                            tma_load_2d(u_region + (kb * 2 + 1) * A_TILE_BYTES, &map_al, kb * TK, tile * TM, u_full);
+                        }
                     }
+                    __syncwarp();
                     ++seg;
                 }
                 const int src0 = static_cast<int>(u % nsb) * TN;
                 for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
                     const int slot = it % ST;
                     mbar_wait(&empty_bar[slot], ((it / ST) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[slot], SLOT_BYTES);
                     unsigned char* dst = ring + slot * SLOT_BYTES;
-                    tma_load_2d(dst, &map_bh, kb * TK, src0, &full_bar[slot]);
-                    tma_load_2d(dst + HALF_SLOT, &map_bl, kb * TK, src0, &full_bar[slot]);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&full_bar[slot], SLOT_BYTES);
+                        tma_load_2d(dst, &map_bh, kb * TK, src0, &full_bar[slot]);
+                        tma_load_2d(dst + HALF_SLOT, &map_bl, kb * TK, src0, &full_bar[slot]);
+                    }
+                    __syncwarp();
                 }
                 if (prev >= 0) emit_signal(prev);   // consumed by PV(n-1), issued after S(n)
                 prev = u;
