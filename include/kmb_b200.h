@@ -64,6 +64,11 @@ enum {
                                   2^(-|u|^2) 2^(2u.v) 2^(-|v|^2) is used instead (4 FMA slots per pair, not 7) */
     KMB_PATH_TENSOR_3XTF32 = 2, /* |x|^2+|y|^2-2x.y (bruteforce.py:36-49) on tcgen05, 3xTF32 split, D >= 32 */
     KMB_PATH_DIRECT_DIFF = 3,  /* KMB_PATH_DIRECT_F32 restricted to the difference form */
+    KMB_PATH_TENSOR_3XF16 = 5, /* the same tensor path with FP16 hi/lo operand planes instead of TF32 ones: the data are
+                                  centred and scaled by a power of two (chosen on the device from the column extrema)
+                                  so that the largest operand lies in [2^13, 2^15); hi + lo carry 22 significand
+                                  bits as the TF32 split does, kind::f16 MMAs run at twice the TF32 rate and the
+                                  operand planes are half as large.  What KMB_PATH_AUTO picks for D > 16. */
     KMB_PATH_DIRECT_SYM = 4    /* targets == sources (the reference's same_points, base.py:56-79): x must be the
                                   same pointer as y.  Plain Gaussian product or density, D <= 3, E == 1: every kernel
                                   value is evaluated once and feeds a_i += k b_j and a_j += k b_i (K is

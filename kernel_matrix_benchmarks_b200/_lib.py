@@ -17,7 +17,7 @@ KMB_OK, KMB_ERR_INVALID, KMB_ERR_UNSUPPORTED, KMB_ERR_WORKSPACE, KMB_ERR_CUDA = 
 
 KERNEL_IDS = {"gaussian": 0, "absolute-exponential": 1, "inverse-distance": 2}
 FLAG_NORMALIZE_ROWS, FLAG_DENSITY = 1, 2
-PATH_IDS = {"auto": 0, "direct": 1, "tensor": 2, "direct_diff": 3, "direct_sym": 4}
+PATH_IDS = {"auto": 0, "direct": 1, "tensor": 5, "tensor_tf32": 2, "tensor_f16": 5, "direct_diff": 3, "direct_sym": 4}
 
 
 class DeviceInfo(ctypes.Structure):

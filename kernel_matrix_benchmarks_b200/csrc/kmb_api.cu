@@ -174,7 +174,7 @@ static int check_product_args(int64_t N, int64_t M, int D, int E, int kid, int f
     if (kid < 0 || kid > KMB_KERNEL_INVERSE_DISTANCE) return set_error(KMB_ERR_UNSUPPORTED, "unknown kernel id %d", kid);
     if (flags & ~(KMB_FLAG_NORMALIZE_ROWS | KMB_FLAG_DENSITY)) return set_error(KMB_ERR_INVALID, "unknown flags 0x%x", flags);
     if ((flags & KMB_FLAG_DENSITY) && E != 1) return set_error(KMB_ERR_INVALID, "density estimation implies E == 1 (got %d)", E);
-    if (path < KMB_PATH_AUTO || path > KMB_PATH_DIRECT_SYM) return set_error(KMB_ERR_INVALID, "unknown path %d", path);
+    if (path < KMB_PATH_AUTO || path > KMB_PATH_TENSOR_3XF16) return set_error(KMB_ERR_INVALID, "unknown path %d", path);
     if (path == KMB_PATH_DIRECT_SYM) {
         if (N != M) return set_error(KMB_ERR_INVALID, "the symmetric path needs targets == sources (N=%lld, M=%lld)", (long long)N, (long long)M);
         if (kid != KMB_KERNEL_GAUSSIAN || (flags & KMB_FLAG_NORMALIZE_ROWS) || E != 1 || !sym_supported(D))
@@ -185,7 +185,7 @@ static int check_product_args(int64_t N, int64_t M, int D, int E, int kid, int f
 
 static int resolve_path(int D, int path) {
     if (path != KMB_PATH_AUTO) return path;
-    return D <= 16 ? KMB_PATH_DIRECT_F32 : KMB_PATH_TENSOR_3XTF32;
+    return D <= 16 ? KMB_PATH_DIRECT_F32 : KMB_PATH_TENSOR_3XF16;
 }
 
 // Enqueue the direct pipeline on `stream`: bounding-box statistics -> source packing -> main kernels.
@@ -365,7 +365,7 @@ int kmb_product_workspace_bytes(int64_t N, int64_t M, int D, int E, int kernel_i
         *bytes = pl.total_bytes;
         return KMB_OK;
     }
-    return tensor_workspace_bytes(N, M, D, E, kernel_id, flags, bytes);
+    return tensor_workspace_bytes(N, M, D, E, kernel_id, flags, p == KMB_PATH_TENSOR_3XF16 ? 1 : 0, bytes);
 }
 
 int kmb_product_f32(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D,
@@ -388,12 +388,12 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
     const int p = resolve_path(D, path);
     if (reinterpret_cast<uintptr_t>(workspace) % 256)
         return set_error(KMB_ERR_INVALID, "workspace must be 256-byte aligned");
-    if (p == KMB_PATH_TENSOR_3XTF32) {
+    if (p == KMB_PATH_TENSOR_3XTF32 || p == KMB_PATH_TENSOR_3XF16) {
         if (g_profile && !g_ev0) {
             KMB_CUDA_CHECK(cudaEventCreate(&g_ev0));
             KMB_CUDA_CHECK(cudaEventCreate(&g_ev1));
         }
-        const int rc = tensor_product(x, y, density ? nullptr : b, out, N, M, D, E, kernel_id, flags, row_offset, workspace,
+        const int rc = tensor_product(x, y, density ? nullptr : b, out, N, M, D, E, kernel_id, flags, p == KMB_PATH_TENSOR_3XF16 ? 1 : 0, row_offset, workspace,
                                       workspace_bytes, stream, g_profile ? g_ev0 : nullptr, g_profile ? g_ev1 : nullptr);
         if (rc == KMB_OK && g_profile) g_ev_valid = true;
         return rc;

@@ -10,9 +10,19 @@
 //               warps 2-5   epilogue: tcgen05.ld the S tile (one target row per thread), d2 = |u|^2 + |v|^2 - S,
 //                           kernel function (MUFU), reduce against b in registers; online max-rescale for
 //                           the row-normalised variant
-//   work      stream-K over (128-row tile x 256-source block) units, as in the direct kernel: equal
-//             contiguous unit ranges per CTA, split tiles combined in CTA order by the last CTA to arrive.
+//   work      waves of R row tiles x C CTAs per tile (R C <= grid): the CTAs of one row tile split its source
+//             blocks into C contiguous ranges, and all R CTAs with the same range index walk the SAME
+//             source blocks at the same time, so a v block is fetched from HBM once per wave and served to the
+//             other R - 1 CTAs by L2 (with equal contiguous unit ranges per CTA, the first version, every CTA
+//             sat at a different source block: 46.7 GB of DRAM reads per C3 product, 86 % of HBM peak).
+//             Row tiles split over C > 1 CTAs are combined in range order by the last CTA to arrive.
+//   operands  ELT_TF32: 3xTF32 (hi.hi + hi.lo + lo.hi), 32 floats per 128-byte K block.
+//             ELT_F16:  the same three-term split with FP16 hi / lo parts of the data scaled by a power of
+//             two (max |operand| in [2^13, 2^15)): 22 significand bits as 3xTF32, kind::f16 runs at twice
+//             the TF32 rate and moves half the bytes; 64 halves per K block; S is rescaled in the epilogue.
 #include <algorithm>
+
+#include <cuda_fp16.h>
 
 #include "kprod_tensor.cuh"
 #include "tensor_common.cuh"
@@ -27,8 +37,8 @@ namespace tc {
 constexpr int TN = KMB_TC_TN;      // sources per tile      (UMMA N, one TMEM column per source): 128 or 256
 static_assert(TN == 128 || TN == 256, "TN");
 constexpr int STAGES = TN == 256 ? 2 : 3;
-constexpr int TILE_BYTES = TM * TK * 4;        // 16 KB: one 128 x 32-float A tile
-constexpr int B_TILE_BYTES = TN * TK * 4;      // one TN x 32-float B tile
+constexpr int TILE_BYTES = TM * 128;           // 16 KB: one 128-row A tile of 128-byte K blocks
+constexpr int B_TILE_BYTES = TN * 128;         // one TN-row B tile
 constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;    // A hi, A lo, B hi, B lo
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * TN;     // 256 columns of 32-bit
@@ -43,10 +53,42 @@ struct Params {
     float* out;          // (N, E)
     float* partial;
     int* tile_counter;
+    const float* sscale; // ELT_F16: S = sscale[1] * accumulator (2^-2p); unused for TF32
     long long N, M, row_offset;
     int E, e0;
-    int n_tiles, nsb, kblocks;
+    int n_tiles, nsb, kblocks, ksteps_last;
+    int R, C, W, R_last, C_last, slots_per_wave;   // wave schedule (plan_waves)
 };
+
+// work of CTA `cta` in wave w: row tile, source-block range [sb_lo, sb_hi), range index c of Cw
+struct WaveWork { int tile, sb_lo, sb_hi, c, Cw, tile_in_wave; };
+__device__ __forceinline__ bool wave_work(const Params& P, int w, int cta, WaveWork& ww) {
+    const bool last = (w == P.W - 1);
+    const int Rw = last ? P.R_last : P.R, Cw = last ? P.C_last : P.C;
+    if (cta >= Rw * Cw) return false;
+    ww.Cw = Cw;
+    ww.tile_in_wave = cta / Cw;
+    ww.c = cta - ww.tile_in_wave * Cw;
+    ww.tile = w * P.R + ww.tile_in_wave;
+    ww.sb_lo = static_cast<int>(static_cast<long long>(P.nsb) * ww.c / Cw);
+    ww.sb_hi = static_cast<int>(static_cast<long long>(P.nsb) * (ww.c + 1) / Cw);
+    return true;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// instruction descriptor: D = F32, A = B = F16, both K-major
+__host__ __device__ constexpr uint32_t idesc_f16(int n) {
+    return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(TM >> 4) << 24);
+}
 
 template <int EP, int KID, bool NORM>
 struct Cfg {
@@ -57,7 +99,7 @@ struct Cfg {
                                       (2 * STAGES + 2 * ACC_STAGES) * 8 + 16;
 };
 
-template <int EP, int KID, bool NORM>
+template <int EP, int KID, bool NORM, int ELT>
 __global__ void __launch_bounds__(THREADS, 1)
 kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                     const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
@@ -75,10 +117,7 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
     int* s_flag = reinterpret_cast<int*>(tmem_base_smem + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int G = gridDim.x;
-    const long long nsb = P.nsb;
-    const long long U = static_cast<long long>(P.n_tiles) * nsb;
-    const long long u0 = U * blockIdx.x / G, u1 = U * (blockIdx.x + 1) / G;
+    const int cta = blockIdx.x;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -95,22 +134,27 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
         // ------------------------------------ TMA producer ------------------------------------
         // all 32 lanes walk the loop (uniform control flow); one elected lane issues (see elect_one)
         {
+            constexpr int TKE = ELT == ELT_F16 ? 64 : 32;   // elements per 128-byte K block
             uint32_t it = 0;
-            for (long long u = u0; u < u1; ++u) {
-                const int row0 = static_cast<int>(u / nsb) * TM;
-                const int src0 = static_cast<int>(u % nsb) * TN;
-                for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
-                    const int stage = it % STAGES;
-                    mbar_wait(&empty_bar[stage], ((it / STAGES) & 1) ^ 1);
-                    unsigned char* st = stages + stage * STAGE_BYTES;
-                    if (elect_one()) {
-                        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                        tma_load_2d(st + 0 * TILE_BYTES, &map_ah, kb * TK, row0, &full_bar[stage]);
-                        tma_load_2d(st + 1 * TILE_BYTES, &map_al, kb * TK, row0, &full_bar[stage]);
-                        tma_load_2d(st + 2 * TILE_BYTES, &map_bh, kb * TK, src0, &full_bar[stage]);
-                        tma_load_2d(st + 2 * TILE_BYTES + B_TILE_BYTES, &map_bl, kb * TK, src0, &full_bar[stage]);
+            WaveWork ww;
+            for (int w = 0; w < P.W; ++w) {
+                if (!wave_work(P, w, cta, ww)) continue;
+                const int row0 = ww.tile * TM;
+                for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb) {
+                    const int src0 = sb * TN;
+                    for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+                        const int stage = it % STAGES;
+                        mbar_wait(&empty_bar[stage], ((it / STAGES) & 1) ^ 1);
+                        unsigned char* st = stages + stage * STAGE_BYTES;
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                            tma_load_2d(st + 0 * TILE_BYTES, &map_ah, kb * TKE, row0, &full_bar[stage]);
+                            tma_load_2d(st + 1 * TILE_BYTES, &map_al, kb * TKE, row0, &full_bar[stage]);
+                            tma_load_2d(st + 2 * TILE_BYTES, &map_bh, kb * TKE, src0, &full_bar[stage]);
+                            tma_load_2d(st + 2 * TILE_BYTES + B_TILE_BYTES, &map_bl, kb * TKE, src0, &full_bar[stage]);
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
         }
@@ -119,34 +163,47 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
         // all 32 lanes walk the loop and wait on the barriers; one elected lane issues (see elect_one)
         {
             uint32_t it = 0, unit = 0;
-            for (long long u = u0; u < u1; ++u, ++unit) {
-                const int a = unit % ACC_STAGES;
-                mbar_wait(&acc_empty[a], ((unit / ACC_STAGES) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + a * TN;
-                for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
-                    const int stage = it % STAGES;
-                    mbar_wait(&full_bar[stage], (it / STAGES) & 1);
+            WaveWork ww;
+            for (int w = 0; w < P.W; ++w) {
+                if (!wave_work(P, w, cta, ww)) continue;
+                for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++unit) {
+                    const int a = unit % ACC_STAGES;
+                    mbar_wait(&acc_empty[a], ((unit / ACC_STAGES) & 1) ^ 1);
                     tc_fence_after();
-                    const unsigned char* st = stages + stage * STAGE_BYTES;
-                    if (elect_one()) {
+                    const uint32_t d_tmem = tmem_base + a * TN;
+                    for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+                        const int stage = it % STAGES;
+                        mbar_wait(&full_bar[stage], (it / STAGES) & 1);
+                        tc_fence_after();
+                        const unsigned char* st = stages + stage * STAGE_BYTES;
+                        const int ksteps = (kb == P.kblocks - 1) ? P.ksteps_last : 4;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < TK / UMMA_K; ++k) {
-                            const uint64_t ah = umma_desc_sw128(st + 0 * TILE_BYTES, k * UMMA_K * 4);
-                            const uint64_t al = umma_desc_sw128(st + 1 * TILE_BYTES, k * UMMA_K * 4);
-                            const uint64_t bh = umma_desc_sw128(st + 2 * TILE_BYTES, k * UMMA_K * 4);
-                            const uint64_t bl = umma_desc_sw128(st + 2 * TILE_BYTES + B_TILE_BYTES, k * UMMA_K * 4);
-                            // 3xTF32: the two small cross terms first, then hi.hi
-                            umma_tf32(d_tmem, al, bh, idesc_tf32(TN), (kb | k) != 0);
-                            umma_tf32(d_tmem, ah, bl, idesc_tf32(TN), 1);
-                            umma_tf32(d_tmem, ah, bh, idesc_tf32(TN), 1);
+                            for (int k = 0; k < 4; ++k) {   // 32 bytes of K per instruction
+                                if (k < ksteps) {
+                                    const uint64_t ah = umma_desc_sw128(st + 0 * TILE_BYTES, k * 32);
+                                    const uint64_t al = umma_desc_sw128(st + 1 * TILE_BYTES, k * 32);
+                                    const uint64_t bh = umma_desc_sw128(st + 2 * TILE_BYTES, k * 32);
+                                    const uint64_t bl = umma_desc_sw128(st + 2 * TILE_BYTES + B_TILE_BYTES, k * 32);
+                                    // three-term split: the two small cross terms first, then hi.hi
+                                    if constexpr (ELT == ELT_F16) {
+                                        umma_f16(d_tmem, al, bh, idesc_f16(TN), (kb | k) != 0);
+                                        umma_f16(d_tmem, ah, bl, idesc_f16(TN), 1);
+                                        umma_f16(d_tmem, ah, bh, idesc_f16(TN), 1);
+                                    } else {
+                                        umma_tf32(d_tmem, al, bh, idesc_tf32(TN), (kb | k) != 0);
+                                        umma_tf32(d_tmem, ah, bl, idesc_tf32(TN), 1);
+                                        umma_tf32(d_tmem, ah, bh, idesc_tf32(TN), 1);
+                                    }
+                                }
+                            }
+                            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
                         }
-                        umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+                        __syncwarp();
                     }
+                    if (elect_one()) umma_commit(&acc_full[a]);   // accumulator complete
                     __syncwarp();
                 }
-                if (elect_one()) umma_commit(&acc_full[a]);   // accumulator complete
-                __syncwarp();
             }
         }
     } else {
@@ -154,12 +211,13 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
         const int et = tid - 64;                       // 0..127
         const int lane_group = warp & 3;               // TMEM lanes this warp may access
         const int row_in_tile = lane_group * 32 + lane;
+        [[maybe_unused]] float sscale = 1.f;
+        if constexpr (ELT == ELT_F16) sscale = __ldg(P.sscale + 1);
         uint32_t unit = 0;
-        long long u = u0;
-        while (u < u1) {
-            const int tile = static_cast<int>(u / nsb);
-            const long long sb0 = u - tile * nsb;
-            const int cnt = static_cast<int>(min(nsb - sb0, u1 - u));
+        WaveWork ww;
+        for (int w = 0; w < P.W; ++w) {
+            if (!wave_work(P, w, cta, ww)) continue;
+            const int tile = ww.tile;
             const long long row = static_cast<long long>(tile) * TM + row_in_tile;
             const bool row_ok = row < P.N;
             const float un = row_ok ? __ldg(P.un + row) : 0.f;
@@ -169,8 +227,8 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
 #pragma unroll
             for (int e = 0; e < EP; ++e) tot[e] = 0.f;
 
-            for (int k = 0; k < cnt; ++k, ++unit) {
-                const long long j0 = (sb0 + k) * TN;
+            for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++unit) {
+                const long long j0 = static_cast<long long>(sb) * TN;
                 // stage |v|^2 and the signal of this source block in shared memory (double buffered)
                 float* ax = aux + (unit & 1) * C::AUX_FLOATS;
 #pragma unroll
@@ -198,6 +256,10 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
                 for (int ch = 0; ch < TN / 32; ++ch) {
                     float s[32];
                     tmem_ld_32x32(t_addr + ch * 32, s);
+                    if constexpr (ELT == ELT_F16) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) s[c] *= sscale;   // exact: a power of two
+                    }
                     if constexpr (!C::ONLINE_MAX) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
@@ -245,28 +307,26 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
                 ktot += ksum;
             }
 
-            // ------------------------------ write this segment ------------------------------
-            if (cnt == nsb) {
+            // ------------------------------ write this row tile ------------------------------
+            if (ww.Cw == 1) {
                 if (row_ok) {
 #pragma unroll
                     for (int e = 0; e < EP; ++e)
                         if (P.e0 + e < P.E) P.out[row * P.E + P.e0 + e] = NORM ? tot[e] / ktot : tot[e];
                 }
             } else {
-                const int slot = (u == u0) ? 0 : 1;
-                float* mine = P.partial + (static_cast<size_t>(blockIdx.x) * 2 + slot) * (TM * C::PS);
+                // one partial per (wave, CTA); the last CTA of the row tile to arrive adds them in range order
+                const size_t slot0 = static_cast<size_t>(w) * P.slots_per_wave + static_cast<size_t>(ww.tile_in_wave) * ww.Cw;
+                float* mine = P.partial + (slot0 + ww.c) * (TM * C::PS);
 #pragma unroll
                 for (int e = 0; e < EP; ++e) mine[e * TM + row_in_tile] = tot[e];
                 if constexpr (NORM) mine[EP * TM + row_in_tile] = ktot;
                 if constexpr (C::ONLINE_MAX) mine[(EP + 1) * TM + row_in_tile] = kmax;
                 __threadfence();
                 named_bar_sync(2, EPI_THREADS);
-                const long long tile_u0 = static_cast<long long>(tile) * nsb;
-                const int c_first = static_cast<int>(((tile_u0 + 1) * G - 1) / U);
-                const int c_last = static_cast<int>(((tile_u0 + nsb) * G - 1) / U);
                 if (et == 0) {
                     const int old = atomicAdd(&P.tile_counter[tile], 1);
-                    const int last = (old == c_last - c_first);
+                    const int last = (old == ww.Cw - 1);
                     if (last) P.tile_counter[tile] = 0;
                     *s_flag = last;
                 }
@@ -279,30 +339,25 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
 #pragma unroll
                     for (int e = 0; e < EP; ++e) sum[e] = 0.f;
                     if constexpr (C::ONLINE_MAX) {
-                        for (int c = c_first; c <= c_last; ++c) {
-                            const int sl = (U * c / G) / nsb == tile ? 0 : 1;
-                            const float* ps = P.partial + (static_cast<size_t>(c) * 2 + sl) * (TM * C::PS);
-                            mx = fmaxf(mx, __ldcg(ps + (EP + 1) * TM + row_in_tile));
-                        }
+                        for (int c = 0; c < ww.Cw; ++c)
+                            mx = fmaxf(mx, __ldcg(P.partial + (slot0 + c) * (TM * C::PS) + (EP + 1) * TM + row_in_tile));
                     }
-                    for (int c = c_first; c <= c_last; ++c) {
-                        const int sl = (U * c / G) / nsb == tile ? 0 : 1;
-                        const float* ps = P.partial + (static_cast<size_t>(c) * 2 + sl) * (TM * C::PS);
-                        float w = 1.f;
+                    for (int c = 0; c < ww.Cw; ++c) {
+                        const float* ps = P.partial + (slot0 + c) * (TM * C::PS);
+                        float wgt = 1.f;
                         if constexpr (C::ONLINE_MAX) {
                             const float m = __ldcg(ps + (EP + 1) * TM + row_in_tile);
-                            w = (m == -INFINITY) ? 0.f : ex2_approx(m - mx);
+                            wgt = (m == -INFINITY) ? 0.f : ex2_approx(m - mx);
                         }
 #pragma unroll
-                        for (int e = 0; e < EP; ++e) sum[e] = fmaf(w, __ldcg(ps + e * TM + row_in_tile), sum[e]);
-                        if constexpr (NORM) l = fmaf(w, __ldcg(ps + EP * TM + row_in_tile), l);
+                        for (int e = 0; e < EP; ++e) sum[e] = fmaf(wgt, __ldcg(ps + e * TM + row_in_tile), sum[e]);
+                        if constexpr (NORM) l = fmaf(wgt, __ldcg(ps + EP * TM + row_in_tile), l);
                     }
 #pragma unroll
                     for (int e = 0; e < EP; ++e)
                         if (P.e0 + e < P.E) P.out[row * P.E + P.e0 + e] = NORM ? sum[e] / l : sum[e];
                 }
             }
-            u += cnt;
         }
     }
 
@@ -405,6 +460,182 @@ int tensor_prepass(const float* x, const float* y, int64_t N, int64_t M, int D, 
     return KMB_OK;
 }
 
+
+// ---- FP16 operands ---------------------------------------------------------------------------------
+
+// per block: column sums, minima and maxima of its rows
+static __global__ void __launch_bounds__(256) column_stats_kernel(const float* __restrict__ pts, long long n, int D,
+                                                                  float* __restrict__ psum, float* __restrict__ pmin,
+                                                                  float* __restrict__ pmax) {
+    __shared__ float sm[3][8][32];
+    const int col = blockIdx.y * 32 + (threadIdx.x & 31);
+    const int rl = threadIdx.x >> 5;
+    float acc = 0.f, lo = INFINITY, hi = -INFINITY;
+    if (col < D)
+        for (long long r = blockIdx.x * 8 + rl; r < n; r += static_cast<long long>(gridDim.x) * 8) {
+            const float v = pts[r * D + col];
+            acc += v;
+            lo = fminf(lo, v);
+            hi = fmaxf(hi, v);
+        }
+    sm[0][rl][threadIdx.x & 31] = acc;
+    sm[1][rl][threadIdx.x & 31] = lo;
+    sm[2][rl][threadIdx.x & 31] = hi;
+    __syncthreads();
+    if (rl == 0 && col < D) {
+        float t = 0.f, l = INFINITY, h = -INFINITY;
+        for (int i = 0; i < 8; ++i) {
+            t += sm[0][i][threadIdx.x];
+            l = fminf(l, sm[1][i][threadIdx.x]);
+            h = fmaxf(h, sm[2][i][threadIdx.x]);
+        }
+        psum[static_cast<size_t>(blockIdx.x) * D + col] = t;
+        pmin[static_cast<size_t>(blockIdx.x) * D + col] = l;
+        pmax[static_cast<size_t>(blockIdx.x) * D + col] = h;
+    }
+}
+// one block: centre = column means of y; the largest |point - centre| follows from the column extrema
+static __global__ void __launch_bounds__(256) center_scale_kernel(const float* __restrict__ ystats, int yblocks,
+                                                                  const float* __restrict__ xstats, int xblocks, long long M,
+                                                                  int D, int Dp, float scale, float* __restrict__ center,
+                                                                  float* __restrict__ sscale) {
+    __shared__ float red[256];
+    const size_t plane_y = static_cast<size_t>(CENTER_BLOCKS) * D;
+    float dev = 0.f;
+    for (int col = threadIdx.x; col < Dp; col += 256) {
+        float c = 0.f;
+        if (col < D) {
+            float t = 0.f, lo = INFINITY, hi = -INFINITY;
+            for (int b = 0; b < yblocks; ++b) {
+                t += ystats[static_cast<size_t>(b) * D + col];
+                lo = fminf(lo, ystats[plane_y + static_cast<size_t>(b) * D + col]);
+                hi = fmaxf(hi, ystats[2 * plane_y + static_cast<size_t>(b) * D + col]);
+            }
+            for (int b = 0; b < xblocks; ++b) {
+                lo = fminf(lo, xstats[plane_y + static_cast<size_t>(b) * D + col]);
+                hi = fmaxf(hi, xstats[2 * plane_y + static_cast<size_t>(b) * D + col]);
+            }
+            c = t / static_cast<float>(M);
+            dev = fmaxf(dev, fmaxf(hi - c, c - lo));
+        }
+        center[col] = c;
+    }
+    red[threadIdx.x] = dev;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float mw = scale * red[0];
+        int p = 0;
+        if (mw > 0.f && mw < INFINITY) p = 13 - ilogbf(mw);   // 2^p mw in [2^13, 2^14)
+        p = max(-60, min(60, p));
+        sscale[0] = exp2f(static_cast<float>(p));
+        sscale[1] = exp2f(static_cast<float>(-2 * p));
+    }
+}
+// One warp per point: w = s (p - c); operand = mult 2^p w split into FP16 hi + lo; norm2 = |w|^2.
+static __global__ void __launch_bounds__(256) split_points_f16_kernel(const float* __restrict__ pts, long long n, int D, int Dp,
+                                                                      const float* __restrict__ center, float scale, float mult,
+                                                                      const float* __restrict__ sscale, __half* __restrict__ hi,
+                                                                      __half* __restrict__ lo, float* __restrict__ norm2) {
+    const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float m2 = mult * __ldg(sscale);
+    float acc = 0.f;
+    for (int d = lane; d < Dp; d += 32) {
+        float w = 0.f;
+        if (d < D) w = scale * (pts[row * D + d] - center[d]);
+        acc = fmaf(w, w, acc);
+        w *= m2;
+        const __half h = __float2half_rn(w);
+        hi[row * Dp + d] = h;
+        lo[row * Dp + d] = __float2half_rn(w - __half2float(h));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) norm2[row] = acc;
+}
+
+int make_tensor_map_f16(CUtensorMap* map, const void* base, long long rows, int cols, int box_rows) {
+    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn enc = nullptr;
+    if (!enc) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        KMB_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) return set_error(KMB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        enc = reinterpret_cast<EncodeFn>(p);
+    }
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+    const cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(KMB_ERR_CUDA, "cuTensorMapEncodeTiled (f16) failed with %d", static_cast<int>(r));
+    return KMB_OK;
+}
+
+int tensor_prepass_f16(const float* x, const float* y, int64_t N, int64_t M, int D, int Dp16, int kid, float* center,
+                       float* stats, float* sscale, void* uh, void* ul, void* vh, void* vl, float* un, float* vn,
+                       cudaStream_t stream) {
+    const float scale = kid == KMB_KERNEL_GAUSSIAN ? 1.2011224087864498f : kid == KMB_KERNEL_ABSOLUTE_EXPONENTIAL ? 1.4426950408889634f : 1.f;
+    const size_t plane = static_cast<size_t>(CENTER_BLOCKS) * D;
+    float* ys = stats;
+    float* xs = stats + 3 * plane;
+    const int yblocks = static_cast<int>(std::min<long long>(CENTER_BLOCKS, (M + 7) / 8));
+    const int xblocks = static_cast<int>(std::min<long long>(CENTER_BLOCKS, (N + 7) / 8));
+    column_stats_kernel<<<dim3(yblocks, (D + 31) / 32), 256, 0, stream>>>(y, M, D, ys, ys + plane, ys + 2 * plane);
+    KMB_CUDA_CHECK(cudaGetLastError());
+    column_stats_kernel<<<dim3(xblocks, (D + 31) / 32), 256, 0, stream>>>(x, N, D, xs, xs + plane, xs + 2 * plane);
+    KMB_CUDA_CHECK(cudaGetLastError());
+    center_scale_kernel<<<1, 256, 0, stream>>>(ys, yblocks, xs, xblocks, M, D, Dp16, scale, center, sscale);
+    KMB_CUDA_CHECK(cudaGetLastError());
+    split_points_f16_kernel<<<static_cast<unsigned>((N * 32 + 255) / 256), 256, 0, stream>>>(
+        x, N, D, Dp16, center, scale, 2.f, sscale, static_cast<__half*>(uh), static_cast<__half*>(ul), un);
+    KMB_CUDA_CHECK(cudaGetLastError());
+    split_points_f16_kernel<<<static_cast<unsigned>((M * 32 + 255) / 256), 256, 0, stream>>>(
+        y, M, D, Dp16, center, scale, 1.f, sscale, static_cast<__half*>(vh), static_cast<__half*>(vl), vn);
+    KMB_CUDA_CHECK(cudaGetLastError());
+    count_launch(5);
+    return KMB_OK;
+}
+
+// Choose R (row tiles per wave) to minimise the number of source-block steps a CTA walks; ties go to the
+// larger R (each v block is read from HBM once per wave).  R row tiles of u must stay L2-resident.
+void plan_waves(long long n_tiles, long long nsb, int grid, size_t row_tile_bytes, WavePlan* wp) {
+    const size_t l2_budget = 48u << 20;
+    long long rmax = static_cast<long long>(l2_budget / std::max<size_t>(row_tile_bytes, 1));
+    rmax = std::max<long long>(1, std::min<long long>({rmax, static_cast<long long>(grid), n_tiles}));
+    long long best_steps = -1;
+    for (long long R = 1; R <= rmax; ++R) {
+        const long long C = std::max<long long>(1, std::min<long long>(grid / R, nsb));
+        const long long W = (n_tiles + R - 1) / R;
+        const long long Rl = n_tiles - (W - 1) * R;
+        const long long Cl = std::max<long long>(1, std::min<long long>(grid / Rl, nsb));
+        const long long steps = (W - 1) * ((nsb + C - 1) / C) + (nsb + Cl - 1) / Cl;
+        if (best_steps < 0 || steps <= best_steps) {
+            best_steps = steps;
+            wp->R = static_cast<int>(R);
+            wp->C = static_cast<int>(C);
+            wp->W = static_cast<int>(W);
+            wp->R_last = static_cast<int>(Rl);
+            wp->C_last = static_cast<int>(Cl);
+        }
+    }
+    // partial results: one slot per (wave, CTA) when the full waves split row tiles, else only the last wave does
+    const bool all = wp->C > 1 && wp->W > 1;
+    const bool any = all || wp->C_last > 1;
+    wp->slots_per_wave = all ? grid : 0;
+    wp->partial_slots = all ? static_cast<long long>(wp->W) * grid : (any ? grid : 1);
+}
+
 }  // namespace tc
 
 // ---- host side ---------------------------------------------------------------------------------------
@@ -413,13 +644,20 @@ namespace {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct TensorPlan {
-    int Dp, e_chunk, n_passes, grid_max;
+    int Dp, e_chunk, n_passes, grid, kblocks, ksteps_last;
     long long n_tiles, nsb;
-    size_t off_center, off_cpart, off_uh, off_ul, off_vh, off_vl, off_un, off_vn, off_partial, off_counter, total;
+    tc::WavePlan waves;
+    size_t esz;   // bytes per stored operand element
+    size_t off_center, off_cpart, off_sscale, off_uh, off_ul, off_vh, off_vl, off_un, off_vn, off_partial, off_counter, total;
 };
 
-int plan_tensor(int64_t N, int64_t M, int D, int E, int flags, TensorPlan* pl) {
-    pl->Dp = (D + tc::TK - 1) / tc::TK * tc::TK;
+int plan_tensor(int64_t N, int64_t M, int D, int E, int elt, TensorPlan* pl) {
+    const bool f16 = elt == tc::ELT_F16;
+    pl->Dp = f16 ? (D + 15) / 16 * 16 : (D + tc::TK - 1) / tc::TK * tc::TK;
+    const int tke = f16 ? 64 : 32;
+    pl->kblocks = (pl->Dp + tke - 1) / tke;
+    pl->ksteps_last = (pl->Dp - (pl->kblocks - 1) * tke) / (f16 ? 16 : 8);
+    pl->esz = f16 ? 2 : 4;
     pl->e_chunk = E >= 4 ? 4 : E;
     pl->n_passes = (E + pl->e_chunk - 1) / pl->e_chunk;
     pl->n_tiles = (N + tc::TM - 1) / tc::TM;
@@ -427,31 +665,32 @@ int plan_tensor(int64_t N, int64_t M, int D, int E, int flags, TensorPlan* pl) {
     int dev = 0, sms = 0;
     KMB_CUDA_CHECK(cudaGetDevice(&dev));
     KMB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    pl->grid_max = sms;
+    pl->grid = sms;
+    tc::plan_waves(pl->n_tiles, pl->nsb, pl->grid, static_cast<size_t>(tc::TM) * pl->Dp * pl->esz * 2, &pl->waves);
     const int PS = tc::MAX_EP + 2;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
     pl->off_center = take(sizeof(float) * pl->Dp);
-    pl->off_cpart = take(sizeof(float) * tc::CENTER_BLOCKS * D);
-    pl->off_uh = take(sizeof(float) * N * pl->Dp);
-    pl->off_ul = take(sizeof(float) * N * pl->Dp);
-    pl->off_vh = take(sizeof(float) * M * pl->Dp);
-    pl->off_vl = take(sizeof(float) * M * pl->Dp);
+    pl->off_cpart = take(sizeof(float) * tc::CENTER_BLOCKS * D * (f16 ? 6 : 1));
+    pl->off_sscale = take(sizeof(float) * 2);
+    pl->off_uh = take(pl->esz * N * pl->Dp);
+    pl->off_ul = take(pl->esz * N * pl->Dp);
+    pl->off_vh = take(pl->esz * M * pl->Dp);
+    pl->off_vl = take(pl->esz * M * pl->Dp);
     pl->off_un = take(sizeof(float) * N);
     pl->off_vn = take(sizeof(float) * M);
-    pl->off_partial = take(sizeof(float) * pl->grid_max * 2 * tc::TM * PS);
+    pl->off_partial = take(sizeof(float) * pl->waves.partial_slots * tc::TM * PS);
     pl->off_counter = take(sizeof(int) * pl->n_tiles);
     pl->total = o;
-    (void)flags;
     return KMB_OK;
 }
 
 using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const tc::Params);
 
-template <int EP, int KID, bool NORM>
+template <int EP, int KID, bool NORM, int ELT>
 int launch_one(const CUtensorMap* maps, const tc::Params& P, int grid, cudaStream_t stream) {
     using C = tc::Cfg<EP, KID, NORM>;
-    auto fn = tc::kprod_tensor_kernel<EP, KID, NORM>;
+    auto fn = tc::kprod_tensor_kernel<EP, KID, NORM, ELT>;
     static bool attr = false;
     if (!attr) {
         KMB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -462,53 +701,57 @@ int launch_one(const CUtensorMap* maps, const tc::Params& P, int grid, cudaStrea
     return KMB_OK;
 }
 
-template <int KID, bool NORM>
+template <int KID, bool NORM, int ELT>
 int launch_ep(int ep, const CUtensorMap* maps, const tc::Params& P, int grid, cudaStream_t stream) {
-    if (ep == 1) return launch_one<1, KID, NORM>(maps, P, grid, stream);
-    if (ep == 2) return launch_one<2, KID, NORM>(maps, P, grid, stream);
-    return launch_one<4, KID, NORM>(maps, P, grid, stream);
+    if (ep == 1) return launch_one<1, KID, NORM, ELT>(maps, P, grid, stream);
+    if (ep == 2) return launch_one<2, KID, NORM, ELT>(maps, P, grid, stream);
+    return launch_one<4, KID, NORM, ELT>(maps, P, grid, stream);
 }
 
+template <int ELT>
 int launch_any(int kid, bool norm, int ep, const CUtensorMap* maps, const tc::Params& P, int grid, cudaStream_t stream) {
     switch (kid * 2 + (norm ? 1 : 0)) {
-        case 0: return launch_ep<KMB_KERNEL_GAUSSIAN, false>(ep, maps, P, grid, stream);
-        case 1: return launch_ep<KMB_KERNEL_GAUSSIAN, true>(ep, maps, P, grid, stream);
-        case 2: return launch_ep<KMB_KERNEL_ABSOLUTE_EXPONENTIAL, false>(ep, maps, P, grid, stream);
-        case 3: return launch_ep<KMB_KERNEL_ABSOLUTE_EXPONENTIAL, true>(ep, maps, P, grid, stream);
-        case 4: return launch_ep<KMB_KERNEL_INVERSE_DISTANCE, false>(ep, maps, P, grid, stream);
-        default: return launch_ep<KMB_KERNEL_INVERSE_DISTANCE, true>(ep, maps, P, grid, stream);
+        case 0: return launch_ep<KMB_KERNEL_GAUSSIAN, false, ELT>(ep, maps, P, grid, stream);
+        case 1: return launch_ep<KMB_KERNEL_GAUSSIAN, true, ELT>(ep, maps, P, grid, stream);
+        case 2: return launch_ep<KMB_KERNEL_ABSOLUTE_EXPONENTIAL, false, ELT>(ep, maps, P, grid, stream);
+        case 3: return launch_ep<KMB_KERNEL_ABSOLUTE_EXPONENTIAL, true, ELT>(ep, maps, P, grid, stream);
+        case 4: return launch_ep<KMB_KERNEL_INVERSE_DISTANCE, false, ELT>(ep, maps, P, grid, stream);
+        default: return launch_ep<KMB_KERNEL_INVERSE_DISTANCE, true, ELT>(ep, maps, P, grid, stream);
     }
 }
 
 }  // namespace
 
-int tensor_workspace_bytes(int64_t N, int64_t M, int D, int E, int kid, int flags, size_t* bytes) {
+int tensor_workspace_bytes(int64_t N, int64_t M, int D, int E, int kid, int flags, int elt, size_t* bytes) {
     (void)kid;
+    (void)flags;
     if (tensor_pv_applicable(D, E)) return tensor_pv_workspace_bytes(N, M, D, E, bytes);
     TensorPlan pl{};
-    if (int rc = plan_tensor(N, M, D, E, flags, &pl)) return rc;
+    if (int rc = plan_tensor(N, M, D, E, elt, &pl)) return rc;
     *bytes = pl.total;
     return KMB_OK;
 }
 
 int tensor_product(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D, int E,
-                   int kid, int flags, int64_t row_offset, void* workspace, size_t workspace_bytes, cudaStream_t stream,
-                   cudaEvent_t ev0, cudaEvent_t ev1) {
+                   int kid, int flags, int elt, int64_t row_offset, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1) {
     if (tensor_pv_applicable(D, E))
         return tensor_pv_product(x, y, b, out, N, M, D, E, kid, flags, row_offset, workspace, workspace_bytes, stream, ev0, ev1);
     TensorPlan pl{};
-    if (int rc = plan_tensor(N, M, D, E, flags, &pl)) return rc;
+    if (int rc = plan_tensor(N, M, D, E, elt, &pl)) return rc;
     if (!workspace || workspace_bytes < pl.total)
         return set_error(KMB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);
     if (N >= (1ll << 31) - tc::TM || M >= (1ll << 31) - tc::TN)
         return set_error(KMB_ERR_UNSUPPORTED, "tensor path indexes rows with 32-bit TMA coordinates");
+    const bool f16 = elt == tc::ELT_F16;
     char* ws = static_cast<char*>(workspace);
     float* center = reinterpret_cast<float*>(ws + pl.off_center);
     float* cpart = reinterpret_cast<float*>(ws + pl.off_cpart);
-    float* uh = reinterpret_cast<float*>(ws + pl.off_uh);
-    float* ul = reinterpret_cast<float*>(ws + pl.off_ul);
-    float* vh = reinterpret_cast<float*>(ws + pl.off_vh);
-    float* vl = reinterpret_cast<float*>(ws + pl.off_vl);
+    float* sscale = reinterpret_cast<float*>(ws + pl.off_sscale);
+    void* uh = ws + pl.off_uh;
+    void* ul = ws + pl.off_ul;
+    void* vh = ws + pl.off_vh;
+    void* vl = ws + pl.off_vl;
     float* un = reinterpret_cast<float*>(ws + pl.off_un);
     float* vn = reinterpret_cast<float*>(ws + pl.off_vn);
     float* partial = reinterpret_cast<float*>(ws + pl.off_partial);
@@ -517,15 +760,24 @@ int tensor_product(const float* x, const float* y, const float* b, float* out, i
     const bool density = flags & KMB_FLAG_DENSITY;
 
     KMB_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(int) * pl.n_tiles, stream));
-    if (int rc = tc::tensor_prepass(x, y, N, M, D, pl.Dp, kid, center, cpart, uh, ul, vh, vl, un, vn, stream)) return rc;
     CUtensorMap maps[4];
-    if (int rc = tc::make_tensor_map(&maps[0], uh, N, pl.Dp, tc::TM)) return rc;
-    if (int rc = tc::make_tensor_map(&maps[1], ul, N, pl.Dp, tc::TM)) return rc;
-    if (int rc = tc::make_tensor_map(&maps[2], vh, M, pl.Dp, tc::TN)) return rc;
-    if (int rc = tc::make_tensor_map(&maps[3], vl, M, pl.Dp, tc::TN)) return rc;
+    if (f16) {
+        if (int rc = tc::tensor_prepass_f16(x, y, N, M, D, pl.Dp, kid, center, cpart, sscale, uh, ul, vh, vl, un, vn, stream)) return rc;
+        if (int rc = tc::make_tensor_map_f16(&maps[0], uh, N, pl.Dp, tc::TM)) return rc;
+        if (int rc = tc::make_tensor_map_f16(&maps[1], ul, N, pl.Dp, tc::TM)) return rc;
+        if (int rc = tc::make_tensor_map_f16(&maps[2], vh, M, pl.Dp, tc::TN)) return rc;
+        if (int rc = tc::make_tensor_map_f16(&maps[3], vl, M, pl.Dp, tc::TN)) return rc;
+    } else {
+        if (int rc = tc::tensor_prepass(x, y, N, M, D, pl.Dp, kid, center, cpart, static_cast<float*>(uh), static_cast<float*>(ul),
+                                        static_cast<float*>(vh), static_cast<float*>(vl), un, vn, stream))
+            return rc;
+        if (int rc = tc::make_tensor_map(&maps[0], static_cast<float*>(uh), N, pl.Dp, tc::TM)) return rc;
+        if (int rc = tc::make_tensor_map(&maps[1], static_cast<float*>(ul), N, pl.Dp, tc::TM)) return rc;
+        if (int rc = tc::make_tensor_map(&maps[2], static_cast<float*>(vh), M, pl.Dp, tc::TN)) return rc;
+        if (int rc = tc::make_tensor_map(&maps[3], static_cast<float*>(vl), M, pl.Dp, tc::TN)) return rc;
+    }
 
-    const long long units = pl.n_tiles * pl.nsb;
-    const int grid = static_cast<int>(std::min<long long>(pl.grid_max, units));
+    const int grid = pl.grid;
     for (int pass = 0; pass < pl.n_passes; ++pass) {
         tc::Params P;
         P.un = un;
@@ -534,6 +786,7 @@ int tensor_product(const float* x, const float* y, const float* b, float* out, i
         P.out = out;
         P.partial = partial;
         P.tile_counter = counters;
+        P.sscale = sscale;
         P.N = N;
         P.M = M;
         P.row_offset = row_offset;
@@ -541,9 +794,18 @@ int tensor_product(const float* x, const float* y, const float* b, float* out, i
         P.e0 = pass * pl.e_chunk;
         P.n_tiles = static_cast<int>(pl.n_tiles);
         P.nsb = static_cast<int>(pl.nsb);
-        P.kblocks = pl.Dp / tc::TK;
+        P.kblocks = pl.kblocks;
+        P.ksteps_last = pl.ksteps_last;
+        P.R = pl.waves.R;
+        P.C = pl.waves.C;
+        P.W = pl.waves.W;
+        P.R_last = pl.waves.R_last;
+        P.C_last = pl.waves.C_last;
+        P.slots_per_wave = pl.waves.slots_per_wave;
         if (ev0 && pass == pl.n_passes - 1) KMB_CUDA_CHECK(cudaEventRecord(ev0, stream));
-        if (int rc = launch_any(kid, norm, pl.e_chunk, maps, P, grid, stream)) return rc;
+        if (int rc = f16 ? launch_any<tc::ELT_F16>(kid, norm, pl.e_chunk, maps, P, grid, stream)
+                         : launch_any<tc::ELT_TF32>(kid, norm, pl.e_chunk, maps, P, grid, stream))
+            return rc;
         if (ev1 && pass == pl.n_passes - 1) KMB_CUDA_CHECK(cudaEventRecord(ev1, stream));
         count_launch();
     }

@@ -7,12 +7,13 @@
 
 namespace kmb {
 
-int tensor_workspace_bytes(int64_t N, int64_t M, int D, int E, int kid, int flags, size_t* bytes);
+// elt: 0 = TF32 hi/lo operands (KMB_PATH_TENSOR_3XTF32), 1 = FP16 hi/lo operands (KMB_PATH_TENSOR_3XF16)
+int tensor_workspace_bytes(int64_t N, int64_t M, int D, int E, int kid, int flags, int elt, size_t* bytes);
 
 // Enqueue the whole tensor-path product on `stream` (prepass + main kernel per signal chunk).
 // ev0/ev1: optional events recorded around the last main kernel.
 int tensor_product(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D, int E,
-                   int kid, int flags, int64_t row_offset, void* workspace, size_t workspace_bytes,
+                   int kid, int flags, int elt, int64_t row_offset, void* workspace, size_t workspace_bytes,
                    cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1);
 
 }  // namespace kmb

@@ -11,6 +11,8 @@ namespace tc {
 constexpr int TM = 128;            // target rows per tile  (UMMA M, one TMEM lane per row)
 constexpr int TK = 32;             // floats per K block = one 128-byte swizzle atom
 constexpr int UMMA_K = 8;          // TF32: 32 bytes per instruction
+constexpr int ELT_TF32 = 0;        // operand element: TF32 hi / lo planes (fp32 storage)
+constexpr int ELT_F16 = 1;         // FP16 hi / lo planes of power-of-two scaled data (see tensor_prepass_f16)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -168,6 +170,21 @@ int make_tensor_map(CUtensorMap* map, const float* base, long long rows, int col
 int tensor_prepass(const float* x, const float* y, int64_t N, int64_t M, int D, int Dp, int kid, float* center,
                    float* cpart, float* uh, float* ul, float* vh, float* vl, float* un, float* vn, cudaStream_t stream);
 constexpr int CENTER_BLOCKS = 128;
+
+// FP16 operands.  (rows, cols) half row-major; box = 64 halves x box_rows rows, 128-byte swizzle.
+int make_tensor_map_f16(CUtensorMap* map, const void* base, long long rows, int cols, int box_rows);
+// centre (column means of y); p = power of two that brings max |s (point - c)| over x and y into [2^13, 2^14);
+// FP16 hi / lo split of A = 2 s 2^p (x - c) and B = s 2^p (y - c) (Dp16 = D rounded up to 16 columns, zero
+// padded), squared norms of s (point - c) in FP32; sscale[0] = 2^p, sscale[1] = 2^-2p (device).
+// stats: 6 * CENTER_BLOCKS * D floats of scratch.
+int tensor_prepass_f16(const float* x, const float* y, int64_t N, int64_t M, int D, int Dp16, int kid, float* center,
+                       float* stats, float* sscale, void* uh, void* ul, void* vh, void* vl, float* un, float* vn,
+                       cudaStream_t stream);
+
+// L2-aware wave schedule shared by the tensor kernels (see kprod_tensor.cu): full waves of R row tiles x C CTAs,
+// a last wave of R_last x C_last.
+struct WavePlan { int R, C, W, R_last, C_last, slots_per_wave; long long partial_slots; };
+void plan_waves(long long n_tiles, long long nsb, int grid, size_t row_tile_bytes, WavePlan* wp);
 
 }  // namespace tc
 

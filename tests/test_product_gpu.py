@@ -222,14 +222,18 @@ def test_c_abi_error_paths():
 # ---------------------------------------------------------------- tensor-core (3xTF32) path
 
 
+TENSOR_PATHS = ["tensor_f16", "tensor_tf32"]   # FP16 hi/lo operands (what "auto" picks) and the TF32 hi/lo ones
+
+
+@pytest.mark.parametrize("path", TENSOR_PATHS)
 @pytest.mark.parametrize("kernel", ["gaussian", "absolute-exponential", "inverse-distance"])
 @pytest.mark.parametrize("N,M,D,E", [(1, 1, 17, 1), (130, 257, 33, 1), (300, 1000, 64, 2), (129, 640, 100, 5), (257, 129, 784, 1)])
-def test_tensor_path_shapes(kernel, N, M, D, E):
+def test_tensor_path_shapes(kernel, N, M, D, E, path):
     rng = np.random.RandomState(N + M + D)
     r = (3.0 / D) ** 0.5
     y, x, b = r * rng.rand(M, D), r * rng.rand(N, D), rng.randn(M, E)
     for norm in (False, True):
-        out, extra = run_plugin(kernel, y, x, b, normalize_rows=norm)
+        out, extra = run_plugin(kernel, y, x, b, normalize_rows=norm, path=path)
         want = c_oracle.kernel_product(kernel, y, x, b, normalize_rows=norm)
         if np.isnan(want).any():  # 0/0 rows (e.g. the 1 x 1 inverse-distance matrix): the reference returns NaN too
             assert np.array_equal(np.isnan(out), np.isnan(want))
@@ -250,15 +254,54 @@ def test_tensor_path_agrees_with_direct_path_on_small_d():
     assert orc.rel_l2(tensor, direct) <= TOL_TENSOR
 
 
-def test_tensor_path_uncentred_data():
+@pytest.mark.parametrize("path", TENSOR_PATHS)
+def test_tensor_path_uncentred_data(path):
     """Offset data (all coordinates near 50): the prepass centres on the source mean, so the
     cancellation in |x|^2 + |y|^2 - 2x.y stays at the scale of the spread, not of the offset."""
     rng = np.random.RandomState(9)
     y = (50.0 + 0.2 * rng.rand(2000, 64)).astype(np.float32).astype(np.float64)
     x = (50.0 + 0.2 * rng.rand(300, 64)).astype(np.float32).astype(np.float64)
     b = rng.randn(2000, 1)
-    out, _ = run_plugin("gaussian", y, x, b)
+    out, _ = run_plugin("gaussian", y, x, b, path=path)
     assert orc.rel_l2(out, c_oracle.kernel_product("gaussian", y, x, b)) <= TOL_TENSOR
+
+
+@pytest.mark.parametrize("path", TENSOR_PATHS)
+@pytest.mark.parametrize("N,M,D", [(20000, 3000, 40), (128 * 79, 256 * 9 + 1, 48), (128 * 149, 300, 20), (5000, 70000, 32)])
+def test_tensor_path_wave_schedule(N, M, D, path):
+    """Shapes that exercise the wave schedule: several waves, row tiles split over many CTAs (combined by
+    the last CTA to arrive), a last wave with a different split, more row tiles than CTAs.  Sampled rows."""
+    rng = np.random.RandomState(N + M)
+    r = (3.0 / D) ** 0.5
+    y, x, b = r * rng.rand(M, D), r * rng.rand(N, D), rng.randn(M, 1)
+    rows = np.unique(np.concatenate([np.arange(0, N, 97), [N - 1]]))
+    for norm in (False, True):
+        out, _ = run_plugin("gaussian", y, x, b, normalize_rows=norm, path=path)
+        want = c_oracle.kernel_product("gaussian", y, x, b, normalize_rows=norm, rows=rows)
+        err = orc.rel_l2(out[rows], want)
+        assert err <= TOL_TENSOR, (norm, err)
+    again, _ = run_plugin("gaussian", y, x, b, normalize_rows=True, path=path)
+    assert np.array_equal(again, out)   # deterministic: fixed combine order
+
+
+def test_tensor_f16_scaling_range():
+    """FP16 operand planes: the power-of-two scale follows the data (tiny and huge coordinates, one outlier
+    column) and the result keeps FP32-class accuracy."""
+    rng = np.random.RandomState(11)
+    D = 48
+    base_y, base_x, b = rng.rand(3000, D), rng.rand(400, D), rng.randn(3000, 1)
+    r = (3.0 / D) ** 0.5
+    for name, scale in (("unit", r), ("tiny", 1e-3 * r), ("wide", 4.0 * r)):
+        y, x = scale * base_y, scale * base_x
+        out, _ = run_plugin("gaussian", y, x, b, path="tensor_f16")
+        err = orc.rel_l2(out, c_oracle.kernel_product("gaussian", y, x, b))
+        assert err <= 1e-5, (name, err)
+    # one far outlier among the sources stretches the scale by 2^7: the other points keep their accuracy
+    y = r * base_y
+    y[0, :] += 100.0 * r
+    out, _ = run_plugin("gaussian", y, r * base_x, b, path="tensor_f16")
+    err = orc.rel_l2(out, c_oracle.kernel_product("gaussian", y, r * base_x, b))
+    assert err <= TOL_TENSOR, err
 
 
 def test_config_c3_sampled():
@@ -267,12 +310,13 @@ def test_config_c3_sampled():
     from kernel_matrix_benchmarks_b200 import datasets
 
     ds = datasets.config_c3()
-    out, extra = run_plugin("gaussian", ds.source_points, ds.target_points, ds.source_signal)
     rows = np.arange(0, ds.N, 40)
     want = c_oracle.kernel_product("gaussian", ds.source_points, ds.target_points, ds.source_signal, rows=rows)
-    err = orc.rel_l2(out[rows], want)
-    print(f"C3 sampled rel-L2 {err:.2e} {extra}")
-    assert err <= TOL_TENSOR
+    for path in TENSOR_PATHS:
+        out, extra = run_plugin("gaussian", ds.source_points, ds.target_points, ds.source_signal, path=path)
+        err = orc.rel_l2(out[rows], want)
+        print(f"C3 sampled rel-L2 {path} {err:.2e} {extra}")
+        assert err <= TOL_TENSOR
 
 
 def test_config_c4_reduced():
