@@ -723,8 +723,8 @@ int launch_any(int kid, bool norm, int ep, const CUtensorMap* maps, const tc::Pa
 }  // namespace
 
 int tensor_workspace_bytes(int64_t N, int64_t M, int D, int E, int kid, int flags, int elt, size_t* bytes) {
-    (void)kid;
     (void)flags;
+    if (elt == tc::ELT_F16 && tensor_pv16_applicable(D, E, kid)) return tensor_pv16_workspace_bytes(N, M, D, E, bytes);
     if (tensor_pv_applicable(D, E)) return tensor_pv_workspace_bytes(N, M, D, E, bytes);
     TensorPlan pl{};
     if (int rc = plan_tensor(N, M, D, E, elt, &pl)) return rc;
@@ -735,6 +735,8 @@ int tensor_workspace_bytes(int64_t N, int64_t M, int D, int E, int kid, int flag
 int tensor_product(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D, int E,
                    int kid, int flags, int elt, int64_t row_offset, void* workspace, size_t workspace_bytes,
                    cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1) {
+    if (elt == tc::ELT_F16 && tensor_pv16_applicable(D, E, kid))
+        return tensor_pv16_product(x, y, b, out, N, M, D, E, kid, flags, workspace, workspace_bytes, stream, ev0, ev1);
     if (tensor_pv_applicable(D, E))
         return tensor_pv_product(x, y, b, out, N, M, D, E, kid, flags, row_offset, workspace, workspace_bytes, stream, ev0, ev1);
     TensorPlan pl{};

@@ -1,0 +1,681 @@
+// kprod_tensor_pv16: a_i = sum_j k(x_i, y_j) b_j for 16 < D <= 128 and E > 4, Gaussian and exponential kernels --
+// both contractions on the tensor cores with FP16 hi / lo operand planes (config C4: exponential-kernel
+// attention, N = M = 262144, D = E = 64).  Same algorithm as kprod_tensor_pv.cu (TF32 planes), re-shaped after
+// tools/ubench_umma.cu: a 128 x 64 x 8 SS MMA takes 60 cycles for 32 cycles of math, a 128 x 128 x 16 one 75 for
+// 64, and kind::f16 does twice the work of kind::tf32 per instruction.
+//
+//   S = 2 u.v^T   128 rows x 128 sources per block; tcgen05.mma kind::f16, three-term split
+//                 (lo.hi + hi.lo + hi.hi), A = u tile (hi, lo) resident in shared memory for the whole row
+//                 tile, B = v blocks streamed by TMA, FP32 accumulator in TMEM (two stages)
+//   P = k(S)      16 epilogue warps (4 column groups x 4 TMEM lane quarters): tcgen05.ld S, log2 of the kernel,
+//                 running reference exponent per row (lazy rescale of O when the row maximum outgrows it by
+//                 2^8, so P <= 2^8 fits FP16 and rows whose kernel values all underflow FP32 still normalise),
+//                 P = 2^(log2 k - ref) split into FP16 hi + lo, packed two per 32-bit TMEM column (tcgen05.st)
+//   O += P.B      tcgen05.mma with A = P from TMEM (hi, lo), B = transposed signal block (FP16 hi, lo, scaled per
+//                 signal column by a power of two) from shared memory; O (128 x E) stays in TMEM for the whole
+//                 row tile and is read once
+//
+// TMEM columns: S stage 0 [0,128) | S stage 1 [128,256) | P hi [256,320) | P lo [320,384) | O [384,384+E).
+// Work split: the wave schedule of kprod_tensor.cu -- every CTA of a wave walks the SAME source blocks at the same
+// time (all of them when there are at least as many row tiles as CTAs), so v and b blocks come from L2.
+#include <algorithm>
+
+#include <cuda_fp16.h>
+
+#include "tensor_common.cuh"
+
+namespace kmb {
+namespace pv16 {
+
+using namespace tc;
+
+constexpr int TNS = 128;               // sources per S block
+constexpr int SLOT_BYTES = 32768;      // ring slot: v block of one K block (hi 16 KB | lo 16 KB) or one signal block
+constexpr int A_TILE_BYTES = TM * 128; // 16 KB: 128 rows of one 128-byte K block
+constexpr int PANEL_BYTES = 64 * 128;  // signal: 64 signal columns x 64 sources (one swizzle atom wide)
+constexpr int NG = 4;                  // epilogue column groups (4 warps each)
+constexpr int CPT = TNS / NG;          // S columns per epilogue thread (32)
+constexpr int EPI_WARPS = 4 * NG;
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
+constexpr int THREADS = 64 + EPI_THREADS;
+constexpr int TMEM_COLS = 512;
+constexpr int COL_S = 0, COL_PH = 256, COL_PL = 320, COL_O = 384;
+constexpr int MAX_EB = 64;             // signal columns per pass
+constexpr float kLazyRescale = 8.f;    // rescale O only when the row maximum outgrew the reference by 2^8
+constexpr int PS = MAX_EB + 2;         // partial record: O row, sum of weights, reference exponent
+
+struct Params {
+    const float* un;
+    const float* vn;
+    const float* sscale;       // [1] = 2^-2p: S = sscale[1] * accumulator
+    const float* binv;         // (Ep) 2^-q_e: undoes the per-column scale of the signal planes
+    float* out;
+    float* partial;
+    int* tile_counter;
+    long long N, M;
+    int E, e0, eb, ebp;        // this pass covers signal columns e0 .. e0+eb-1; ebp = eb rounded up to 32
+    int n_tiles, nsb, kblocks, ksteps_last, stages;
+    int R, C, W, R_last, C_last, slots_per_wave;
+};
+
+struct WaveWork { int tile, sb_lo, sb_hi, c, Cw, tile_in_wave; };
+__device__ __forceinline__ bool wave_work(const Params& P, int w, int cta, WaveWork& ww) {
+    const bool last = (w == P.W - 1);
+    const int Rw = last ? P.R_last : P.R, Cw = last ? P.C_last : P.C;
+    if (cta >= Rw * Cw) return false;
+    ww.Cw = Cw;
+    ww.tile_in_wave = cta / Cw;
+    ww.c = cta - ww.tile_in_wave * Cw;
+    ww.tile = w * P.R + ww.tile_in_wave;
+    ww.sb_lo = static_cast<int>(static_cast<long long>(P.nsb) * ww.c / Cw);
+    ww.sb_hi = static_cast<int>(static_cast<long long>(P.nsb) * (ww.c + 1) / Cw);
+    return true;
+}
+
+__device__ __forceinline__ void umma_f16_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d),
+                 "l"(a), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d),
+                 "r"(a), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_f16(int n) {   // D = F32, A = B = F16, K-major
+    return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(TM >> 4) << 24);
+}
+// two floats -> one 32-bit word of two halves: `even` in bits [0,16), `odd` in bits [16,32)
+__device__ __forceinline__ uint32_t pack_half2(float even, float odd) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd), "f"(even));
+    return r;
+}
+
+template <int KID>
+__device__ __forceinline__ float log2_kernel(float s_raw, float sscale, float un, float vn) {
+    // s_raw sscale = 2 u.v on log2-scaled data
+    if constexpr (KID == KMB_KERNEL_GAUSSIAN) return fmaf(s_raw, sscale, -vn) - un;
+    else {
+        const float d2 = fmaf(s_raw, -sscale, vn) + un;   // bruteforce.py:21: maximum(sqdists, 0) inside sqrt_approx's clamp
+        return -sqrt_approx(d2);
+    }
+}
+
+template <int KID, bool NORM>
+__global__ void __launch_bounds__(THREADS, 1)
+kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                         const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                         const __grid_constant__ CUtensorMap map_sh, const __grid_constant__ CUtensorMap map_sl,
+                         const Params P) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* u_region = smem;                                   // kblocks x [A hi 16 KB | A lo 16 KB]
+    unsigned char* ring = u_region + P.kblocks * 2 * A_TILE_BYTES;    // stages x 32 KB
+    float* aux = reinterpret_cast<float*>(ring + P.stages * SLOT_BYTES);   // 2 x TNS floats (|v|^2)
+    float* cmbuf = aux + 2 * TNS;                                           // 2 x NG x TM: per-group row maxima of a block
+    float* ksbuf = cmbuf + 2 * NG * TM;                                     // NG x TM: per-group sums of weights
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ksbuf + NG * TM);
+    uint64_t* empty_bar = full_bar + P.stages;
+    uint64_t* acc_full = empty_bar + P.stages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* u_full = acc_empty + 2;
+    uint64_t* u_free = u_full + 1;
+    uint64_t* p_ready = u_free + 1;
+    uint64_t* pv_done = p_ready + 1;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(pv_done + 1);
+    int* s_flag = reinterpret_cast<int*>(tmem_base_smem + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x;
+    const int ST = P.stages;
+
+    if (tid == 0) {
+        for (int s = 0; s < ST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
+        mbar_init(u_full, 1);
+        mbar_init(u_free, 1);
+        mbar_init(p_ready, EPI_WARPS);
+        mbar_init(pv_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp == 0) {
+        // ------------------------------------ TMA producer ------------------------------------
+        // all 32 lanes walk the loop (uniform control flow); one elected lane issues (see elect_one)
+        uint32_t it = 0, seg = 0;
+        auto emit_signal = [&](int sb) {   // one slot: hi panels 0, 1 | lo panels 0, 1
+            const int src0 = sb * TNS;
+            const int slot = it % ST;
+            mbar_wait(&empty_bar[slot], ((it / ST) & 1) ^ 1);
+            unsigned char* dst = ring + slot * SLOT_BYTES;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&full_bar[slot], 4 * PANEL_BYTES);
+                tma_load_2d(dst + 0 * PANEL_BYTES, &map_sh, src0, P.e0, &full_bar[slot]);
+                tma_load_2d(dst + 1 * PANEL_BYTES, &map_sh, src0 + 64, P.e0, &full_bar[slot]);
+                tma_load_2d(dst + 2 * PANEL_BYTES, &map_sl, src0, P.e0, &full_bar[slot]);
+                tma_load_2d(dst + 3 * PANEL_BYTES, &map_sl, src0 + 64, P.e0, &full_bar[slot]);
+            }
+            __syncwarp();
+            ++it;
+        };
+        int prev = -1;
+        WaveWork ww;
+        for (int w = 0; w < P.W; ++w) {
+            if (!wave_work(P, w, cta, ww)) continue;
+            // new row tile: (re)load the resident u tile once the last S of the previous tile has read it
+            mbar_wait(u_free, (seg & 1) ^ 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(u_full, P.kblocks * 2 * A_TILE_BYTES);
+                for (int kb = 0; kb < P.kblocks; ++kb) {
+                    tma_load_2d(u_region + (kb * 2 + 0) * A_TILE_BYTES, &map_ah, kb * 64, ww.tile * TM, u_full);
+                    tma_load_2d(u_region + (kb * 2 + 1) * A_TILE_BYTES, &map_al, kb * 64, ww.tile * TM, u_full);
+                }
+            }
+            __syncwarp();
+            ++seg;
+            for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb) {
+                for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+                    const int slot = it % ST;
+                    mbar_wait(&empty_bar[slot], ((it / ST) & 1) ^ 1);
+                    unsigned char* dst = ring + slot * SLOT_BYTES;
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&full_bar[slot], 2 * A_TILE_BYTES);
+                        tma_load_2d(dst, &map_bh, kb * 64, sb * TNS, &full_bar[slot]);
+                        tma_load_2d(dst + A_TILE_BYTES, &map_bl, kb * 64, sb * TNS, &full_bar[slot]);
+                    }
+                    __syncwarp();
+                }
+                if (prev >= 0) emit_signal(prev);   // consumed by PV(n-1), issued after S(n)
+                prev = sb;
+            }
+        }
+        if (prev >= 0) emit_signal(prev);
+    } else if (warp == 1) {
+        // ------------------------------------- MMA issuer -------------------------------------
+        // All 32 lanes walk the loop and wait on the barriers; one elected lane issues (see elect_one).
+        // Order: S(0), S(1), PV(0), S(2), PV(1), ...
+        uint32_t it = 0, n = 0, seg = 0;
+        const uint32_t d_o = tmem_base + COL_O;
+        const uint32_t idesc_s = idesc_f16(TNS), idesc_o = idesc_f16(P.ebp);
+        auto issue_pv = [&](uint32_t m, bool first_of_tile) {
+            mbar_wait(p_ready, m & 1);
+            const int slot = it % ST;
+            mbar_wait(&full_bar[slot], (it / ST) & 1);
+            ++it;
+            tc_fence_after();
+            const unsigned char* sg = ring + slot * SLOT_BYTES;
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < TNS / 16; ++k) {   // 16 sources per instruction
+                    const int panel = k >> 2, koff = (k & 3) * 32;
+                    const uint64_t bh = umma_desc_sw128(sg + panel * PANEL_BYTES, koff);
+                    const uint64_t bl = umma_desc_sw128(sg + (2 + panel) * PANEL_BYTES, koff);
+                    const uint32_t a_hi = tmem_base + COL_PH + k * 8, a_lo = tmem_base + COL_PL + k * 8;
+                    umma_f16_ts(d_o, a_lo, bh, idesc_o, !(first_of_tile && k == 0));
+                    umma_f16_ts(d_o, a_hi, bl, idesc_o, 1);
+                    umma_f16_ts(d_o, a_hi, bh, idesc_o, 1);
+                }
+                umma_commit(&empty_bar[slot]);
+                umma_commit(pv_done);
+            }
+            __syncwarp();
+        };
+        bool prev_first = false, pv_pending = false;
+        WaveWork ww;
+        for (int w = 0; w < P.W; ++w) {
+            if (!wave_work(P, w, cta, ww)) continue;
+            mbar_wait(u_full, seg & 1);
+            ++seg;
+            for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++n) {
+                const bool first = (sb == ww.sb_lo);
+                const int a = n & 1;
+                mbar_wait(&acc_empty[a], ((n >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_s = tmem_base + COL_S + a * TNS;
+                for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+                    const int slot = it % ST;
+                    mbar_wait(&full_bar[slot], (it / ST) & 1);
+                    tc_fence_after();
+                    const unsigned char* bt = ring + slot * SLOT_BYTES;
+                    const unsigned char* at = u_region + kb * 2 * A_TILE_BYTES;
+                    const int ksteps = (kb == P.kblocks - 1) ? P.ksteps_last : 4;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k < ksteps) {
+                                const uint64_t ah = umma_desc_sw128(at, k * 32);
+                                const uint64_t al = umma_desc_sw128(at + A_TILE_BYTES, k * 32);
+                                const uint64_t bh = umma_desc_sw128(bt, k * 32);
+                                const uint64_t bl = umma_desc_sw128(bt + A_TILE_BYTES, k * 32);
+                                umma_f16_ss(d_s, al, bh, idesc_s, (kb | k) != 0);
+                                umma_f16_ss(d_s, ah, bl, idesc_s, 1);
+                                umma_f16_ss(d_s, ah, bh, idesc_s, 1);
+                            }
+                        }
+                        umma_commit(&empty_bar[slot]);
+                    }
+                    __syncwarp();
+                }
+                const bool last_of_tile = (sb + 1 == ww.sb_hi);
+                if (elect_one()) {
+                    umma_commit(&acc_full[a]);
+                    if (last_of_tile) umma_commit(u_free);   // last S of this row tile
+                }
+                __syncwarp();
+                if (pv_pending) issue_pv(n - 1, prev_first);
+                pv_pending = true;
+                prev_first = first;
+            }
+        }
+        if (pv_pending) issue_pv(n - 1, prev_first);
+    } else {
+        // -------------------------------------- epilogue --------------------------------------
+        const int et = tid - 64;
+        const int lane_group = warp & 3;             // TMEM lane quarter this warp may touch
+        const int cg = (warp - 2) >> 2;              // column group
+        const int col0 = cg * CPT;                   // first S column of this thread
+        const int row_in_tile = lane_group * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(lane_group * 32) << 16;
+        const float sscale = __ldg(P.sscale + 1);
+        uint32_t n = 0;   // blocks this CTA has processed (all waves)
+
+        // |v|^2 of the next block's source `et`, fetched one block ahead by the threads that stage it
+        auto load_vn = [&](long long sb, bool valid) -> float {
+            const long long j = sb * TNS + et;
+            return (valid && j < P.M) ? __ldg(P.vn + j) : 1.0e30f;   // padded sources: log2 k = -1e30
+        };
+        WaveWork ww;
+        int w = 0;
+        bool have = false;
+        for (; w < P.W && !have; ++w) have = wave_work(P, w, cta, ww);   // first wave with work (w is one past it)
+        float vn_next = 1.0e30f;
+        if (have && et < TNS) vn_next = load_vn(ww.sb_lo, true);
+
+        while (have) {
+            const int w_cur = w - 1;
+            const int tile = ww.tile;
+            const long long row = static_cast<long long>(tile) * TM + row_in_tile;
+            const bool row_ok = row < P.N;
+            const float un = row_ok ? __ldg(P.un + row) : 0.f;
+            float ksum = 0.f, ref = -INFINITY;   // ksum: this group's columns only
+            // the next wave's work (for the |v|^2 prefetch across the tile boundary)
+            WaveWork wn;
+            bool have_next = false;
+            int w_next = w;
+            for (; w_next < P.W && !have_next; ++w_next) have_next = wave_work(P, w_next, cta, wn);
+
+            for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++n) {
+                float* ax = aux + (n & 1) * TNS;
+                if (et < TNS) {
+                    ax[et] = vn_next;   // loaded one block ago: the global-load latency stays off the critical path
+                    if (sb + 1 < ww.sb_hi) vn_next = load_vn(sb + 1, true);
+                    else vn_next = load_vn(have_next ? wn.sb_lo : 0, have_next);
+                }
+                named_bar_sync(1, EPI_THREADS);
+                const int a = n & 1;
+                mbar_wait(&acc_full[a], (n >> 1) & 1);
+                tc_fence_after();
+                float s[CPT];
+                tmem_ld_cols<CPT>(tmem_base + COL_S + a * TNS + col0 + lane_addr, s);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[a]);   // S is in registers: the MMA warp may refill this stage
+
+                // log2 of the kernel values and their maximum over this thread's columns
+                float cm = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < CPT; c += 4) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(ax + col0 + c);
+                    s[c + 0] = log2_kernel<KID>(s[c + 0], sscale, un, v4.x);
+                    s[c + 1] = log2_kernel<KID>(s[c + 1], sscale, un, v4.y);
+                    s[c + 2] = log2_kernel<KID>(s[c + 2], sscale, un, v4.z);
+                    s[c + 3] = log2_kernel<KID>(s[c + 3], sscale, un, v4.w);
+                    cm = fmaxf(cm, fmaxf(fmaxf(s[c], s[c + 1]), fmaxf(s[c + 2], s[c + 3])));
+                }
+                {   // the groups agree on the row maximum of the block (so that they take the same decisions)
+                    float* cmb = cmbuf + (n & 1) * (NG * TM);
+                    cmb[cg * TM + row_in_tile] = cm;
+                    named_bar_sync(3, EPI_THREADS);
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) cm = fmaxf(cm, cmb[g * TM + row_in_tile]);
+                }
+                if (n > 0) {   // PV(n-1) has read P and finished accumulating into O
+                    mbar_wait(pv_done, (n - 1) & 1);
+                    tc_fence_after();
+                }
+                // lazy rescale: keep the reference exponent unless the row maximum outgrew it by 2^8
+                {
+                    bool need = false;
+                    if (ref == -INFINITY) ref = cm;   // first block(s) of the row (O is overwritten by its first PV or still zero-weighted)
+                    else need = cm > ref + kLazyRescale;
+                    if (__any_sync(0xffffffffu, need)) {   // same lanes, same data in every group: same branch
+                        const float sc = need ? ex2_approx(ref - cm) : 1.f;
+                        if (sb > ww.sb_lo) {                 // O holds this tile's sums
+                            for (int c0 = cg * 16; c0 < P.ebp; c0 += NG * 16) {   // this group's 16-column chunks of O
+                                float o[16];
+                                tmem_ld_cols<16>(tmem_base + COL_O + c0 + lane_addr, o);
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) o[c] *= sc;
+                                tmem_st_cols<16>(tmem_base + COL_O + c0 + lane_addr, o);
+                            }
+                            tmem_st_wait();
+                        }
+                        ksum *= sc;
+                        if (need) ref = cm;
+                    }
+                }
+                // P = 2^(log2 k - ref), FP16 hi / lo, two sources per TMEM column
+                {
+                    uint32_t ph[CPT / 2], pl[CPT / 2];
+                    float kacc = 0.f;   // two-level sum of the weights (see kprod_direct.cuh)
+                    const float nref = (ref == -INFINITY) ? 0.f : ref;   // all -inf so far: every weight is 2^-inf = 0
+#pragma unroll
+                    for (int c = 0; c < CPT; c += 2) {
+                        const float p0 = ex2_approx(s[c] - nref), p1 = ex2_approx(s[c + 1] - nref);
+                        kacc += p0 + p1;
+                        const float h0 = __uint_as_float(__float_as_uint(p0) & 0xffffe000u);   // 11 significant bits: exact in FP16
+                        const float h1 = __uint_as_float(__float_as_uint(p1) & 0xffffe000u);
+                        ph[c / 2] = pack_half2(h0, h1);
+                        pl[c / 2] = pack_half2(p0 - h0, p1 - h1);
+                    }
+                    tmem_st_32x16(tmem_base + COL_PH + cg * (CPT / 2) + lane_addr, reinterpret_cast<const float*>(ph));
+                    tmem_st_32x16(tmem_base + COL_PL + cg * (CPT / 2) + lane_addr, reinterpret_cast<const float*>(pl));
+                    ksum += kacc;
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_ready);
+            }
+
+            // ------------------------------ row tile done ------------------------------
+            mbar_wait(pv_done, (n - 1) & 1);   // the tile's last PV
+            tc_fence_after();
+            // the row's sum of weights over all column groups, in a fixed order
+            ksbuf[cg * TM + row_in_tile] = ksum;
+            named_bar_sync(2, EPI_THREADS);
+            float ktot = 0.f;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) ktot += ksbuf[g * TM + row_in_tile];
+            const bool complete = (ww.Cw == 1);
+            const size_t slot0 = static_cast<size_t>(w_cur) * P.slots_per_wave + static_cast<size_t>(ww.tile_in_wave) * ww.Cw;
+            float* mine = P.partial + (slot0 + ww.c) * (TM * PS);
+            // plain product: undo the reference exponent (2^ref may underflow exactly where FP32 K b would)
+            const float row_scale = NORM ? 1.f / ktot : ((ref == -INFINITY) ? 0.f : ex2_approx(ref));
+            for (int c0 = cg * 16; c0 < P.ebp; c0 += NG * 16) {   // this group's 16-column chunks of O
+                float o[16];
+                tmem_ld_cols<16>(tmem_base + COL_O + c0 + lane_addr, o);
+                if (complete) {
+                    if (row_ok) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            if (c0 + c < P.eb) P.out[row * P.E + P.e0 + c0 + c] = o[c] * __ldg(P.binv + P.e0 + c0 + c) * row_scale;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) mine[(c0 + c) * TM + row_in_tile] = o[c];
+                }
+            }
+            tc_fence_before();
+            if (!complete) {
+                if (cg == 0) {
+                    mine[MAX_EB * TM + row_in_tile] = ktot;
+                    mine[(MAX_EB + 1) * TM + row_in_tile] = ref;
+                }
+                __threadfence();
+                named_bar_sync(2, EPI_THREADS);
+                if (et == 0) {
+                    const int old = atomicAdd(&P.tile_counter[tile], 1);
+                    const int last = (old == ww.Cw - 1);
+                    if (last) P.tile_counter[tile] = 0;
+                    *s_flag = last;
+                }
+                named_bar_sync(2, EPI_THREADS);
+                const bool is_last = *s_flag != 0;
+                named_bar_sync(2, EPI_THREADS);
+                if (is_last && row_ok) {
+                    __threadfence();
+                    float mx = -INFINITY;
+                    for (int c = 0; c < ww.Cw; ++c)
+                        mx = fmaxf(mx, __ldcg(P.partial + (slot0 + c) * (TM * PS) + (MAX_EB + 1) * TM + row_in_tile));
+                    for (int e = cg; e < P.eb; e += NG) {   // the groups share the signal columns of the row
+                        float sum = 0.f, l = 0.f;
+                        for (int c = 0; c < ww.Cw; ++c) {
+                            const float* ps = P.partial + (slot0 + c) * (TM * PS);
+                            const float m = __ldcg(ps + (MAX_EB + 1) * TM + row_in_tile);
+                            const float wgt = (m == -INFINITY) ? 0.f : ex2_approx(m - mx);
+                            sum = fmaf(wgt, __ldcg(ps + e * TM + row_in_tile), sum);
+                            l = fmaf(wgt, __ldcg(ps + MAX_EB * TM + row_in_tile), l);
+                        }
+                        const float rs = NORM ? 1.f / l : ((mx == -INFINITY) ? 0.f : ex2_approx(mx));
+                        P.out[row * P.E + P.e0 + e] = sum * __ldg(P.binv + P.e0 + e) * rs;
+                    }
+                }
+            } else {
+                named_bar_sync(2, EPI_THREADS);   // ksbuf is rewritten at the end of the next tile
+            }
+            ww = wn;
+            have = have_next;
+            w = w_next;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- signal planes -----------------------------------------------------------------------------------
+// per block: column maxima of |b|
+static __global__ void __launch_bounds__(256) signal_absmax_kernel(const float* __restrict__ b, long long M, int E,
+                                                                   float* __restrict__ pmax) {
+    __shared__ float sm[8][32];
+    const int col = blockIdx.y * 32 + (threadIdx.x & 31);
+    const int rl = threadIdx.x >> 5;
+    float hi = 0.f;
+    if (col < E)
+        for (long long r = blockIdx.x * 8 + rl; r < M; r += static_cast<long long>(gridDim.x) * 8) hi = fmaxf(hi, fabsf(b[r * E + col]));
+    sm[rl][threadIdx.x & 31] = hi;
+    __syncthreads();
+    if (rl == 0 && col < E) {
+        float h = 0.f;
+        for (int i = 0; i < 8; ++i) h = fmaxf(h, sm[i][threadIdx.x]);
+        pmax[static_cast<size_t>(blockIdx.x) * E + col] = h;
+    }
+}
+// bscale[e] = 2^q with 2^q max_j |b[j][e]| in [2^13, 2^14); binv[e] = 2^-q
+static __global__ void signal_scale_kernel(const float* __restrict__ pmax, int blocks, int E, int Ep, float* __restrict__ bscale,
+                                           float* __restrict__ binv) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Ep) return;
+    float m = 0.f;
+    if (e < E)
+        for (int b = 0; b < blocks; ++b) m = fmaxf(m, pmax[static_cast<size_t>(b) * E + e]);
+    int q = 0;
+    if (m > 0.f && m < INFINITY) q = 13 - ilogbf(m);
+    q = max(-100, min(100, q));
+    bscale[e] = exp2f(static_cast<float>(q));
+    binv[e] = exp2f(static_cast<float>(-q));
+}
+// hi/lo[e][j] = FP16 hi/lo of 2^q_e b[j][e]  (K-major signal for the P.B contraction), zero padded
+static __global__ void transpose_split_signal_f16_kernel(const float* __restrict__ b, long long M, long long Mp, int E,
+                                                         const float* __restrict__ bscale, __half* __restrict__ hi,
+                                                         __half* __restrict__ lo) {
+    const long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const int e = blockIdx.y;
+    if (j >= Mp) return;
+    const float v = (j < M && e < E) ? b[j * E + e] * bscale[e] : 0.f;
+    const __half h = __float2half_rn(v);
+    hi[e * Mp + j] = h;
+    lo[e * Mp + j] = __float2half_rn(v - __half2float(h));
+}
+
+}  // namespace pv16
+
+namespace {
+
+size_t align_up_pv16(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Pv16Plan {
+    int Dp, Ep, kblocks, ksteps_last, stages, grid, smem;
+    long long n_tiles, nsb, Mp;
+    tc::WavePlan waves;
+    size_t off_center, off_stats, off_sscale, off_uh, off_ul, off_vh, off_vl, off_un, off_vn, off_sh, off_sl, off_bmax, off_bscale,
+        off_binv, off_partial, off_counter, total;
+};
+
+int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
+    pl->Dp = (D + 15) / 16 * 16;
+    pl->kblocks = (pl->Dp + 63) / 64;
+    pl->ksteps_last = (pl->Dp - (pl->kblocks - 1) * 64) / 16;
+    pl->Ep = (E + pv16::MAX_EB - 1) / pv16::MAX_EB * pv16::MAX_EB;
+    pl->Mp = (M + pv16::TNS - 1) / pv16::TNS * pv16::TNS;
+    pl->n_tiles = (N + tc::TM - 1) / tc::TM;
+    pl->nsb = (M + pv16::TNS - 1) / pv16::TNS;
+    int dev = 0, sms = 0, smem_max = 0;
+    KMB_CUDA_CHECK(cudaGetDevice(&dev));
+    KMB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    KMB_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    pl->grid = sms;
+    const int fixed = 1024 + pl->kblocks * 2 * pv16::A_TILE_BYTES + 2 * pv16::TNS * 4 + 3 * pv16::NG * tc::TM * 4 + 512;
+    pl->stages = std::min(6, (smem_max - fixed) / pv16::SLOT_BYTES);
+    if (pl->stages < 3) return set_error(KMB_ERR_UNSUPPORTED, "not enough shared memory for D=%d", D);
+    pl->smem = fixed + pl->stages * pv16::SLOT_BYTES;
+    tc::plan_waves(pl->n_tiles, pl->nsb, pl->grid, static_cast<size_t>(tc::TM) * pl->Dp * 4, &pl->waves);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += align_up_pv16(bytes, 256); return at; };
+    pl->off_center = take(sizeof(float) * pl->Dp);
+    pl->off_stats = take(sizeof(float) * tc::CENTER_BLOCKS * D * 6);
+    pl->off_sscale = take(sizeof(float) * 2);
+    pl->off_uh = take(2 * static_cast<size_t>(N) * pl->Dp);
+    pl->off_ul = take(2 * static_cast<size_t>(N) * pl->Dp);
+    pl->off_vh = take(2 * static_cast<size_t>(M) * pl->Dp);
+    pl->off_vl = take(2 * static_cast<size_t>(M) * pl->Dp);
+    pl->off_un = take(sizeof(float) * N);
+    pl->off_vn = take(sizeof(float) * M);
+    pl->off_sh = take(2 * static_cast<size_t>(pl->Ep) * pl->Mp);
+    pl->off_sl = take(2 * static_cast<size_t>(pl->Ep) * pl->Mp);
+    pl->off_bmax = take(sizeof(float) * tc::CENTER_BLOCKS * E);
+    pl->off_bscale = take(sizeof(float) * pl->Ep);
+    pl->off_binv = take(sizeof(float) * pl->Ep);
+    pl->off_partial = take(sizeof(float) * pl->waves.partial_slots * tc::TM * pv16::PS);
+    pl->off_counter = take(sizeof(int) * pl->n_tiles);
+    pl->total = o;
+    return KMB_OK;
+}
+
+template <int KID, bool NORM>
+int launch_pv16(const CUtensorMap* m, const pv16::Params& P, int grid, int smem, cudaStream_t stream) {
+    auto fn = pv16::kprod_tensor_pv16_kernel<KID, NORM>;
+    static int attr_smem = 0;
+    if (attr_smem < smem) {
+        KMB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    fn<<<grid, pv16::THREADS, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
+    KMB_CUDA_CHECK(cudaGetLastError());
+    return KMB_OK;
+}
+
+}  // namespace
+
+bool tensor_pv16_applicable(int D, int E, int kid) {
+    return E > 4 && D <= 128 && (kid == KMB_KERNEL_GAUSSIAN || kid == KMB_KERNEL_ABSOLUTE_EXPONENTIAL);
+}
+
+int tensor_pv16_workspace_bytes(int64_t N, int64_t M, int D, int E, size_t* bytes) {
+    Pv16Plan pl{};
+    if (int rc = plan_pv16(N, M, D, E, &pl)) return rc;
+    *bytes = pl.total;
+    return KMB_OK;
+}
+
+int tensor_pv16_product(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D, int E, int kid,
+                        int flags, void* workspace, size_t workspace_bytes, cudaStream_t stream, cudaEvent_t ev0,
+                        cudaEvent_t ev1) {
+    Pv16Plan pl{};
+    if (int rc = plan_pv16(N, M, D, E, &pl)) return rc;
+    if (!workspace || workspace_bytes < pl.total)
+        return set_error(KMB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);
+    if (N >= (1ll << 31) - tc::TM || M >= (1ll << 31) - pv16::TNS)
+        return set_error(KMB_ERR_UNSUPPORTED, "tensor path indexes rows with 32-bit TMA coordinates");
+    if (!b) return set_error(KMB_ERR_INVALID, "signal is NULL");
+    char* ws = static_cast<char*>(workspace);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    void *uh = ws + pl.off_uh, *ul = ws + pl.off_ul, *vh = ws + pl.off_vh, *vl = ws + pl.off_vl, *sh = ws + pl.off_sh, *sl = ws + pl.off_sl;
+    int* counters = reinterpret_cast<int*>(ws + pl.off_counter);
+    const bool norm = flags & KMB_FLAG_NORMALIZE_ROWS;
+
+    KMB_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(int) * pl.n_tiles, stream));
+    if (int rc = tc::tensor_prepass_f16(x, y, N, M, D, pl.Dp, kid, F(pl.off_center), F(pl.off_stats), F(pl.off_sscale), uh, ul, vh, vl,
+                                        F(pl.off_un), F(pl.off_vn), stream))
+        return rc;
+    {
+        const int blocks = static_cast<int>(std::min<long long>(tc::CENTER_BLOCKS, (M + 7) / 8));
+        pv16::signal_absmax_kernel<<<dim3(blocks, (E + 31) / 32), 256, 0, stream>>>(b, M, E, F(pl.off_bmax));
+        KMB_CUDA_CHECK(cudaGetLastError());
+        pv16::signal_scale_kernel<<<(pl.Ep + 127) / 128, 128, 0, stream>>>(F(pl.off_bmax), blocks, E, pl.Ep, F(pl.off_bscale), F(pl.off_binv));
+        KMB_CUDA_CHECK(cudaGetLastError());
+        dim3 g(static_cast<unsigned>((pl.Mp + 255) / 256), pl.Ep);
+        pv16::transpose_split_signal_f16_kernel<<<g, 256, 0, stream>>>(b, M, pl.Mp, E, F(pl.off_bscale), static_cast<__half*>(sh),
+                                                                        static_cast<__half*>(sl));
+        KMB_CUDA_CHECK(cudaGetLastError());
+        count_launch(3);
+    }
+    CUtensorMap maps[6];
+    if (int rc = tc::make_tensor_map_f16(&maps[0], uh, N, pl.Dp, tc::TM)) return rc;
+    if (int rc = tc::make_tensor_map_f16(&maps[1], ul, N, pl.Dp, tc::TM)) return rc;
+    if (int rc = tc::make_tensor_map_f16(&maps[2], vh, M, pl.Dp, pv16::TNS)) return rc;
+    if (int rc = tc::make_tensor_map_f16(&maps[3], vl, M, pl.Dp, pv16::TNS)) return rc;
+    if (int rc = tc::make_tensor_map_f16(&maps[4], sh, pl.Ep, static_cast<int>(pl.Mp), pv16::MAX_EB)) return rc;
+    if (int rc = tc::make_tensor_map_f16(&maps[5], sl, pl.Ep, static_cast<int>(pl.Mp), pv16::MAX_EB)) return rc;
+
+    const int n_passes = pl.Ep / pv16::MAX_EB;
+    for (int pass = 0; pass < n_passes; ++pass) {
+        pv16::Params P;
+        P.un = F(pl.off_un);
+        P.vn = F(pl.off_vn);
+        P.sscale = F(pl.off_sscale);
+        P.binv = F(pl.off_binv);
+        P.out = out;
+        P.partial = F(pl.off_partial);
+        P.tile_counter = counters;
+        P.N = N;
+        P.M = M;
+        P.E = E;
+        P.e0 = pass * pv16::MAX_EB;
+        P.eb = std::min(pv16::MAX_EB, E - P.e0);
+        P.ebp = (P.eb + 31) / 32 * 32;
+        P.n_tiles = static_cast<int>(pl.n_tiles);
+        P.nsb = static_cast<int>(pl.nsb);
+        P.kblocks = pl.kblocks;
+        P.ksteps_last = pl.ksteps_last;
+        P.stages = pl.stages;
+        P.R = pl.waves.R;
+        P.C = pl.waves.C;
+        P.W = pl.waves.W;
+        P.R_last = pl.waves.R_last;
+        P.C_last = pl.waves.C_last;
+        P.slots_per_wave = pl.waves.slots_per_wave;
+        if (ev0 && pass == n_passes - 1) KMB_CUDA_CHECK(cudaEventRecord(ev0, stream));
+        int rc;
+        switch (kid * 2 + (norm ? 1 : 0)) {
+            case 0: rc = launch_pv16<KMB_KERNEL_GAUSSIAN, false>(maps, P, pl.grid, pl.smem, stream); break;
+            case 1: rc = launch_pv16<KMB_KERNEL_GAUSSIAN, true>(maps, P, pl.grid, pl.smem, stream); break;
+            case 2: rc = launch_pv16<KMB_KERNEL_ABSOLUTE_EXPONENTIAL, false>(maps, P, pl.grid, pl.smem, stream); break;
+            default: rc = launch_pv16<KMB_KERNEL_ABSOLUTE_EXPONENTIAL, true>(maps, P, pl.grid, pl.smem, stream); break;
+        }
+        if (rc) return rc;
+        if (ev1 && pass == n_passes - 1) KMB_CUDA_CHECK(cudaEventRecord(ev1, stream));
+        count_launch();
+    }
+    return KMB_OK;
+}
+
+}  // namespace kmb

@@ -195,4 +195,12 @@ int tensor_pv_product(const float* x, const float* y, const float* b, float* out
                       int kid, int flags, int64_t row_offset, void* workspace, size_t workspace_bytes,
                       cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1);
 
+
+// the same with FP16 hi/lo operand planes (kprod_tensor_pv16.cu): Gaussian and exponential kernels
+bool tensor_pv16_applicable(int D, int E, int kid);
+int tensor_pv16_workspace_bytes(int64_t N, int64_t M, int D, int E, size_t* bytes);
+int tensor_pv16_product(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D, int E, int kid,
+                        int flags, void* workspace, size_t workspace_bytes, cudaStream_t stream, cudaEvent_t ev0,
+                        cudaEvent_t ev1);
+
 }  // namespace kmb

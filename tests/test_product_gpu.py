@@ -116,7 +116,7 @@ def test_attention_survives_fp32_underflow(kernel):
     rng = np.random.RandomState(5)
     y, b = rng.rand(900, 3), rng.randn(900, 2)
     x = rng.rand(64, 3) + (12.0 if kernel == "gaussian" else 150.0)
-    out, _ = run_plugin(kernel, y, x, b, normalize_rows=True)
+    out, _ = run_plugin(kernel, y, x, b, normalize_rows=True, path=path)
     want = orc.kernel_product(kernel, y, x, b, normalize_rows=True)
     assert np.isfinite(out).all()
     assert orc.rel_l2(out, want) <= 2e-4  # the exponent itself is ~1e3 ulps of FP32 away from zero here
@@ -338,23 +338,27 @@ def test_config_c4_reduced():
 # ------------------------------------------- tensor path with the second contraction on tcgen05 (E > 4)
 
 
+@pytest.mark.parametrize("path", TENSOR_PATHS)
 @pytest.mark.parametrize("kernel", ["gaussian", "absolute-exponential", "inverse-distance"])
 @pytest.mark.parametrize("norm", [False, True])
-@pytest.mark.parametrize("N,M,D,E", [(100, 20000, 64, 64), (300, 1000, 32, 5), (129, 641, 100, 33), (1000, 130, 128, 70)])
-def test_tensor_pv_shapes(kernel, norm, N, M, D, E):
-    """P.B on the tensor cores: one row tile split over many CTAs (stream-K combine), ragged sizes,
-    E not a multiple of 32, two passes over the signal (E > 64)."""
+@pytest.mark.parametrize("N,M,D,E", [(100, 20000, 64, 64), (300, 1000, 32, 5), (129, 641, 100, 33), (1000, 130, 128, 70),
+                                     (128 * 150 + 3, 700, 48, 8)])
+def test_tensor_pv_shapes(kernel, norm, N, M, D, E, path):
+    """P.B on the tensor cores: one row tile split over many CTAs (combined by the last to arrive), ragged
+    sizes, E not a multiple of 32, two passes over the signal (E > 64), more row tiles than CTAs.
+    tensor_f16: kprod_tensor_pv16 (inverse-distance: the TF32 kernel); tensor_tf32: kprod_tensor_pv."""
     rng = np.random.RandomState(N + M + D + E)
     r = (3.0 / D) ** 0.5
-    y, x, b = r * rng.rand(M, D), r * rng.rand(N, D), rng.randn(M, E)
-    out, _ = run_plugin(kernel, y, x, b, normalize_rows=norm)
+    y, x, b = r * rng.rand(M, D), r * rng.rand(N, D), rng.randn(M, E) * (1.0 + 100.0 * (np.arange(E) % 3 == 0))
+    out, _ = run_plugin(kernel, y, x, b, normalize_rows=norm, path=path)
     want = c_oracle.kernel_product(kernel, y, x, b, normalize_rows=norm)
     assert out.shape == want.shape
     assert orc.rel_l2(out, want) <= TOL_TENSOR
 
 
+@pytest.mark.parametrize("path", TENSOR_PATHS)
 @pytest.mark.parametrize("kernel", ["gaussian", "absolute-exponential"])
-def test_tensor_pv_lazy_rescale(kernel):
+def test_tensor_pv_lazy_rescale(kernel, path):
     """Sources ordered far -> near: the running reference exponent must be rescaled (growth > 2^64)
     and rows that only ever see far sources must still normalise (FP32 exp would underflow)."""
     rng = np.random.RandomState(4)
@@ -364,7 +368,7 @@ def test_tensor_pv_lazy_rescale(kernel):
     y = np.concatenate((near + far / np.sqrt(D) * 3, near + far / np.sqrt(D), near), axis=0)  # far, closer, near
     x = np.concatenate((0.2 * rng.rand(200, D), 0.2 * rng.rand(56, D) - far / np.sqrt(D)), axis=0)
     b = rng.randn(y.shape[0], E)
-    out, _ = run_plugin(kernel, y, x, b, normalize_rows=True)
+    out, _ = run_plugin(kernel, y, x, b, normalize_rows=True, path=path)
     want = orc.kernel_product(kernel, y, x, b, normalize_rows=True)
     assert np.isfinite(out).all()
     assert orc.rel_l2(out, want) <= 5e-4  # |u||v| ~ 1e4 here: the 3xTF32 cancellation error of d^2 is ~1e-2
