@@ -7,15 +7,20 @@
 //   S = 2 u.v^T   128 rows x 128 sources per block; tcgen05.mma kind::f16, three-term split
 //                 (lo.hi + hi.lo + hi.hi), A = u tile (hi, lo) resident in shared memory for the whole row
 //                 tile, B = v blocks streamed by TMA, FP32 accumulator in TMEM (two stages)
-//   P = k(S)      16 epilogue warps (4 column groups x 4 TMEM lane quarters): tcgen05.ld S, log2 of the kernel,
-//                 running reference exponent per row (lazy rescale of O when the row maximum outgrows it by
-//                 2^8, so P <= 2^8 fits FP16 and rows whose kernel values all underflow FP32 still normalise),
-//                 P = 2^(log2 k - ref) split into FP16 hi + lo, packed two per 32-bit TMEM column (tcgen05.st)
-//   O += P.B      tcgen05.mma with A = P from TMEM (hi, lo), B = transposed signal block (FP16 hi, lo, scaled per
-//                 signal column by a power of two) from shared memory; O (128 x E) stays in TMEM for the whole
-//                 row tile and is read once
+//   P = k(S)      16 epilogue warps = 4 column groups x 4 TMEM lane quarters.  Group g owns columns [32g, 32g+32)
+//                 of every S block and runs its OWN online-softmax stream over those sources: tcgen05.ld S, log2
+//                 of the kernel, a running reference exponent per (row, group) (lazy rescale of the group's O
+//                 when the maximum outgrows it by 2^8, so P <= 2^8 fits FP16 and rows whose kernel values all
+//                 underflow FP32 still normalise), P = 2^(log2 k - ref) split into FP16 hi + lo, packed two per
+//                 32-bit column and stored IN PLACE over the thread's own S columns (tcgen05.st).  No
+//                 block-level synchronisation between epilogue warps inside a row tile.
+//   O_g += P_g.B  tcgen05.mma with A = P from TMEM (hi, lo), B = transposed signal block (FP16 hi, lo, scaled per
+//                 signal column by a power of two) from shared memory; one accumulator O_g (128 x E) per column
+//                 group, kept in TMEM for the whole row tile; the four are merged (weights 2^(ref_g - ref)) when
+//                 the row tile ends -- every thread can read all four because TMEM lanes are rows.
 //
-// TMEM columns: S stage 0 [0,128) | S stage 1 [128,256) | P hi [256,320) | P lo [320,384) | O [384,384+E).
+// TMEM columns: S/P stage 0 [0,128) | S/P stage 1 [128,256) | O_0 .. O_3 at 256 + 64 g.
+// S(n+2) overwrites stage n & 1 after PV(n) has been issued (tensor-pipe order), so P is double buffered for free.
 // Work split: the wave schedule of kprod_tensor.cu -- every CTA of a wave walks the SAME source blocks at the same
 // time (all of them when there are at least as many row tiles as CTAs), so v and b blocks come from L2.
 #include <algorithm>
@@ -39,7 +44,7 @@ constexpr int EPI_WARPS = 4 * NG;
 constexpr int EPI_THREADS = 32 * EPI_WARPS;
 constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int TMEM_COLS = 512;
-constexpr int COL_S = 0, COL_PH = 256, COL_PL = 320, COL_O = 384;
+constexpr int COL_S = 0, COL_O = 256;
 constexpr int MAX_EB = 64;             // signal columns per pass
 constexpr float kLazyRescale = 8.f;    // rescale O only when the row maximum outgrew the reference by 2^8
 constexpr int PS = MAX_EB + 2;         // partial record: O row, sum of weights, reference exponent
@@ -92,13 +97,17 @@ __device__ __forceinline__ uint32_t pack_half2(float even, float odd) {
     return r;
 }
 
+// t = -log2 k for two sources at once (packed FP32: FFMA2 / FADD2 / FMUL2), from the raw accumulators:
+// s_raw sscale = 2 u.v on log2-scaled data, w = |u|^2 + |v|^2
 template <int KID>
-__device__ __forceinline__ float log2_kernel(float s_raw, float sscale, float un, float vn) {
-    // s_raw sscale = 2 u.v on log2-scaled data
-    if constexpr (KID == KMB_KERNEL_GAUSSIAN) return fmaf(s_raw, sscale, -vn) - un;
+__device__ __forceinline__ float2 neg_log2_kernel2(float2 s_raw, float2 nsscale, float2 w) {
+    const float2 d2 = fma2(s_raw, nsscale, w);          // log2(e) |x - y|^2 (Gaussian) or (log2(e) |x - y|)^2
+    if constexpr (KID == KMB_KERNEL_GAUSSIAN) return d2;
     else {
-        const float d2 = fmaf(s_raw, -sscale, vn) + un;   // bruteforce.py:21: maximum(sqdists, 0) inside sqrt_approx's clamp
-        return -sqrt_approx(d2);
+        // bruteforce.py:21: sqrt(maximum(sqdists, 0)); the clamp away from zero keeps rsqrt finite (see sqrt_approx).
+        // d2 is finite: |v|^2 of padded sources is 3.39e38 and |2 u.v| is far below the 1.3e36 left to FLT_MAX.
+        const float2 c = make_float2(fmaxf(d2.x, 1.0e-30f), fmaxf(d2.y, 1.0e-30f));
+        return mul2(c, make_float2(rsqrt_approx(c.x), rsqrt_approx(c.y)));
     }
 }
 
@@ -112,18 +121,16 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char* u_region = smem;                                   // kblocks x [A hi 16 KB | A lo 16 KB]
     unsigned char* ring = u_region + P.kblocks * 2 * A_TILE_BYTES;    // stages x 32 KB
-    float* aux = reinterpret_cast<float*>(ring + P.stages * SLOT_BYTES);   // 2 x TNS floats (|v|^2)
-    float* cmbuf = aux + 2 * TNS;                                           // 2 x NG x TM: per-group row maxima of a block
-    float* ksbuf = cmbuf + 2 * NG * TM;                                     // NG x TM: per-group sums of weights
+    float* refbuf = reinterpret_cast<float*>(ring + P.stages * SLOT_BYTES);   // NG x TM: per-group reference exponents
+    float* ksbuf = refbuf + NG * TM;                                           // NG x TM: per-group sums of weights
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ksbuf + NG * TM);
     uint64_t* empty_bar = full_bar + P.stages;
-    uint64_t* acc_full = empty_bar + P.stages;
-    uint64_t* acc_empty = acc_full + 2;
-    uint64_t* u_full = acc_empty + 2;
+    uint64_t* acc_full = empty_bar + P.stages;     // [2] S(n) complete in stage n & 1
+    uint64_t* p_ready = acc_full + 2;              // [2] P(n) stored in stage n & 1
+    uint64_t* pv_done = p_ready + 2;               // [2] PV(n) complete
+    uint64_t* u_full = pv_done + 2;
     uint64_t* u_free = u_full + 1;
-    uint64_t* p_ready = u_free + 1;
-    uint64_t* pv_done = p_ready + 1;
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(pv_done + 1);
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(u_free + 1);
     int* s_flag = reinterpret_cast<int*>(tmem_base_smem + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -132,11 +139,9 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
 
     if (tid == 0) {
         for (int s = 0; s < ST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&p_ready[a], EPI_WARPS); mbar_init(&pv_done[a], 1); }
         mbar_init(u_full, 1);
         mbar_init(u_free, 1);
-        mbar_init(p_ready, EPI_WARPS);
-        mbar_init(pv_done, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
@@ -204,25 +209,28 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
         const uint32_t d_o = tmem_base + COL_O;
         const uint32_t idesc_s = idesc_f16(TNS), idesc_o = idesc_f16(P.ebp);
         auto issue_pv = [&](uint32_t m, bool first_of_tile) {
-            mbar_wait(p_ready, m & 1);
+            const int a = m & 1;
+            mbar_wait(&p_ready[a], (m >> 1) & 1);
             const int slot = it % ST;
             mbar_wait(&full_bar[slot], (it / ST) & 1);
             ++it;
             tc_fence_after();
             const unsigned char* sg = ring + slot * SLOT_BYTES;
+            const uint32_t p_base = tmem_base + COL_S + a * TNS;
             if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < TNS / 16; ++k) {   // 16 sources per instruction
-                    const int panel = k >> 2, koff = (k & 3) * 32;
+                for (int k = 0; k < TNS / 16; ++k) {   // 16 sources per instruction; column group g = k / 2
+                    const int g = k >> 1, panel = k >> 2, koff = (k & 3) * 32;
                     const uint64_t bh = umma_desc_sw128(sg + panel * PANEL_BYTES, koff);
                     const uint64_t bl = umma_desc_sw128(sg + (2 + panel) * PANEL_BYTES, koff);
-                    const uint32_t a_hi = tmem_base + COL_PH + k * 8, a_lo = tmem_base + COL_PL + k * 8;
-                    umma_f16_ts(d_o, a_lo, bh, idesc_o, !(first_of_tile && k == 0));
-                    umma_f16_ts(d_o, a_hi, bl, idesc_o, 1);
-                    umma_f16_ts(d_o, a_hi, bh, idesc_o, 1);
+                    const uint32_t a_hi = p_base + g * CPT + (k & 1) * 8, a_lo = a_hi + CPT / 2;
+                    const uint32_t d_g = d_o + g * MAX_EB;
+                    umma_f16_ts(d_g, a_lo, bh, idesc_o, !(first_of_tile && (k & 1) == 0));
+                    umma_f16_ts(d_g, a_hi, bl, idesc_o, 1);
+                    umma_f16_ts(d_g, a_hi, bh, idesc_o, 1);
                 }
                 umma_commit(&empty_bar[slot]);
-                umma_commit(pv_done);
+                umma_commit(&pv_done[a]);
             }
             __syncwarp();
         };
@@ -234,9 +242,7 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
             ++seg;
             for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++n) {
                 const bool first = (sb == ww.sb_lo);
-                const int a = n & 1;
-                mbar_wait(&acc_empty[a], ((n >> 1) & 1) ^ 1);
-                tc_fence_after();
+                const int a = n & 1;   // stage a held P(n-2): PV(n-2) was issued in the previous iteration
                 const uint32_t d_s = tmem_base + COL_S + a * TNS;
                 for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
                     const int slot = it % ST;
@@ -282,87 +288,67 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
         const int col0 = cg * CPT;                   // first S column of this thread
         const int row_in_tile = lane_group * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(lane_group * 32) << 16;
+        const uint32_t o_mine = tmem_base + COL_O + cg * MAX_EB + lane_addr;   // this group's accumulator
         const float sscale = __ldg(P.sscale + 1);
         uint32_t n = 0;   // blocks this CTA has processed (all waves)
-
-        // |v|^2 of the next block's source `et`, fetched one block ahead by the threads that stage it
-        auto load_vn = [&](long long sb, bool valid) -> float {
-            const long long j = sb * TNS + et;
-            return (valid && j < P.M) ? __ldg(P.vn + j) : 1.0e30f;   // padded sources: log2 k = -1e30
+        auto wait_pv = [&](uint32_t m) {   // PV(m) has read P(m) and finished accumulating into the O_g
+            mbar_wait(&pv_done[m & 1], (m >> 1) & 1);
+            tc_fence_after();
         };
-        WaveWork ww;
-        int w = 0;
-        bool have = false;
-        for (; w < P.W && !have; ++w) have = wave_work(P, w, cta, ww);   // first wave with work (w is one past it)
-        float vn_next = 1.0e30f;
-        if (have && et < TNS) vn_next = load_vn(ww.sb_lo, true);
 
-        while (have) {
-            const int w_cur = w - 1;
+        WaveWork ww;
+        for (int w = 0; w < P.W; ++w) {
+            if (!wave_work(P, w, cta, ww)) continue;
             const int tile = ww.tile;
             const long long row = static_cast<long long>(tile) * TM + row_in_tile;
             const bool row_ok = row < P.N;
             const float un = row_ok ? __ldg(P.un + row) : 0.f;
-            float ksum = 0.f, ref = -INFINITY;   // ksum: this group's columns only
-            // the next wave's work (for the |v|^2 prefetch across the tile boundary)
-            WaveWork wn;
-            bool have_next = false;
-            int w_next = w;
-            for (; w_next < P.W && !have_next; ++w_next) have_next = wave_work(P, w_next, cta, wn);
+            float ksum = 0.f, ref = -INFINITY;   // this group's stream
 
             for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++n) {
-                float* ax = aux + (n & 1) * TNS;
-                if (et < TNS) {
-                    ax[et] = vn_next;   // loaded one block ago: the global-load latency stays off the critical path
-                    if (sb + 1 < ww.sb_hi) vn_next = load_vn(sb + 1, true);
-                    else vn_next = load_vn(have_next ? wn.sb_lo : 0, have_next);
-                }
-                named_bar_sync(1, EPI_THREADS);
+                const long long j0 = static_cast<long long>(sb) * TNS + col0;
                 const int a = n & 1;
+                const uint32_t st_addr = tmem_base + COL_S + a * TNS + col0 + lane_addr;
+                const float4* vnq = reinterpret_cast<const float4*>(P.vn + j0);   // |v|^2, padded to whole blocks with 3.4e38
                 mbar_wait(&acc_full[a], (n >> 1) & 1);
                 tc_fence_after();
-                float s[CPT];
-                tmem_ld_cols<CPT>(tmem_base + COL_S + a * TNS + col0 + lane_addr, s);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[a]);   // S is in registers: the MMA warp may refill this stage
+                float2 t2[CPT / 2];   // S as pairs of sources, then t = -log2 k
+                tmem_ld_cols<CPT>(st_addr, reinterpret_cast<float(&)[CPT]>(t2));
 
-                // log2 of the kernel values and their maximum over this thread's columns
-                float cm = -INFINITY;
+                // t = -log2 of the kernel values (packed pairs) and their minimum over this thread's columns
+                float tmin = INFINITY;
+                if (j0 < P.M) {
+                    const float2 nss2 = make_float2(-sscale, -sscale), un2 = make_float2(un, un);
 #pragma unroll
-                for (int c = 0; c < CPT; c += 4) {
-                    const float4 v4 = *reinterpret_cast<const float4*>(ax + col0 + c);
-                    s[c + 0] = log2_kernel<KID>(s[c + 0], sscale, un, v4.x);
-                    s[c + 1] = log2_kernel<KID>(s[c + 1], sscale, un, v4.y);
-                    s[c + 2] = log2_kernel<KID>(s[c + 2], sscale, un, v4.z);
-                    s[c + 3] = log2_kernel<KID>(s[c + 3], sscale, un, v4.w);
-                    cm = fmaxf(cm, fmaxf(fmaxf(s[c], s[c + 1]), fmaxf(s[c + 2], s[c + 3])));
-                }
-                {   // the groups agree on the row maximum of the block (so that they take the same decisions)
-                    float* cmb = cmbuf + (n & 1) * (NG * TM);
-                    cmb[cg * TM + row_in_tile] = cm;
-                    named_bar_sync(3, EPI_THREADS);
+                    for (int c = 0; c < CPT / 4; ++c) {
+                        const float4 vq = __ldg(vnq + c);   // L1-resident broadcast load (all lanes, same address)
+                        const float2 ta = neg_log2_kernel2<KID>(t2[2 * c], nss2, add2(make_float2(vq.x, vq.y), un2));
+                        const float2 tb = neg_log2_kernel2<KID>(t2[2 * c + 1], nss2, add2(make_float2(vq.z, vq.w), un2));
+                        t2[2 * c] = ta;
+                        t2[2 * c + 1] = tb;
+                        tmin = fminf(fminf(tmin, ta.x), ta.y);
+                        tmin = fminf(fminf(tmin, tb.x), tb.y);
+                    }
+                } else {   // every source of this group is padding (warp-uniform): all weights are zero
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) cm = fmaxf(cm, cmb[g * TM + row_in_tile]);
+                    for (int c = 0; c < CPT / 2; ++c) t2[c] = make_float2(INFINITY, INFINITY);
                 }
-                if (n > 0) {   // PV(n-1) has read P and finished accumulating into O
-                    mbar_wait(pv_done, (n - 1) & 1);
-                    tc_fence_after();
-                }
-                // lazy rescale: keep the reference exponent unless the row maximum outgrew it by 2^8
+                const float cm = -tmin;   // largest log2 k of the block
+                // lazy rescale: keep the reference exponent unless the maximum outgrew it by 2^8
                 {
                     bool need = false;
-                    if (ref == -INFINITY) ref = cm;   // first block(s) of the row (O is overwritten by its first PV or still zero-weighted)
+                    if (ref == -INFINITY) ref = cm;   // nothing but zero weights so far
                     else need = cm > ref + kLazyRescale;
-                    if (__any_sync(0xffffffffu, need)) {   // same lanes, same data in every group: same branch
+                    if (__any_sync(0xffffffffu, need)) {
                         const float sc = need ? ex2_approx(ref - cm) : 1.f;
-                        if (sb > ww.sb_lo) {                 // O holds this tile's sums
-                            for (int c0 = cg * 16; c0 < P.ebp; c0 += NG * 16) {   // this group's 16-column chunks of O
+                        if (sb > ww.sb_lo) {   // O_g holds this tile's sums
+                            wait_pv(n - 1);
+                            for (int c0 = 0; c0 < P.ebp; c0 += 16) {
                                 float o[16];
-                                tmem_ld_cols<16>(tmem_base + COL_O + c0 + lane_addr, o);
+                                tmem_ld_cols<16>(o_mine + c0, o);
 #pragma unroll
                                 for (int c = 0; c < 16; ++c) o[c] *= sc;
-                                tmem_st_cols<16>(tmem_base + COL_O + c0 + lane_addr, o);
+                                tmem_st_cols<16>(o_mine + c0, o);
                             }
                             tmem_st_wait();
                         }
@@ -370,47 +356,64 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                         if (need) ref = cm;
                     }
                 }
-                // P = 2^(log2 k - ref), FP16 hi / lo, two sources per TMEM column
+                // P = 2^(log2 k - ref) = 2^(-ref - t), FP16 hi / lo, two sources per TMEM column, over this thread's own S columns
                 {
                     uint32_t ph[CPT / 2], pl[CPT / 2];
-                    float kacc = 0.f;   // two-level sum of the weights (see kprod_direct.cuh)
-                    const float nref = (ref == -INFINITY) ? 0.f : ref;   // all -inf so far: every weight is 2^-inf = 0
+                    float2 kacc = make_float2(0.f, 0.f);   // two-level sum of the weights (see kprod_direct.cuh)
+                    const float nref = (ref == -INFINITY) ? 0.f : -ref;   // all -inf so far: every weight is 2^-inf = 0
+                    const float2 nref2 = make_float2(nref, nref);
 #pragma unroll
-                    for (int c = 0; c < CPT; c += 2) {
-                        const float p0 = ex2_approx(s[c] - nref), p1 = ex2_approx(s[c + 1] - nref);
-                        kacc += p0 + p1;
-                        const float h0 = __uint_as_float(__float_as_uint(p0) & 0xffffe000u);   // 11 significant bits: exact in FP16
-                        const float h1 = __uint_as_float(__float_as_uint(p1) & 0xffffe000u);
-                        ph[c / 2] = pack_half2(h0, h1);
-                        pl[c / 2] = pack_half2(p0 - h0, p1 - h1);
+                    for (int c = 0; c < CPT / 2; ++c) {
+                        const float2 e = sub2(nref2, t2[c]);
+                        const float2 pw = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+                        kacc = add2(kacc, pw);
+                        // 11 significant bits: exact in FP16
+                        const float2 h = make_float2(__uint_as_float(__float_as_uint(pw.x) & 0xffffe000u),
+                                                     __uint_as_float(__float_as_uint(pw.y) & 0xffffe000u));
+                        const float2 l = sub2(pw, h);
+                        ph[c] = pack_half2(h.x, h.y);
+                        pl[c] = pack_half2(l.x, l.y);
                     }
-                    tmem_st_32x16(tmem_base + COL_PH + cg * (CPT / 2) + lane_addr, reinterpret_cast<const float*>(ph));
-                    tmem_st_32x16(tmem_base + COL_PL + cg * (CPT / 2) + lane_addr, reinterpret_cast<const float*>(pl));
-                    ksum += kacc;
+                    tmem_st_32x16(st_addr, reinterpret_cast<const float*>(ph));
+                    tmem_st_32x16(st_addr + CPT / 2, reinterpret_cast<const float*>(pl));
+                    ksum += kacc.x + kacc.y;
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(p_ready);
+                if (lane == 0) mbar_arrive(&p_ready[a]);
             }
 
-            // ------------------------------ row tile done ------------------------------
-            mbar_wait(pv_done, (n - 1) & 1);   // the tile's last PV
-            tc_fence_after();
-            // the row's sum of weights over all column groups, in a fixed order
+            // ------------------------------ row tile done: merge the four streams ------------------------------
+            refbuf[cg * TM + row_in_tile] = ref;
             ksbuf[cg * TM + row_in_tile] = ksum;
             named_bar_sync(2, EPI_THREADS);
-            float ktot = 0.f;
+            float rmax = -INFINITY, wg[NG], ktot = 0.f;
 #pragma unroll
-            for (int g = 0; g < NG; ++g) ktot += ksbuf[g * TM + row_in_tile];
+            for (int g = 0; g < NG; ++g) rmax = fmaxf(rmax, refbuf[g * TM + row_in_tile]);
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const float rg = refbuf[g * TM + row_in_tile];
+                wg[g] = (rg == -INFINITY) ? 0.f : ex2_approx(rg - rmax);
+                ktot = fmaf(wg[g], ksbuf[g * TM + row_in_tile], ktot);   // fixed order
+            }
+            wait_pv(n - 1);   // the tile's last PV
             const bool complete = (ww.Cw == 1);
-            const size_t slot0 = static_cast<size_t>(w_cur) * P.slots_per_wave + static_cast<size_t>(ww.tile_in_wave) * ww.Cw;
+            const size_t slot0 = static_cast<size_t>(w) * P.slots_per_wave + static_cast<size_t>(ww.tile_in_wave) * ww.Cw;
             float* mine = P.partial + (slot0 + ww.c) * (TM * PS);
             // plain product: undo the reference exponent (2^ref may underflow exactly where FP32 K b would)
-            const float row_scale = NORM ? 1.f / ktot : ((ref == -INFINITY) ? 0.f : ex2_approx(ref));
-            for (int c0 = cg * 16; c0 < P.ebp; c0 += NG * 16) {   // this group's 16-column chunks of O
+            const float row_scale = NORM ? 1.f / ktot : ((rmax == -INFINITY) ? 0.f : ex2_approx(rmax));
+            for (int c0 = cg * 16; c0 < P.ebp; c0 += NG * 16) {   // this thread merges 16-column chunks c0 of all four O_g
                 float o[16];
-                tmem_ld_cols<16>(tmem_base + COL_O + c0 + lane_addr, o);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) o[c] = 0.f;
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    float og[16];
+                    tmem_ld_cols<16>(tmem_base + COL_O + g * MAX_EB + c0 + lane_addr, og);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) o[c] = fmaf(wg[g], og[c], o[c]);
+                }
                 if (complete) {
                     if (row_ok) {
 #pragma unroll
@@ -426,7 +429,7 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
             if (!complete) {
                 if (cg == 0) {
                     mine[MAX_EB * TM + row_in_tile] = ktot;
-                    mine[(MAX_EB + 1) * TM + row_in_tile] = ref;
+                    mine[(MAX_EB + 1) * TM + row_in_tile] = rmax;
                 }
                 __threadfence();
                 named_bar_sync(2, EPI_THREADS);
@@ -458,11 +461,8 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                     }
                 }
             } else {
-                named_bar_sync(2, EPI_THREADS);   // ksbuf is rewritten at the end of the next tile
+                named_bar_sync(2, EPI_THREADS);   // refbuf / ksbuf are rewritten at the end of the next tile
             }
-            ww = wn;
-            have = have_next;
-            w = w_next;
         }
     }
 
@@ -543,7 +543,7 @@ int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
     KMB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     KMB_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     pl->grid = sms;
-    const int fixed = 1024 + pl->kblocks * 2 * pv16::A_TILE_BYTES + 2 * pv16::TNS * 4 + 3 * pv16::NG * tc::TM * 4 + 512;
+    const int fixed = 1024 + pl->kblocks * 2 * pv16::A_TILE_BYTES + 2 * pv16::NG * tc::TM * 4 + 512;
     pl->stages = std::min(6, (smem_max - fixed) / pv16::SLOT_BYTES);
     if (pl->stages < 3) return set_error(KMB_ERR_UNSUPPORTED, "not enough shared memory for D=%d", D);
     pl->smem = fixed + pl->stages * pv16::SLOT_BYTES;
@@ -558,7 +558,7 @@ int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
     pl->off_vh = take(2 * static_cast<size_t>(M) * pl->Dp);
     pl->off_vl = take(2 * static_cast<size_t>(M) * pl->Dp);
     pl->off_un = take(sizeof(float) * N);
-    pl->off_vn = take(sizeof(float) * M);
+    pl->off_vn = take(sizeof(float) * pl->Mp);   // padded: the epilogue reads whole 128-source blocks
     pl->off_sh = take(2 * static_cast<size_t>(pl->Ep) * pl->Mp);
     pl->off_sl = take(2 * static_cast<size_t>(pl->Ep) * pl->Mp);
     pl->off_bmax = take(sizeof(float) * tc::CENTER_BLOCKS * E);
@@ -616,6 +616,8 @@ int tensor_pv16_product(const float* x, const float* y, const float* b, float* o
     if (int rc = tc::tensor_prepass_f16(x, y, N, M, D, pl.Dp, kid, F(pl.off_center), F(pl.off_stats), F(pl.off_sscale), uh, ul, vh, vl,
                                         F(pl.off_un), F(pl.off_vn), stream))
         return rc;
+    if (pl.Mp > M)   // |v|^2 of padded sources: 0x7f7f7f7f = 3.4e38, their weights underflow to zero
+        KMB_CUDA_CHECK(cudaMemsetAsync(F(pl.off_vn) + M, 0x7f, sizeof(float) * (pl.Mp - M), stream));
     {
         const int blocks = static_cast<int>(std::min<long long>(tc::CENTER_BLOCKS, (M + 7) / 8));
         pv16::signal_absmax_kernel<<<dim3(blocks, (E + 31) / 32), 256, 0, stream>>>(b, M, E, F(pl.off_bmax));

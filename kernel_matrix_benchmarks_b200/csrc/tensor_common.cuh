@@ -60,6 +60,29 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// tcgen05.wait::ld that the 16 destination registers of a preceding tcgen05.ld depend on.  A bare wait is only
+// ordered against other volatile asm: ptxas / nvcc may (and did, in kprod_tensor_pv16) schedule arithmetic that
+// consumes the loaded registers ABOVE it.  Passing the registers through the wait as "+r" operands pins every
+// consumer below it.
+#define KMB_DEP16(u)                                                                                                      \
+    "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]), "+r"(u[8]), "+r"(u[9]), \
+        "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15])
+__device__ __forceinline__ void tmem_ld_wait16(float* r) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(r);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : KMB_DEP16(u)::"memory");
+}
+__device__ __forceinline__ void tmem_ld_dep16(float* r) {   // after tmem_ld_wait16: the same pin for 16 more registers
+    uint32_t* u = reinterpret_cast<uint32_t*>(r);
+    asm volatile("" : KMB_DEP16(u)::"memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const float* r) {
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(r);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]),
+        "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+        : "memory");
+}
 // 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread = lane = row)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&r)[32]) {
     uint32_t* u = reinterpret_cast<uint32_t*>(r);
@@ -72,7 +95,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&r)[32]) {
           "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    tmem_ld_wait16(r);
+    tmem_ld_dep16(r + 16);
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 version 1): rows are 128 bytes,
@@ -119,21 +143,15 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* r) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const float* r) {
-    const uint32_t* u = reinterpret_cast<const uint32_t*>(r);
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-        "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]),
-        "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
-        : "memory");
-}
 // CPT (16 or 32) consecutive columns of this warp's 32 lanes <-> registers
 template <int CPT>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&r)[CPT]) {
     static_assert(CPT % 16 == 0, "16-column chunks");
 #pragma unroll
     for (int c = 0; c < CPT; c += 16) tmem_ld_32x16(taddr + c, r + c);
-    tmem_ld_wait();
+    tmem_ld_wait16(r);
+#pragma unroll
+    for (int c = 16; c < CPT; c += 16) tmem_ld_dep16(r + c);
 }
 template <int CPT>
 __device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const float (&r)[CPT]) {
