@@ -59,7 +59,7 @@ struct Params {
     int* tile_counter;
     long long N, M;
     int E, e0, eb, ebp;        // this pass covers signal columns e0 .. e0+eb-1; ebp = eb rounded up to 32
-    int n_tiles, nsb, kblocks, ksteps_last, stages;
+    int n_tiles, nsb, kblocks, ksteps_last, stages, ep_rows;
     int R, C, W, R_last, C_last, slots_per_wave;
 };
 
@@ -121,7 +121,8 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char* u_region = smem;                                   // kblocks x [A hi 16 KB | A lo 16 KB]
     unsigned char* ring = u_region + P.kblocks * 2 * A_TILE_BYTES;    // stages x 32 KB
-    float* refbuf = reinterpret_cast<float*>(ring + P.stages * SLOT_BYTES);   // NG x TM: per-group reference exponents
+    float* vline = reinterpret_cast<float*>(ring + P.stages * SLOT_BYTES);    // EPI_WARPS x 2 x 32: per-warp |v|^2 lines
+    float* refbuf = vline + EPI_WARPS * 2 * 32;                                // NG x TM: per-group reference exponents
     float* ksbuf = refbuf + NG * TM;                                           // NG x TM: per-group sums of weights
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ksbuf + NG * TM);
     uint64_t* empty_bar = full_bar + P.stages;
@@ -155,16 +156,16 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
         // all 32 lanes walk the loop (uniform control flow); one elected lane issues (see elect_one)
         uint32_t it = 0, seg = 0;
         auto emit_signal = [&](int sb) {   // one slot: hi panels 0, 1 | lo panels 0, 1
-            const int src0 = sb * TNS;
+            const int row0 = sb * P.ep_rows + P.e0;   // slab sb, signal column e0
             const int slot = it % ST;
             mbar_wait(&empty_bar[slot], ((it / ST) & 1) ^ 1);
             unsigned char* dst = ring + slot * SLOT_BYTES;
             if (elect_one()) {
                 mbar_arrive_expect_tx(&full_bar[slot], 4 * PANEL_BYTES);
-                tma_load_2d(dst + 0 * PANEL_BYTES, &map_sh, src0, P.e0, &full_bar[slot]);
-                tma_load_2d(dst + 1 * PANEL_BYTES, &map_sh, src0 + 64, P.e0, &full_bar[slot]);
-                tma_load_2d(dst + 2 * PANEL_BYTES, &map_sl, src0, P.e0, &full_bar[slot]);
-                tma_load_2d(dst + 3 * PANEL_BYTES, &map_sl, src0 + 64, P.e0, &full_bar[slot]);
+                tma_load_2d(dst + 0 * PANEL_BYTES, &map_sh, 0, row0, &full_bar[slot]);
+                tma_load_2d(dst + 1 * PANEL_BYTES, &map_sh, 64, row0, &full_bar[slot]);
+                tma_load_2d(dst + 2 * PANEL_BYTES, &map_sl, 0, row0, &full_bar[slot]);
+                tma_load_2d(dst + 3 * PANEL_BYTES, &map_sl, 64, row0, &full_bar[slot]);
             }
             __syncwarp();
             ++it;
@@ -208,13 +209,22 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
         uint32_t it = 0, n = 0, seg = 0;
         const uint32_t d_o = tmem_base + COL_O;
         const uint32_t idesc_s = idesc_f16(TNS), idesc_o = idesc_f16(P.ebp);
+#ifdef KMB_PV16_TIMING
+        long long macc[6] = {0, 0, 0, 0, 0, 0}, mprev = clock64();
+#define KMB_M(i) do { const long long t_ = clock64(); macc[i] += t_ - mprev; mprev = t_; } while (0)
+#else
+#define KMB_M(i) do { } while (0)
+#endif
         auto issue_pv = [&](uint32_t m, bool first_of_tile) {
             const int a = m & 1;
+            KMB_M(0);
             mbar_wait(&p_ready[a], (m >> 1) & 1);
+            KMB_M(1);
             const int slot = it % ST;
             mbar_wait(&full_bar[slot], (it / ST) & 1);
             ++it;
             tc_fence_after();
+            KMB_M(2);
             const unsigned char* sg = ring + slot * SLOT_BYTES;
             const uint32_t p_base = tmem_base + COL_S + a * TNS;
             if (elect_one()) {
@@ -246,8 +256,10 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                 const uint32_t d_s = tmem_base + COL_S + a * TNS;
                 for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
                     const int slot = it % ST;
+                    KMB_M(3);
                     mbar_wait(&full_bar[slot], (it / ST) & 1);
                     tc_fence_after();
+                    KMB_M(4);
                     const unsigned char* bt = ring + slot * SLOT_BYTES;
                     const unsigned char* at = u_region + kb * 2 * A_TILE_BYTES;
                     const int ksteps = (kb == P.kblocks - 1) ? P.ksteps_last : 4;
@@ -280,6 +292,11 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
             }
         }
         if (pv_pending) issue_pv(n - 1, prev_first);
+#ifdef KMB_PV16_TIMING
+        if (blockIdx.x == 0 && lane == 0) {
+            for (int i = 0; i < 5; ++i) P.out[8 + i] = static_cast<float>(macc[i]) / n;
+        }
+#endif
     } else {
         // -------------------------------------- epilogue --------------------------------------
         const int et = tid - 64;
@@ -291,11 +308,22 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
         const uint32_t o_mine = tmem_base + COL_O + cg * MAX_EB + lane_addr;   // this group's accumulator
         const float sscale = __ldg(P.sscale + 1);
         uint32_t n = 0;   // blocks this CTA has processed (all waves)
+#ifdef KMB_PV16_TIMING
+        long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define KMB_T(i) do { const long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } while (0)
+#else
+#define KMB_T(i) do { } while (0)
+#endif
         auto wait_pv = [&](uint32_t m) {   // PV(m) has read P(m) and finished accumulating into the O_g
             mbar_wait(&pv_done[m & 1], (m >> 1) & 1);
             tc_fence_after();
         };
 
+        // |v|^2 of this group's 32 sources: lane l fetches source l of the NEXT block (one coalesced load, a block
+        // ahead of its use), parks it in the warp's shared-memory line and every lane reads the line back as float4s
+        float* my_line = vline + (warp - 2) * 2 * 32;
+        float vn_next = 0.f;
+        bool primed = false;
         WaveWork ww;
         for (int w = 0; w < P.W; ++w) {
             if (!wave_work(P, w, cta, ww)) continue;
@@ -304,16 +332,37 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
             const bool row_ok = row < P.N;
             const float un = row_ok ? __ldg(P.un + row) : 0.f;
             float ksum = 0.f, ref = -INFINITY;   // this group's stream
+            if (!primed) {
+                vn_next = __ldg(P.vn + static_cast<long long>(ww.sb_lo) * TNS + col0 + lane);   // padded to whole blocks with 3.4e38
+                primed = true;
+            }
+            // first block of the next wave this CTA works in (for the prefetch across the tile boundary)
+            int sb_next_tile = -1;
+            {
+                WaveWork wn;
+                for (int w2 = w + 1; w2 < P.W && sb_next_tile < 0; ++w2)
+                    if (wave_work(P, w2, cta, wn)) sb_next_tile = wn.sb_lo;
+            }
 
             for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++n) {
                 const long long j0 = static_cast<long long>(sb) * TNS + col0;
                 const int a = n & 1;
                 const uint32_t st_addr = tmem_base + COL_S + a * TNS + col0 + lane_addr;
-                const float4* vnq = reinterpret_cast<const float4*>(P.vn + j0);   // |v|^2, padded to whole blocks with 3.4e38
+                float* line = my_line + (n & 1) * 32;
+                line[lane] = vn_next;
+                {
+                    const int sbn = (sb + 1 < ww.sb_hi) ? sb + 1 : sb_next_tile;
+                    if (sbn >= 0) vn_next = __ldg(P.vn + static_cast<long long>(sbn) * TNS + col0 + lane);
+                }
+                __syncwarp();
+                const float4* vnq = reinterpret_cast<const float4*>(line);
+                KMB_T(0);
                 mbar_wait(&acc_full[a], (n >> 1) & 1);
                 tc_fence_after();
+                KMB_T(1);
                 float2 t2[CPT / 2];   // S as pairs of sources, then t = -log2 k
                 tmem_ld_cols<CPT>(st_addr, reinterpret_cast<float(&)[CPT]>(t2));
+                KMB_T(2);
 
                 // t = -log2 of the kernel values (packed pairs) and their minimum over this thread's columns
                 float tmin = INFINITY;
@@ -321,7 +370,7 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                     const float2 nss2 = make_float2(-sscale, -sscale), un2 = make_float2(un, un);
 #pragma unroll
                     for (int c = 0; c < CPT / 4; ++c) {
-                        const float4 vq = __ldg(vnq + c);   // L1-resident broadcast load (all lanes, same address)
+                        const float4 vq = vnq[c];   // broadcast read of the warp's line
                         const float2 ta = neg_log2_kernel2<KID>(t2[2 * c], nss2, add2(make_float2(vq.x, vq.y), un2));
                         const float2 tb = neg_log2_kernel2<KID>(t2[2 * c + 1], nss2, add2(make_float2(vq.z, vq.w), un2));
                         t2[2 * c] = ta;
@@ -334,6 +383,7 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                     for (int c = 0; c < CPT / 2; ++c) t2[c] = make_float2(INFINITY, INFINITY);
                 }
                 const float cm = -tmin;   // largest log2 k of the block
+                KMB_T(3);
                 // lazy rescale: keep the reference exponent unless the maximum outgrew it by 2^8
                 {
                     bool need = false;
@@ -356,6 +406,7 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                         if (need) ref = cm;
                     }
                 }
+                KMB_T(4);
                 // P = 2^(log2 k - ref) = 2^(-ref - t), FP16 hi / lo, two sources per TMEM column, over this thread's own S columns
                 {
                     uint32_t ph[CPT / 2], pl[CPT / 2];
@@ -378,11 +429,19 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                     tmem_st_32x16(st_addr + CPT / 2, reinterpret_cast<const float*>(pl));
                     ksum += kacc.x + kacc.y;
                 }
+                KMB_T(5);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_ready[a]);
+                KMB_T(6);
             }
+#ifdef KMB_PV16_TIMING
+            if (blockIdx.x == 0 && et == 0) {
+                for (int i = 0; i < 7; ++i) P.out[i] = static_cast<float>(tacc[i]) / n;
+                P.out[7] = static_cast<float>(n);
+            }
+#endif
 
             // ------------------------------ row tile done: merge the four streams ------------------------------
             refbuf[cg * TM + row_in_tile] = ref;
@@ -503,8 +562,10 @@ static __global__ void signal_scale_kernel(const float* __restrict__ pmax, int b
     bscale[e] = exp2f(static_cast<float>(q));
     binv[e] = exp2f(static_cast<float>(-q));
 }
-// hi/lo[e][j] = FP16 hi/lo of 2^q_e b[j][e]  (K-major signal for the P.B contraction), zero padded
-static __global__ void transpose_split_signal_f16_kernel(const float* __restrict__ b, long long M, long long Mp, int E,
+// hi/lo[sb][e][jj] = FP16 hi/lo of 2^q_e b[128 sb + jj][e]: the K-major signal of the P.B contraction, one contiguous
+// (Ep x 128) slab per source block (a TMA box then reads 64 rows of 128 bytes 256 bytes apart, not 64 rows that are
+// 2 Mp bytes apart), zero padded
+static __global__ void transpose_split_signal_f16_kernel(const float* __restrict__ b, long long M, long long Mp, int E, int Ep,
                                                          const float* __restrict__ bscale, __half* __restrict__ hi,
                                                          __half* __restrict__ lo) {
     const long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -512,8 +573,9 @@ static __global__ void transpose_split_signal_f16_kernel(const float* __restrict
     if (j >= Mp) return;
     const float v = (j < M && e < E) ? b[j * E + e] * bscale[e] : 0.f;
     const __half h = __float2half_rn(v);
-    hi[e * Mp + j] = h;
-    lo[e * Mp + j] = __float2half_rn(v - __half2float(h));
+    const long long at = ((j / TNS) * Ep + e) * TNS + (j % TNS);
+    hi[at] = h;
+    lo[at] = __float2half_rn(v - __half2float(h));
 }
 
 }  // namespace pv16
@@ -543,7 +605,7 @@ int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
     KMB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     KMB_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     pl->grid = sms;
-    const int fixed = 1024 + pl->kblocks * 2 * pv16::A_TILE_BYTES + 2 * pv16::NG * tc::TM * 4 + 512;
+    const int fixed = 1024 + pl->kblocks * 2 * pv16::A_TILE_BYTES + pv16::EPI_WARPS * 2 * 32 * 4 + 2 * pv16::NG * tc::TM * 4 + 512;
     pl->stages = std::min(6, (smem_max - fixed) / pv16::SLOT_BYTES);
     if (pl->stages < 3) return set_error(KMB_ERR_UNSUPPORTED, "not enough shared memory for D=%d", D);
     pl->smem = fixed + pl->stages * pv16::SLOT_BYTES;
@@ -625,7 +687,7 @@ int tensor_pv16_product(const float* x, const float* y, const float* b, float* o
         pv16::signal_scale_kernel<<<(pl.Ep + 127) / 128, 128, 0, stream>>>(F(pl.off_bmax), blocks, E, pl.Ep, F(pl.off_bscale), F(pl.off_binv));
         KMB_CUDA_CHECK(cudaGetLastError());
         dim3 g(static_cast<unsigned>((pl.Mp + 255) / 256), pl.Ep);
-        pv16::transpose_split_signal_f16_kernel<<<g, 256, 0, stream>>>(b, M, pl.Mp, E, F(pl.off_bscale), static_cast<__half*>(sh),
+        pv16::transpose_split_signal_f16_kernel<<<g, 256, 0, stream>>>(b, M, pl.Mp, E, pl.Ep, F(pl.off_bscale), static_cast<__half*>(sh),
                                                                         static_cast<__half*>(sl));
         KMB_CUDA_CHECK(cudaGetLastError());
         count_launch(3);
@@ -635,8 +697,8 @@ int tensor_pv16_product(const float* x, const float* y, const float* b, float* o
     if (int rc = tc::make_tensor_map_f16(&maps[1], ul, N, pl.Dp, tc::TM)) return rc;
     if (int rc = tc::make_tensor_map_f16(&maps[2], vh, M, pl.Dp, pv16::TNS)) return rc;
     if (int rc = tc::make_tensor_map_f16(&maps[3], vl, M, pl.Dp, pv16::TNS)) return rc;
-    if (int rc = tc::make_tensor_map_f16(&maps[4], sh, pl.Ep, static_cast<int>(pl.Mp), pv16::MAX_EB)) return rc;
-    if (int rc = tc::make_tensor_map_f16(&maps[5], sl, pl.Ep, static_cast<int>(pl.Mp), pv16::MAX_EB)) return rc;
+    if (int rc = tc::make_tensor_map_f16(&maps[4], sh, pl.nsb * pl.Ep, pv16::TNS, pv16::MAX_EB)) return rc;
+    if (int rc = tc::make_tensor_map_f16(&maps[5], sl, pl.nsb * pl.Ep, pv16::TNS, pv16::MAX_EB)) return rc;
 
     const int n_passes = pl.Ep / pv16::MAX_EB;
     for (int pass = 0; pass < n_passes; ++pass) {
@@ -659,6 +721,7 @@ int tensor_pv16_product(const float* x, const float* y, const float* b, float* o
         P.kblocks = pl.kblocks;
         P.ksteps_last = pl.ksteps_last;
         P.stages = pl.stages;
+        P.ep_rows = pl.Ep;
         P.R = pl.waves.R;
         P.C = pl.waves.C;
         P.W = pl.waves.W;
