@@ -140,6 +140,14 @@ int kmb_product_f64(const double* x, const double* y, const double* b, double* o
                     int64_t n_sources, int D, int E, int kernel_id, int flags, int64_t row_offset,
                     void* stream);
 
+/* out[i, j] = k(x_i, y_j) in double precision: an explicit (n, m) block of the kernel matrix -- kernel_matrix(...)
+ * of bruteforce.py:25-58 (difference form, :53-54) restricted to m source points.  Used for the m landmark columns of
+ * the Nystrom preconditioner of the CG solve (m ~ 10^3; the full matrix is never formed).  x (n, D), y (m, D),
+ * out (n, m): float64 device arrays, row-major.  The inverse-distance kernel returns +inf on coincident points (the
+ * reference zeroes those by flat index, bruteforce.py:12-14; not applied here). */
+int kmb_kernel_block_f64(const double* x, const double* y, double* out, int64_t n, int64_t m, int D, int kernel_id,
+                         void* stream);
+
 /* Number of this library's kernels the last kmb_product_f32 / kmb_cg_* call on this
  * thread launched (bench.py's gpu_launches). */
 int kmb_last_launch_count(void);

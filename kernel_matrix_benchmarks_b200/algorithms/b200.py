@@ -26,7 +26,8 @@ import torch
 from .. import _lib
 from .. import product as _product
 from ..product import Workspace, device_info, kernel_product, kernel_product_sym_part, last_launch_count
-from ..solver import CudaShardOps, CudaSymmetricOps, LocalComm, TorchDistComm, cg_solve, shard_bounds
+from ..solver import (CudaShardOps, CudaSymmetricOps, LocalComm, NystromPreconditioner, TorchDistComm, cg_solve,
+                      landmark_indices, pcg_solve, shard_bounds)
 from .base import BaseProduct, BaseSolver
 
 
@@ -245,10 +246,13 @@ class B200Solver(BaseSolver):
     """
 
     def __init__(self, *, kernel, dimension, normalize_rows=False, precision="float32", lam=0.0, rtol=1e-6,
-                 max_iter=500, path="auto", device=0, distributed=False):
+                 max_iter=500, path="auto", device=0, distributed=False, preconditioner="nystrom", precond_rank=1024):
         super().__init__(kernel=kernel, dimension=dimension, normalize_rows=normalize_rows, precision=precision)
         if kernel not in _lib.KERNEL_IDS:
             raise NotImplementedError(f"B200Solver doesn't support kernel {kernel}.")
+        if preconditioner not in ("nystrom", "none"):
+            raise ValueError(f"unknown preconditioner {preconditioner!r} (expected 'nystrom' or 'none')")
+        self.preconditioner, self.precond_rank = preconditioner, int(precond_rank)
         _check_precision(precision, "B200Solver")
         _lib.load()
         if not torch.cuda.is_available():
@@ -262,7 +266,8 @@ class B200Solver(BaseSolver):
         self.res = None
 
     def _set_name(self):
-        self.name = f"B200Solver({self.precision_name}, lam={self.lam:g}, rtol={self.rtol:g})"
+        pc = f", nystrom{self.precond_rank}" if self.preconditioner == "nystrom" else ""
+        self.name = f"B200Solver({self.precision_name}, lam={self.lam:g}, rtol={self.rtol:g}{pc})"
 
     def set_query_arguments(self, **kwargs):
         """``query-args`` of algos.yaml (runner.py:123): rtol / max_iter / lam can be swept without refitting."""
@@ -278,17 +283,49 @@ class B200Solver(BaseSolver):
         torch.cuda.synchronize(self.device)
 
     def fit(self):
-        """Timed.  Nothing to factorise: the system is applied through the on-the-fly product."""
-        self._ops = {}
-        torch.cuda.synchronize(self.device)
+        """Timed (the harness books it as build time).  The system itself is never factorised -- it is applied
+        through the on-the-fly product -- but the Nystrom preconditioner (solver.NystromPreconditioner: m landmark
+        columns of K, an m x m eigendecomposition) depends on the points only and is built here."""
+        self._ops, self._precond = {}, {}
+        with torch.cuda.device(self.device):
+            with _GpuTimer() as t:
+                if self._use_precond():
+                    self._precond_for(self._mode(1))
+            torch.cuda.synchronize(self.device)
+        self.fit_ms = t.ms()
+
+    def _mode(self, E):
+        symmetric = self.path == "auto" and CudaSymmetricOps.applies(self.source_points, self.kernel, E)
+        return "symmetric" if symmetric else "rows"
+
+    def _use_precond(self):
+        return (self.preconditioner == "nystrom" and self.kernel != "inverse-distance" and self.precond_rank > 0 and
+                self.source_points.shape[0] >= 2 * self.precond_rank)
+
+    def _precond_for(self, key):
+        """Symmetric matvec: every rank holds all rows (no collective inside the preconditioner); row-sharded
+        matvec: each rank holds its rows of U and the small products are all-reduced."""
+        if key not in self._precond:
+            n = self.source_points.shape[0]
+            idx = landmark_indices(n, self.precond_rank).to(self.device)
+            landmarks = self.source_points[idx]
+            if key == "symmetric":
+                pts, comm = self.source_points, LocalComm()
+            else:
+                lo, hi, _ = shard_bounds(n, self.comm.rank, self.comm.world)
+                pts, comm = self.source_points[lo:hi], self.comm
+            self._precond[key] = NystromPreconditioner(pts, landmarks, self.kernel, self.lam, comm)
+        pc = self._precond[key]
+        pc.set_shift(self.lam)   # lam may have been changed by set_query_arguments
+        return pc
 
     def _ops_for(self, E):
         """The matvec of the solve always has targets == sources: the symmetric product applies whenever
         the kernel is Gaussian, D <= 3 and there is one right-hand side (every rank then holds all CG
         vectors and the ranks share the unit list); otherwise the rows of the system are sharded."""
         n = self.source_points.shape[0]
-        symmetric = self.path == "auto" and CudaSymmetricOps.applies(self.source_points, self.kernel, E)
-        key = "symmetric" if symmetric else "rows"
+        key = self._mode(E)
+        symmetric = key == "symmetric"
         if key not in self._ops:
             if symmetric:
                 self._ops[key] = CudaSymmetricOps(self.source_points, self.kernel, self.comm)
@@ -308,15 +345,18 @@ class B200Solver(BaseSolver):
         with torch.cuda.device(self.device):
             with _GpuTimer() as t:
                 self._ops_for(self.target_signal.shape[1])
+                pc = self._precond_for("symmetric" if self.symmetric else "rows") if self._use_precond() else None
+                self.precond_rank_used = pc.rank if pc is not None else 0
                 if self.symmetric:  # replicated vectors; the only collective is inside ops.matvec
-                    self.info = cg_solve(self.ops, LocalComm(), self.target_signal, n, lam=self.lam, rtol=self.rtol,
-                                         max_iter=self.max_iter)
-                    self.x_full = self.info.x
+                    comm, rhs = LocalComm(), self.target_signal
                 else:
                     lo, hi = self.rows
-                    self.info = cg_solve(self.ops, self.comm, self.target_signal[lo:hi].contiguous(), n, lam=self.lam,
-                                         rtol=self.rtol, max_iter=self.max_iter)
-                    self.x_full = self.comm.all_gather(self.info.x, n)
+                    comm, rhs = self.comm, self.target_signal[lo:hi].contiguous()
+                if pc is not None:
+                    self.info = pcg_solve(self.ops, comm, rhs, n, pc, lam=self.lam, rtol=self.rtol, max_iter=self.max_iter)
+                else:
+                    self.info = cg_solve(self.ops, comm, rhs, n, lam=self.lam, rtol=self.rtol, max_iter=self.max_iter)
+                self.x_full = self.info.x if self.symmetric else self.comm.all_gather(self.info.x, n)
             torch.cuda.synchronize(self.device)
         self.query_ms = t.ms()
 
@@ -333,6 +373,8 @@ class B200Solver(BaseSolver):
             "cg_rel_residual": float(self.info.rel_residual),
             "cg_converged": bool(self.info.converged),
             "matvec": "symmetric" if self.symmetric else "rows",
+            "preconditioner": f"nystrom(rank={self.precond_rank_used})" if self.precond_rank_used else "none",
+            "gpu_fit_ms": float(getattr(self, "fit_ms", 0.0)),
             "gpu_launches": int(self.ops.launches),
         }
 
@@ -340,7 +382,7 @@ class B200Solver(BaseSolver):
         return super().get_memory_usage() + torch.cuda.memory_allocated(self.device) / 1024
 
     def done(self):
-        for k in ("source_points", "target_signal", "ops", "_ops", "x_full"):
+        for k in ("source_points", "target_signal", "ops", "_ops", "_precond", "x_full"):
             self.__dict__.pop(k, None)
 
     def __del__(self):

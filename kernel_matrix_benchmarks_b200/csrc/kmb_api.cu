@@ -42,6 +42,7 @@ KMB_DECLARE_TABLE(kDirect_gaussprod_n1)
 // kprod_f64.cu
 int product_f64(const double* x, const double* y, const double* b, double* out, int64_t N, int64_t M, int D, int E,
                 int kernel_id, int flags, int64_t row_offset, cudaStream_t stream);
+int kernel_block_f64(const double* x, const double* y, double* out, int64_t n, int64_t m, int D, int kernel_id, cudaStream_t stream);
 // kprod_sym.cu
 bool sym_supported(int D);
 int sym_tile_rows();
@@ -419,6 +420,15 @@ int kmb_product_f64(const double* x, const double* y, const double* b, double* o
     if (!(flags & KMB_FLAG_DENSITY) && !b) return set_error(KMB_ERR_INVALID, "b is NULL without KMB_FLAG_DENSITY");
     if (N == 0) return KMB_OK;
     return product_f64(x, y, b, out, N, M, D, E, kernel_id, flags, row_offset, static_cast<cudaStream_t>(stream_));
+}
+
+int kmb_kernel_block_f64(const double* x, const double* y, double* out, int64_t n, int64_t m, int D, int kernel_id, void* stream_) {
+    g_launches = 0;
+    if (n < 0 || m < 1 || D < 1) return set_error(KMB_ERR_INVALID, "bad sizes n=%lld m=%lld D=%d", (long long)n, (long long)m, D);
+    if (kernel_id < KMB_KERNEL_GAUSSIAN || kernel_id > KMB_KERNEL_INVERSE_DISTANCE) return set_error(KMB_ERR_UNSUPPORTED, "unknown kernel %d", kernel_id);
+    if (!x || !y || !out) return set_error(KMB_ERR_INVALID, "x, y and out must not be NULL");
+    if (n == 0) return KMB_OK;
+    return kernel_block_f64(x, y, out, n, m, D, kernel_id, static_cast<cudaStream_t>(stream_));
 }
 
 int kmb_product_sym_workspace_bytes(int64_t n, int D, int part, int n_parts, size_t* bytes) {

@@ -102,7 +102,36 @@ int launch_f64(const double* x, const double* y, const double* b, double* out, i
     return KMB_OK;
 }
 
+// out[i][j] = k(x_i, y_j): an explicit (n x m) block of the kernel matrix, m small (the landmark columns of the
+// Nystrom preconditioner, solver.py).  kernel_matrix(...) of bruteforce.py:25-58 restricted to m source points.
+template <int KID>
+__global__ void __launch_bounds__(256) kernel_block_f64_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                                double* __restrict__ out, long long n, long long m, int D) {
+    const long long j = blockIdx.y * 32ll + threadIdx.x;
+    const long long i = blockIdx.x * 8ll + threadIdx.y;
+    if (i >= n || j >= m) return;
+    double d2 = 0.0;
+    for (int d = 0; d < D; ++d) {
+        const double diff = x[i * D + d] - y[j * D + d];
+        d2 = fma(diff, diff, d2);
+    }
+    out[i * m + j] = kernel_value_f64<KID>(d2);
+}
+
 }  // namespace
+
+int kernel_block_f64(const double* x, const double* y, double* out, int64_t n, int64_t m, int D, int kernel_id, cudaStream_t stream) {
+    if ((m + 31) / 32 > 65535 || (n + 7) / 8 > 2147483647ll) return set_error(KMB_ERR_UNSUPPORTED, "block too large (n=%lld, m=%lld)", (long long)n, (long long)m);
+    const dim3 block(32, 8), grid(static_cast<unsigned>((n + 7) / 8), static_cast<unsigned>((m + 31) / 32));
+    switch (kernel_id) {
+        case KMB_KERNEL_GAUSSIAN: kernel_block_f64_kernel<KMB_KERNEL_GAUSSIAN><<<grid, block, 0, stream>>>(x, y, out, n, m, D); break;
+        case KMB_KERNEL_ABSOLUTE_EXPONENTIAL: kernel_block_f64_kernel<KMB_KERNEL_ABSOLUTE_EXPONENTIAL><<<grid, block, 0, stream>>>(x, y, out, n, m, D); break;
+        default: kernel_block_f64_kernel<KMB_KERNEL_INVERSE_DISTANCE><<<grid, block, 0, stream>>>(x, y, out, n, m, D); break;
+    }
+    KMB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return KMB_OK;
+}
 
 int product_f64(const double* x, const double* y, const double* b, double* out, int64_t N, int64_t M, int D, int E,
                 int kernel_id, int flags, int64_t row_offset, cudaStream_t stream) {

@@ -151,6 +151,24 @@ def kernel_product_f64(x, y, b, *, kernel="gaussian", normalize_rows=False, dens
     return out
 
 
+def kernel_block_f64(x, y, *, kernel="gaussian"):
+    """Explicit (n, m) block k(x_i, y_j) of the kernel matrix in float64 (kmb_kernel_block_f64): the landmark
+    columns of the Nystrom preconditioner.  x (n, D), y (m, D): float64 CUDA tensors."""
+    lib = _lib.load()
+    if kernel not in _lib.KERNEL_IDS:
+        raise NotImplementedError(f"B200 kernel product doesn't support kernel {kernel}.")
+    for name, t in (("points", x), ("landmarks", y)):
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.dim() == 2):
+            raise ValueError(f"{name} must be a contiguous 2-D float64 CUDA tensor")
+    if x.shape[1] != y.shape[1]:
+        raise ValueError("points and landmarks disagree on D")
+    out = torch.empty((x.shape[0], y.shape[0]), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.kmb_kernel_block_f64(_ptr(x), _ptr(y), _ptr(out), x.shape[0], y.shape[0], x.shape[1],
+                                            _lib.KERNEL_IDS[kernel], _stream()))
+    return out
+
+
 def direct_stats(workspace=None, device=None):
     """What the device-side statistics pass of the last direct-path product decided (synchronises):
     bounding-box centre, log2(e)*half-diagonal^2 and the evaluation form of the Gaussian kernel."""

@@ -203,3 +203,77 @@ def test_symmetric_cg_gloo(tmp_path, world, n):
     for p in parts:  # every rank holds the whole solution
         assert p["x"].shape == (n, 1) and orc.rel_l2(p["x"], b) <= 1e-8
     assert all(np.array_equal(parts[0]["x"], p["x"]) for p in parts[1:]), "replicated vectors must stay bit-identical"
+
+
+# ---- Nystrom-preconditioned CG: same host logic on CPU, the kernel block from the oracle ----------------
+
+def _oracle_block(kernel):
+    def block(p, q):
+        d2 = ((p[:, None, :] - q[None, :, :]) ** 2).sum(-1)
+        return torch.exp(-d2) if kernel == "gaussian" else torch.exp(-torch.sqrt(d2))
+    return block
+
+
+def test_pcg_single_rank_converges_in_a_few_iterations():
+    from kernel_matrix_benchmarks_b200.solver import NystromPreconditioner, landmark_indices, pcg_solve
+
+    n, lam = 1500, 1.0
+    rng = np.random.RandomState(3)
+    pts, b = rng.rand(n, 3), rng.randn(n, 2)
+    rhs = orc.regularised_matvec("gaussian", pts, b, lam)
+    ops = OracleShardOps(pts, "gaussian", 0, n)
+    plain = cg_solve(ops, LocalComm(), torch.from_numpy(rhs).clone(), n, lam=lam, rtol=1e-9, max_iter=300)
+    tp = torch.from_numpy(pts)
+    idx = landmark_indices(n, 300)
+    assert len(set(idx.tolist())) == 300 and torch.equal(idx, landmark_indices(n, 300))
+    pc = NystromPreconditioner(tp, tp[idx], "gaussian", lam, block_fn=_oracle_block("gaussian"), dtype=torch.float64)
+    res = pcg_solve(ops, LocalComm(), torch.from_numpy(rhs).clone(), n, pc, lam=lam, rtol=1e-9, max_iter=50)
+    assert res.converged and res.iterations <= 4 < plain.iterations
+    assert orc.rel_l2(res.x.numpy(), b) <= 1e-6
+    # the preconditioner is the exact inverse of K_hat + mu I on the span it was built from
+    U, S = pc.U, pc.eigenvalues
+    assert torch.allclose(U.T @ U, torch.eye(pc.rank, dtype=torch.float64), atol=1e-4)   # eigenvalues down to 1e-10 of the largest
+    v = torch.from_numpy(rng.randn(n, 1))
+    Mv = U @ (S.unsqueeze(1) * (U.T @ v)) + pc.mu * v
+    assert orc.rel_l2(pc.apply(Mv).numpy(), v.numpy()) <= 1e-9
+    # lam = 0 (the reference's system): mu falls back to the smallest kept eigenvalue, still SPD
+    pc.set_shift(0.0)
+    assert pc.mu > 0
+
+
+def _pcg_worker(rank, world, port, n, lam, out_dir):
+    from kernel_matrix_benchmarks_b200.solver import NystromPreconditioner, landmark_indices, pcg_solve
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.RandomState(12)
+        pts, b = rng.rand(n, 3), rng.randn(n, 1)
+        rhs = orc.regularised_matvec("absolute-exponential", pts, b, lam)
+        lo, hi, _ = shard_bounds(n, rank, world)
+        comm = TorchDistComm()
+        tp = torch.from_numpy(pts)
+        pc = NystromPreconditioner(tp[lo:hi], tp[landmark_indices(n, 200)], "absolute-exponential", lam, comm,
+                                   block_fn=_oracle_block("absolute-exponential"), dtype=torch.float64)
+        ops = OracleShardOps(pts, "absolute-exponential", lo, hi)
+        res = pcg_solve(ops, comm, torch.from_numpy(rhs[lo:hi]).clone(), n, pc, lam=lam, rtol=1e-9, max_iter=100)
+        np.savez(os.path.join(out_dir, f"pcg{rank}.npz"), x=res.x.numpy(), it=res.iterations, conv=res.converged, lo=lo, hi=hi,
+                 rank_kept=pc.rank)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pcg_sharded_gloo(tmp_path):
+    world, n, lam = 2, 901, 1.0
+    mp.spawn(_pcg_worker, args=(world, _free_port(), n, lam, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.RandomState(12)
+    pts, b = rng.rand(n, 3), rng.randn(n, 1)
+    parts = [np.load(tmp_path / f"pcg{r}.npz") for r in range(world)]
+    assert all(bool(p["conv"]) for p in parts) and len({int(p["it"]) for p in parts}) == 1
+    x = np.concatenate([p["x"] for p in parts], axis=0)
+    assert orc.rel_l2(x, b) <= 1e-6
+    # plain CG on the same system needs several times as many iterations
+    plain = cg_solve(OracleShardOps(pts, "absolute-exponential", 0, n), LocalComm(),
+                     torch.from_numpy(orc.regularised_matvec("absolute-exponential", pts, b, lam)).clone(), n, lam=lam,
+                     rtol=1e-9, max_iter=500)
+    assert int(parts[0]["it"]) * 2 <= plain.iterations

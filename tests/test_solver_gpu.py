@@ -88,3 +88,36 @@ def test_cg_symmetric_matvec_agrees_with_row_matvec():
     # residual on sampled rows with the float64 oracle product
     want = orc.kernel_product("gaussian", ds.source_points, None, x_sym, rows=rows) + lam * x_sym[rows]
     assert orc.rel_l2(want, rhs[rows]) <= 2e-5
+
+
+def test_kernel_block_matches_oracle():
+    """kmb_kernel_block_f64 == kernel_matrix(...) of bruteforce.py:25-58 on the landmark columns."""
+    import torch
+    from kernel_matrix_benchmarks_b200 import product
+
+    rng = np.random.RandomState(2)
+    x, y = rng.rand(777, 3), rng.rand(65, 3)
+    for kernel in ("gaussian", "absolute-exponential"):
+        got = product.kernel_block_f64(torch.tensor(x, device="cuda"), torch.tensor(y, device="cuda"), kernel=kernel).cpu().numpy()
+        d2 = ((x[:, None, :] - y[None, :, :]) ** 2).sum(-1)
+        want = np.exp(-d2) if kernel == "gaussian" else np.exp(-np.sqrt(d2))
+        assert np.abs(got - want).max() <= 1e-14
+
+
+@pytest.mark.parametrize("kernel", ["gaussian", "absolute-exponential"])
+def test_nystrom_preconditioner_cuts_iterations(kernel):
+    """Same system with and without the Nystrom preconditioner: same solution, a fraction of the iterations."""
+    from kernel_matrix_benchmarks_b200 import datasets
+
+    n, lam = 6000, 1.0
+    ds = datasets.uniform_cube(n, 3, 1.0, kernel, "solver")
+    rhs = orc.regularised_matvec(kernel, ds.source_points, ds.source_signal, lam)
+    x_pc, e_pc = run_solver(kernel, ds.source_points, rhs, lam=lam, rtol=1e-6, precond_rank=512)
+    x_cg, e_cg = run_solver(kernel, ds.source_points, rhs, lam=lam, rtol=1e-6, preconditioner="none")
+    assert e_pc["preconditioner"].startswith("nystrom") and e_cg["preconditioner"] == "none"
+    assert e_pc["cg_converged"] and e_cg["cg_converged"]
+    assert e_pc["cg_iterations"] * 4 <= e_cg["cg_iterations"], (e_pc, e_cg)
+    assert orc.rel_l2(x_pc, ds.source_signal) <= 1e-4
+    assert orc.rel_l2(x_pc, x_cg) <= 2e-4
+    res = orc.rel_l2(orc.regularised_matvec(kernel, ds.source_points, x_pc, lam), rhs)
+    assert res <= 5e-6, (res, e_pc)
