@@ -4,6 +4,9 @@
     python tools/bench_configs.py [c1 c3 c4 c5 ...] > profiles/configs_rNN.jsonl
 
 Not the headline bench (that is bench.py, config C2); this records where the other configs stand.
+Under torchrun (WORLD_SIZE > 1; products only) the plugin runs with distributed=True: target rows sharded over the
+ranks, sources replicated, no collective on the data path (the row blocks are gathered in get_result); the time
+reported is the maximum over ranks.
 """
 import json
 import os
@@ -18,7 +21,13 @@ from kernel_matrix_benchmarks_b200 import datasets  # noqa: E402
 from kernel_matrix_benchmarks_b200.algorithms.b200 import B200Product, B200Solver  # noqa: E402
 
 
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+
+
 def run_product(name, ds, runs=3, **kw):
+    if WORLD > 1:
+        kw = dict(kw, distributed=True, device=int(os.environ.get("LOCAL_RANK", "0")))
     algo = B200Product(kernel=ds.kernel, dimension=ds.D, normalize_rows=ds.normalize_rows, precision="float32", **kw)
     algo.prepare_data(source_points=ds.source_points, target_points=ds.target_points, same_points=ds.same_points)
     algo.fit()
@@ -41,6 +50,17 @@ def run_product(name, ds, runs=3, **kw):
     _product.set_profiling(False)
     res = algo.get_result()
     algo.done()
+    if WORLD > 1:
+        import torch
+        import torch.distributed as dist
+
+        t = torch.tensor([best["gpu_query_ms"], best.get("main_kernel_ms", 0.0)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best["gpu_query_ms"], best["main_kernel_ms"] = float(t[0]), float(t[1])
+        best["gpairs_per_s"] = float(ds.N) * ds.M / (best["gpu_query_ms"] * 1e-3) / 1e9
+        best["n_gpus"] = WORLD
+        if RANK != 0:
+            return
     pairs = float(ds.N) * ds.M
     out = {"config": name, "kernel": ds.kernel, "N": ds.N, "M": ds.M, "D": ds.D, "E": ds.E, "normalize_rows": ds.normalize_rows,
            "pairs": pairs, "finite": bool(np.isfinite(res).all()), **best}
@@ -81,6 +101,13 @@ def run_solver(name, n, lam=1.0, rtol=1e-6):
 
 def main():
     which = sys.argv[1:] or ["c1", "c2", "c3", "c4", "c5"]
+    if WORLD > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+        which = [w for w in which if not w.startswith("c5")]
     if "c1" in which:
         run_product("C1", datasets.config_c1())
     if "c2" in which:
@@ -102,3 +129,8 @@ def main():
 
 if __name__ == "__main__":
     main()
+    if WORLD > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
