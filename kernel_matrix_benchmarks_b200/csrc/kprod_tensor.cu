@@ -21,6 +21,7 @@
 //             two (max |operand| in [2^13, 2^15)): 22 significand bits as 3xTF32, kind::f16 runs at twice
 //             the TF32 rate and moves half the bytes; 64 halves per K block; S is rescaled in the epilogue.
 #include <algorithm>
+#include <cstdlib>
 
 #include <cuda_fp16.h>
 
@@ -366,6 +367,355 @@ kprod_tensor_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---- CTA pairs (cta_group::2), FP16 planes -----------------------------------------------------------------
+// The single-CTA kernel above fetches 48 KB of operands from L2 per 6 MMAs and runs into the L2 -> SM bandwidth
+// (ncu: 11.6 TB/s, tensor pipe 72 %).  Here two CTAs on neighbouring SMs work on two adjacent 128-row tiles and the
+// same 256 sources: each loads its own A tile and HALF of the B block, and one tcgen05.mma.cta_group::2 of shape
+// 256 x 256 x 16 (issued by the leader CTA) reads A from both CTAs' shared memory and the two B halves, leaving each
+// CTA its own 128 x 256 accumulator in its own TMEM.  Operand bytes per CTA and K block: 32 KB of A + 32 KB of B
+// (was 32 + 64), and a stage of 64 KB lets three stages fit.
+//   full_bar   leader's; both producers' TMA bytes land on it (cp.async.bulk.tensor ... cta_group::2), the leader's
+//              producer arms it with the bytes of both CTAs, the peer's producer arrives remotely
+//   empty_bar  one per CTA; the leader's tcgen05.commit multicasts to both
+//   acc_full   one per CTA (multicast commit); acc_empty: leader's, 8 arrivals (4 epilogue warps of each CTA)
+namespace pair {
+
+constexpr int STAGES2 = 3;
+constexpr int BH_BYTES = 128 * 128;                      // this CTA's half of a B tile: 128 sources x 128 bytes
+constexpr int STAGE2_BYTES = 2 * TILE_BYTES + 2 * BH_BYTES;   // A hi, A lo, B-half hi, B-half lo = 64 KB
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared-memory object of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
+    uint32_t a;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(p)), "r"(rank));
+    return a;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are counted on the LEADER CTA's barrier at the same offset as `bar`
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far are done
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+// D = F32, A = B = F16, K-major, M = 256 (two CTAs x 128 rows), N = 256
+__host__ __device__ constexpr uint32_t idesc2_f16() {
+    return (1u << 4) | (static_cast<uint32_t>(TN >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
+}
+
+template <int EP, int KID, bool NORM>
+struct Cfg2 {
+    static constexpr int SMEM_BYTES = 1024 + STAGES2 * STAGE2_BYTES + 2 * Cfg<EP, KID, NORM>::AUX_FLOATS * 4 +
+                                      (2 * STAGES2 + 2 * ACC_STAGES) * 8 + 16;
+};
+
+// work of cluster `cid` in wave w (the wave plan counts pairs of row tiles and clusters)
+__device__ __forceinline__ bool pair_wave_work(const Params& P, int w, int cid, WaveWork& ww) {
+    const bool last = (w == P.W - 1);
+    const int Rw = last ? P.R_last : P.R, Cw = last ? P.C_last : P.C;
+    if (cid >= Rw * Cw) return false;
+    ww.Cw = Cw;
+    ww.tile_in_wave = cid / Cw;              // pair of row tiles within the wave
+    ww.c = cid - ww.tile_in_wave * Cw;
+    ww.tile = w * P.R + ww.tile_in_wave;     // pair index
+    ww.sb_lo = static_cast<int>(static_cast<long long>(P.nsb) * ww.c / Cw);
+    ww.sb_hi = static_cast<int>(static_cast<long long>(P.nsb) * (ww.c + 1) / Cw);
+    return true;
+}
+
+template <int EP, int KID, bool NORM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+kprod_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                         const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                         const Params P) {
+    using C = Cfg<EP, KID, NORM>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* stages = smem;
+    float* aux = reinterpret_cast<float*>(smem + STAGES2 * STAGE2_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux + 2 * C::AUX_FLOATS);
+    uint64_t* empty_bar = full_bar + STAGES2;
+    uint64_t* acc_full = empty_bar + STAGES2;
+    uint64_t* acc_empty = acc_full + ACC_STAGES;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+    int* s_flag = reinterpret_cast<int*>(tmem_base_smem + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
+    const int cid = blockIdx.x >> 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 2 * (EPI_THREADS / 32)); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc2(tmem_base_smem, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp == 0) {
+        // ------------------------------------ TMA producer (both CTAs) ------------------------------------
+        uint32_t it = 0;
+        WaveWork ww;
+        for (int w = 0; w < P.W; ++w) {
+            if (!pair_wave_work(P, w, cid, ww)) continue;
+            const int row0 = (ww.tile * 2 + static_cast<int>(rank)) * TM;
+            for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb) {
+                const int src0 = sb * TN + static_cast<int>(rank) * 128;   // this CTA's half of the source block
+                for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+                    const int stage = it % STAGES2;
+                    mbar_wait(&empty_bar[stage], ((it / STAGES2) & 1) ^ 1);
+                    unsigned char* st = stages + stage * STAGE2_BYTES;
+                    const uint32_t leader_full = map_to_cta(&full_bar[stage], 0);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);   // both CTAs' bytes
+                        else mbar_arrive_cluster(leader_full);
+                        tma_load_2d_pair(st + 0 * TILE_BYTES, &map_ah, kb * 64, row0, leader_full);
+                        tma_load_2d_pair(st + 1 * TILE_BYTES, &map_al, kb * 64, row0, leader_full);
+                        tma_load_2d_pair(st + 2 * TILE_BYTES, &map_bh, kb * 64, src0, leader_full);
+                        tma_load_2d_pair(st + 2 * TILE_BYTES + BH_BYTES, &map_bl, kb * 64, src0, leader_full);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------- MMA issuer (leader CTA only) -------------------------------------
+        if (rank == 0) {
+            uint32_t it = 0, unit = 0;
+            WaveWork ww;
+            for (int w = 0; w < P.W; ++w) {
+                if (!pair_wave_work(P, w, cid, ww)) continue;
+                for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++unit) {
+                    const int a = unit % ACC_STAGES;
+                    mbar_wait(&acc_empty[a], ((unit / ACC_STAGES) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + a * TN;
+                    for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+                        const int stage = it % STAGES2;
+                        mbar_wait(&full_bar[stage], (it / STAGES2) & 1);
+                        tc_fence_after();
+                        const unsigned char* st = stages + stage * STAGE2_BYTES;
+                        const int ksteps = (kb == P.kblocks - 1) ? P.ksteps_last : 4;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (k < ksteps) {
+                                    const uint64_t ah = umma_desc_sw128(st + 0 * TILE_BYTES, k * 32);
+                                    const uint64_t al = umma_desc_sw128(st + 1 * TILE_BYTES, k * 32);
+                                    const uint64_t bh = umma_desc_sw128(st + 2 * TILE_BYTES, k * 32);
+                                    const uint64_t bl = umma_desc_sw128(st + 2 * TILE_BYTES + BH_BYTES, k * 32);
+                                    umma2_f16(d_tmem, al, bh, idesc2_f16(), (kb | k) != 0);
+                                    umma2_f16(d_tmem, ah, bl, idesc2_f16(), 1);
+                                    umma2_f16(d_tmem, ah, bh, idesc2_f16(), 1);
+                                }
+                            }
+                            umma2_commit_both(&empty_bar[stage]);   // both CTAs' slots are reusable
+                        }
+                        __syncwarp();
+                    }
+                    if (elect_one()) umma2_commit_both(&acc_full[a]);   // both CTAs' accumulators are complete
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // -------------------------------------- epilogue (both CTAs) --------------------------------------
+        const int et = tid - 64;
+        const int lane_group = warp & 3;
+        const int row_in_tile = lane_group * 32 + lane;
+        const float sscale = __ldg(P.sscale + 1);
+        uint32_t unit = 0;
+        WaveWork ww;
+        for (int w = 0; w < P.W; ++w) {
+            if (!pair_wave_work(P, w, cid, ww)) continue;
+            const int tile = ww.tile * 2 + static_cast<int>(rank);
+            const long long row = static_cast<long long>(tile) * TM + row_in_tile;
+            const bool row_ok = row < P.N;
+            const float un = row_ok ? __ldg(P.un + row) : 0.f;
+            [[maybe_unused]] const long long jz = (P.row_offset + row) % (P.M + 1);
+
+            float tot[EP], ktot = 0.f, kmax = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < EP; ++e) tot[e] = 0.f;
+
+            for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++unit) {
+                const long long j0 = static_cast<long long>(sb) * TN;
+                float* ax = aux + (unit & 1) * C::AUX_FLOATS;
+#pragma unroll
+                for (int jt = et; jt < TN; jt += EPI_THREADS) {
+                    const long long j = j0 + jt;
+                    const bool live = j < P.M;
+                    ax[jt] = live ? __ldg(P.vn + j) : 1.0e30f;
+#pragma unroll
+                    for (int e = 0; e < EP; ++e) {
+                        float v = 0.f;
+                        if (live && P.e0 + e < P.E) v = P.b ? __ldg(P.b + j * P.E + P.e0 + e) : 1.f;
+                        ax[TN + jt * EP + e] = v;
+                    }
+                }
+                named_bar_sync(1, EPI_THREADS);
+                const int a = unit % ACC_STAGES;
+                mbar_wait(&acc_full[a], (unit / ACC_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t t_addr = tmem_base + a * TN + (static_cast<uint32_t>(lane_group * 32) << 16);
+
+                float acc[EP], ksum = 0.f;
+#pragma unroll
+                for (int e = 0; e < EP; ++e) acc[e] = 0.f;
+#pragma unroll 1
+                for (int ch = 0; ch < TN / 32; ++ch) {
+                    float s[32];
+                    tmem_ld_32x32(t_addr + ch * 32, s);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) s[c] *= sscale;
+                    if constexpr (!C::ONLINE_MAX) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int jj = ch * 32 + c;
+                            float kv = kernel_from_parts<KID>(s[c], un, ax[jj]);
+                            if constexpr (KID == KMB_KERNEL_INVERSE_DISTANCE)
+                                if (j0 + jj == jz || j0 + jj >= P.M) kv = 0.f;
+#pragma unroll
+                            for (int e = 0; e < EP; ++e) acc[e] = fmaf(kv, ax[TN + jj * EP + e], acc[e]);
+                            if constexpr (NORM) ksum += kv;
+                        }
+                    } else {
+                        float cm = -INFINITY;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            s[c] = log2_kernel_from_parts<KID>(s[c], un, ax[ch * 32 + c]);
+                            cm = fmaxf(cm, s[c]);
+                        }
+                        const float mnew = fmaxf(kmax, cm);
+                        const float sc = (mnew == -INFINITY) ? 1.f : ex2_approx(kmax - mnew);
+                        const float moff = (mnew == -INFINITY) ? 0.f : mnew;
+                        kmax = mnew;
+                        ksum *= sc;
+                        ktot *= sc;
+#pragma unroll
+                        for (int e = 0; e < EP; ++e) { acc[e] *= sc; tot[e] *= sc; }
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int jj = ch * 32 + c;
+                            const float kv = ex2_approx(s[c] - moff);
+#pragma unroll
+                            for (int e = 0; e < EP; ++e) acc[e] = fmaf(kv, ax[TN + jj * EP + e], acc[e]);
+                            ksum += kv;
+                        }
+                    }
+                }
+                // accumulator drained: tell the leader's MMA warp (remote arrive from the peer)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_cta(&acc_empty[a], 0));
+#pragma unroll
+                for (int e = 0; e < EP; ++e) tot[e] += acc[e];
+                ktot += ksum;
+            }
+
+            // ------------------------------ write this row tile ------------------------------
+            if (tile < P.n_tiles) {   // the last pair may hold a ghost tile (odd number of row tiles)
+                if (ww.Cw == 1) {
+                    if (row_ok) {
+#pragma unroll
+                        for (int e = 0; e < EP; ++e)
+                            if (P.e0 + e < P.E) P.out[row * P.E + P.e0 + e] = NORM ? tot[e] / ktot : tot[e];
+                    }
+                } else {
+                    // partial records of one wave: [pair in wave][range c][rank]
+                    const size_t slot0 = static_cast<size_t>(w) * P.slots_per_wave + static_cast<size_t>(ww.tile_in_wave) * ww.Cw * 2 + rank;
+                    float* mine = P.partial + (slot0 + ww.c * 2) * (TM * C::PS);
+#pragma unroll
+                    for (int e = 0; e < EP; ++e) mine[e * TM + row_in_tile] = tot[e];
+                    if constexpr (NORM) mine[EP * TM + row_in_tile] = ktot;
+                    if constexpr (C::ONLINE_MAX) mine[(EP + 1) * TM + row_in_tile] = kmax;
+                    __threadfence();
+                    named_bar_sync(2, EPI_THREADS);
+                    if (et == 0) {
+                        const int old = atomicAdd(&P.tile_counter[tile], 1);
+                        const int last = (old == ww.Cw - 1);
+                        if (last) P.tile_counter[tile] = 0;
+                        *s_flag = last;
+                    }
+                    named_bar_sync(2, EPI_THREADS);
+                    const bool is_last = *s_flag != 0;
+                    named_bar_sync(2, EPI_THREADS);
+                    if (is_last && row_ok) {
+                        __threadfence();
+                        float sum[EP], l = 0.f, mx = -INFINITY;
+#pragma unroll
+                        for (int e = 0; e < EP; ++e) sum[e] = 0.f;
+                        if constexpr (C::ONLINE_MAX) {
+                            for (int c = 0; c < ww.Cw; ++c)
+                                mx = fmaxf(mx, __ldcg(P.partial + (slot0 + c * 2) * (TM * C::PS) + (EP + 1) * TM + row_in_tile));
+                        }
+                        for (int c = 0; c < ww.Cw; ++c) {
+                            const float* ps = P.partial + (slot0 + c * 2) * (TM * C::PS);
+                            float wgt = 1.f;
+                            if constexpr (C::ONLINE_MAX) {
+                                const float m = __ldcg(ps + (EP + 1) * TM + row_in_tile);
+                                wgt = (m == -INFINITY) ? 0.f : ex2_approx(m - mx);
+                            }
+#pragma unroll
+                            for (int e = 0; e < EP; ++e) sum[e] = fmaf(wgt, __ldcg(ps + e * TM + row_in_tile), sum[e]);
+                            if constexpr (NORM) l = fmaf(wgt, __ldcg(ps + EP * TM + row_in_tile), l);
+                        }
+#pragma unroll
+                        for (int e = 0; e < EP; ++e)
+                            if (P.e0 + e < P.E) P.out[row * P.E + P.e0 + e] = NORM ? sum[e] / l : sum[e];
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // neither CTA frees tensor memory (or exits) while the other may still signal it
+    if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
+}
+
+}  // namespace pair
+
 // ---- prepass ---------------------------------------------------------------------------------------
 
 // partial[blk][col] = sum over this block's rows of y[row][col]
@@ -644,6 +994,7 @@ namespace {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct TensorPlan {
+    bool pair;   // CTA-pair kernel (cta_group::2): FP16 planes, at least two row tiles
     int Dp, e_chunk, n_passes, grid, kblocks, ksteps_last;
     long long n_tiles, nsb;
     tc::WavePlan waves;
@@ -666,7 +1017,20 @@ int plan_tensor(int64_t N, int64_t M, int D, int E, int elt, TensorPlan* pl) {
     KMB_CUDA_CHECK(cudaGetDevice(&dev));
     KMB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     pl->grid = sms;
-    tc::plan_waves(pl->n_tiles, pl->nsb, pl->grid, static_cast<size_t>(tc::TM) * pl->Dp * pl->esz * 2, &pl->waves);
+    static const bool pair_enabled = [] {   // tuning knob: KMB_TENSOR_PAIR=0 keeps the single-CTA kernel
+        const char* e = getenv("KMB_TENSOR_PAIR");
+        return !(e && e[0] == '0');
+    }();
+    pl->pair = f16 && pair_enabled && pl->n_tiles >= 2 && sms >= 2;
+    if (pl->pair) {
+        // the wave plan counts pairs of row tiles and clusters of two CTAs
+        pl->grid = sms / 2 * 2;
+        tc::plan_waves((pl->n_tiles + 1) / 2, pl->nsb, pl->grid / 2, static_cast<size_t>(tc::TM) * pl->Dp * pl->esz * 4, &pl->waves);
+        pl->waves.slots_per_wave *= 2;
+        pl->waves.partial_slots *= 2;
+    } else {
+        tc::plan_waves(pl->n_tiles, pl->nsb, pl->grid, static_cast<size_t>(tc::TM) * pl->Dp * pl->esz * 2, &pl->waves);
+    }
     const int PS = tc::MAX_EP + 2;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
@@ -699,6 +1063,38 @@ int launch_one(const CUtensorMap* maps, const tc::Params& P, int grid, cudaStrea
     fn<<<grid, tc::THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], P);
     KMB_CUDA_CHECK(cudaGetLastError());
     return KMB_OK;
+}
+
+template <int EP, int KID, bool NORM>
+int launch_pair_one(const CUtensorMap* maps, const tc::Params& P, int grid, cudaStream_t stream) {
+    using C = tc::pair::Cfg2<EP, KID, NORM>;
+    auto fn = tc::pair::kprod_tensor_pair_kernel<EP, KID, NORM>;
+    static bool attr = false;
+    if (!attr) {
+        KMB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr = true;
+    }
+    fn<<<grid, tc::THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], P);
+    KMB_CUDA_CHECK(cudaGetLastError());
+    return KMB_OK;
+}
+
+template <int KID, bool NORM>
+int launch_pair_ep(int ep, const CUtensorMap* maps, const tc::Params& P, int grid, cudaStream_t stream) {
+    if (ep == 1) return launch_pair_one<1, KID, NORM>(maps, P, grid, stream);
+    if (ep == 2) return launch_pair_one<2, KID, NORM>(maps, P, grid, stream);
+    return launch_pair_one<4, KID, NORM>(maps, P, grid, stream);
+}
+
+int launch_pair_any(int kid, bool norm, int ep, const CUtensorMap* maps, const tc::Params& P, int grid, cudaStream_t stream) {
+    switch (kid * 2 + (norm ? 1 : 0)) {
+        case 0: return launch_pair_ep<KMB_KERNEL_GAUSSIAN, false>(ep, maps, P, grid, stream);
+        case 1: return launch_pair_ep<KMB_KERNEL_GAUSSIAN, true>(ep, maps, P, grid, stream);
+        case 2: return launch_pair_ep<KMB_KERNEL_ABSOLUTE_EXPONENTIAL, false>(ep, maps, P, grid, stream);
+        case 3: return launch_pair_ep<KMB_KERNEL_ABSOLUTE_EXPONENTIAL, true>(ep, maps, P, grid, stream);
+        case 4: return launch_pair_ep<KMB_KERNEL_INVERSE_DISTANCE, false>(ep, maps, P, grid, stream);
+        default: return launch_pair_ep<KMB_KERNEL_INVERSE_DISTANCE, true>(ep, maps, P, grid, stream);
+    }
 }
 
 template <int KID, bool NORM, int ELT>
@@ -767,8 +1163,9 @@ int tensor_product(const float* x, const float* y, const float* b, float* out, i
         if (int rc = tc::tensor_prepass_f16(x, y, N, M, D, pl.Dp, kid, center, cpart, sscale, uh, ul, vh, vl, un, vn, stream)) return rc;
         if (int rc = tc::make_tensor_map_f16(&maps[0], uh, N, pl.Dp, tc::TM)) return rc;
         if (int rc = tc::make_tensor_map_f16(&maps[1], ul, N, pl.Dp, tc::TM)) return rc;
-        if (int rc = tc::make_tensor_map_f16(&maps[2], vh, M, pl.Dp, tc::TN)) return rc;
-        if (int rc = tc::make_tensor_map_f16(&maps[3], vl, M, pl.Dp, tc::TN)) return rc;
+        // the pair kernel's CTAs each load half a source block (128 rows)
+        if (int rc = tc::make_tensor_map_f16(&maps[2], vh, M, pl.Dp, pl.pair ? 128 : tc::TN)) return rc;
+        if (int rc = tc::make_tensor_map_f16(&maps[3], vl, M, pl.Dp, pl.pair ? 128 : tc::TN)) return rc;
     } else {
         if (int rc = tc::tensor_prepass(x, y, N, M, D, pl.Dp, kid, center, cpart, static_cast<float*>(uh), static_cast<float*>(ul),
                                         static_cast<float*>(vh), static_cast<float*>(vl), un, vn, stream))
@@ -805,7 +1202,8 @@ int tensor_product(const float* x, const float* y, const float* b, float* out, i
         P.C_last = pl.waves.C_last;
         P.slots_per_wave = pl.waves.slots_per_wave;
         if (ev0 && pass == pl.n_passes - 1) KMB_CUDA_CHECK(cudaEventRecord(ev0, stream));
-        if (int rc = f16 ? launch_any<tc::ELT_F16>(kid, norm, pl.e_chunk, maps, P, grid, stream)
+        if (int rc = pl.pair ? launch_pair_any(kid, norm, pl.e_chunk, maps, P, grid, stream)
+                 : f16   ? launch_any<tc::ELT_F16>(kid, norm, pl.e_chunk, maps, P, grid, stream)
                          : launch_any<tc::ELT_TF32>(kid, norm, pl.e_chunk, maps, P, grid, stream))
             return rc;
         if (ev1 && pass == pl.n_passes - 1) KMB_CUDA_CHECK(cudaEventRecord(ev1, stream));
