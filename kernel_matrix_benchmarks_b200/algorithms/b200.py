@@ -300,14 +300,14 @@ class B200Solver(BaseSolver):
 
     def _use_precond(self):
         return (self.preconditioner == "nystrom" and self.kernel != "inverse-distance" and self.precond_rank > 0 and
-                self.source_points.shape[0] >= 2 * self.precond_rank)
+                self.source_points.shape[0] >= 64)
 
     def _precond_for(self, key):
         """Symmetric matvec: every rank holds all rows (no collective inside the preconditioner); row-sharded
         matvec: each rank holds its rows of U and the small products are all-reduced."""
         if key not in self._precond:
             n = self.source_points.shape[0]
-            idx = landmark_indices(n, self.precond_rank).to(self.device)
+            idx = landmark_indices(n, min(self.precond_rank, n // 2)).to(self.device)   # small data sets: half the points
             landmarks = self.source_points[idx]
             if key == "symmetric":
                 pts, comm = self.source_points, LocalComm()

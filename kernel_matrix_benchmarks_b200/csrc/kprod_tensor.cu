@@ -384,55 +384,6 @@ constexpr int STAGES2 = 3;
 constexpr int BH_BYTES = 128 * 128;                      // this CTA's half of a B tile: 128 sources x 128 bytes
 constexpr int STAGE2_BYTES = 2 * TILE_BYTES + 2 * BH_BYTES;   // A hi, A lo, B-half hi, B-half lo = 64 KB
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `p` (a shared-memory object of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
-    uint32_t a;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(p)), "r"(rank));
-    return a;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA load whose completion bytes are counted on the LEADER CTA's barrier at the same offset as `bar`
-__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far are done
-__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
-    const uint16_t mask = 3;
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                 "h"(mask)
-                 : "memory");
-}
 // D = F32, A = B = F16, K-major, M = 256 (two CTAs x 128 rows), N = 256
 __host__ __device__ constexpr uint32_t idesc2_f16() {
     return (1u << 4) | (static_cast<uint32_t>(TN >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
@@ -646,7 +597,10 @@ kprod_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                 // accumulator drained: tell the leader's MMA warp (remote arrive from the peer)
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(map_to_cta(&acc_empty[a], 0));
+                if (lane == 0) {
+                    if (rank != 0) mbar_arrive_cluster(map_to_cta(&acc_empty[a], 0));
+                    else mbar_arrive(&acc_empty[a]);
+                }
 #pragma unroll
                 for (int e = 0; e < EP; ++e) tot[e] += acc[e];
                 ktot += ksum;

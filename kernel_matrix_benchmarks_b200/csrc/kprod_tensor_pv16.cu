@@ -24,6 +24,7 @@
 // Work split: the wave schedule of kprod_tensor.cu -- every CTA of a wave walks the SAME source blocks at the same
 // time (all of them when there are at least as many row tiles as CTAs), so v and b blocks come from L2.
 #include <algorithm>
+#include <cstdlib>
 
 #include <cuda_fp16.h>
 
@@ -36,6 +37,7 @@ using namespace tc;
 
 constexpr int TNS = 128;               // sources per S block
 constexpr int SLOT_BYTES = 32768;      // ring slot: v block of one K block (hi 16 KB | lo 16 KB) or one signal block
+                                       // (CTA pairs: each CTA holds half of either, 16 KB slots)
 constexpr int A_TILE_BYTES = TM * 128; // 16 KB: 128 rows of one 128-byte K block
 constexpr int PANEL_BYTES = 64 * 128;  // signal: 64 signal columns x 64 sources (one swizzle atom wide)
 constexpr int NG = 4;                  // epilogue column groups (4 warps each)
@@ -63,6 +65,7 @@ struct Params {
     int R, C, W, R_last, C_last, slots_per_wave;
 };
 
+// `unit`: the CTA (single-CTA kernel) or the cluster (CTA pairs: the wave plan then counts pairs of row tiles)
 struct WaveWork { int tile, sb_lo, sb_hi, c, Cw, tile_in_wave; };
 __device__ __forceinline__ bool wave_work(const Params& P, int w, int cta, WaveWork& ww) {
     const bool last = (w == P.W - 1);
@@ -111,17 +114,21 @@ __device__ __forceinline__ float2 neg_log2_kernel2(float2 s_raw, float2 nsscale,
     }
 }
 
-template <int KID, bool NORM>
-__global__ void __launch_bounds__(THREADS, 1)
-kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
-                         const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
-                         const __grid_constant__ CUtensorMap map_sh, const __grid_constant__ CUtensorMap map_sl,
-                         const Params P) {
+// PAIR: two CTAs of a cluster (cta_group::2) work on two adjacent row tiles and the same source blocks: every MMA is
+// 256 rows tall (half as many instructions per row tile -- the issuing warp is what bounds the single-CTA kernel),
+// each CTA streams half of every v block (64 sources) and half of every signal block (32 signal columns), the leader
+// CTA issues, tcgen05.commit multicasts to both CTAs' barriers and the peer's epilogue warps arrive on the leader's.
+template <int KID, bool NORM, bool PAIR>
+__device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUtensorMap& map_al, const CUtensorMap& map_bh,
+                                          const CUtensorMap& map_bl, const CUtensorMap& map_sh, const CUtensorMap& map_sl,
+                                          const Params& P) {
+    constexpr int SLOT = PAIR ? SLOT_BYTES / 2 : SLOT_BYTES;       // V: hi | lo halves of the slot
+    constexpr int PANEL = PAIR ? PANEL_BYTES / 2 : PANEL_BYTES;    // signal: 4 panels (hi 0, hi 1, lo 0, lo 1)
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char* u_region = smem;                                   // kblocks x [A hi 16 KB | A lo 16 KB]
     unsigned char* ring = u_region + P.kblocks * 2 * A_TILE_BYTES;    // stages x 32 KB
-    float* vline = reinterpret_cast<float*>(ring + P.stages * SLOT_BYTES);    // EPI_WARPS x 2 x 32: per-warp |v|^2 lines
+    float* vline = reinterpret_cast<float*>(ring + P.stages * SLOT);    // EPI_WARPS x 2 x 32: per-warp |v|^2 lines
     float* refbuf = vline + EPI_WARPS * 2 * 32;                                // NG x TM: per-group reference exponents
     float* ksbuf = refbuf + NG * TM;                                           // NG x TM: per-group sums of weights
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ksbuf + NG * TM);
@@ -135,20 +142,43 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
     int* s_flag = reinterpret_cast<int*>(tmem_base_smem + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int cta = blockIdx.x;
+    const uint32_t rank = PAIR ? pair::cluster_ctarank() : 0;   // 0 = leader (issues the MMAs)
+    const int cta = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);   // unit of the wave plan
     const int ST = P.stages;
+    constexpr int NCTA = PAIR ? 2 : 1;
 
     if (tid == 0) {
-        for (int s = 0; s < ST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&p_ready[a], EPI_WARPS); mbar_init(&pv_done[a], 1); }
-        mbar_init(u_full, 1);
+        for (int s = 0; s < ST; ++s) { mbar_init(&full_bar[s], NCTA); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&p_ready[a], NCTA * EPI_WARPS); mbar_init(&pv_done[a], 1); }
+        mbar_init(u_full, NCTA);
         mbar_init(u_free, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
+    if (warp == 1) {
+        if constexpr (PAIR) pair::tmem_alloc2(tmem_base_smem, TMEM_COLS);
+        else tmem_alloc(tmem_base_smem, TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) pair::cluster_sync_all();   // the peer's barriers exist before anything arrives on them
     tc_fence_after();
+    // barrier-side helpers: where TMA bytes are counted / how the producers arm a full barrier
+    auto arm_full = [&](uint64_t* bar, uint32_t bytes_per_cta) {   // elected lane only
+        if constexpr (PAIR) {
+            if (rank == 0) mbar_arrive_expect_tx(bar, 2 * bytes_per_cta);
+            else pair::mbar_arrive_cluster(pair::map_to_cta(bar, 0));
+        } else {
+            mbar_arrive_expect_tx(bar, bytes_per_cta);
+        }
+    };
+    auto load2d = [&](void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+        if constexpr (PAIR) pair::tma_load_2d_pair(dst, map, c0, c1, pair::map_to_cta(bar, 0));
+        else tma_load_2d(dst, map, c0, c1, bar);
+    };
+    auto commit = [&](uint64_t* bar) {
+        if constexpr (PAIR) pair::umma2_commit_both(bar);
+        else umma_commit(bar);
+    };
     const uint32_t tmem_base = *tmem_base_smem;
 
     if (warp == 0) {
@@ -156,16 +186,17 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
         // all 32 lanes walk the loop (uniform control flow); one elected lane issues (see elect_one)
         uint32_t it = 0, seg = 0;
         auto emit_signal = [&](int sb) {   // one slot: hi panels 0, 1 | lo panels 0, 1
-            const int row0 = sb * P.ep_rows + P.e0;   // slab sb, signal column e0
+            // slab sb, signal column e0 (CTA pairs: this CTA's half of the pass's signal columns)
+            const int row0 = sb * P.ep_rows + P.e0 + (PAIR ? static_cast<int>(rank) * (P.ebp / 2) : 0);
             const int slot = it % ST;
             mbar_wait(&empty_bar[slot], ((it / ST) & 1) ^ 1);
-            unsigned char* dst = ring + slot * SLOT_BYTES;
+            unsigned char* dst = ring + slot * SLOT;
             if (elect_one()) {
-                mbar_arrive_expect_tx(&full_bar[slot], 4 * PANEL_BYTES);
-                tma_load_2d(dst + 0 * PANEL_BYTES, &map_sh, 0, row0, &full_bar[slot]);
-                tma_load_2d(dst + 1 * PANEL_BYTES, &map_sh, 64, row0, &full_bar[slot]);
-                tma_load_2d(dst + 2 * PANEL_BYTES, &map_sl, 0, row0, &full_bar[slot]);
-                tma_load_2d(dst + 3 * PANEL_BYTES, &map_sl, 64, row0, &full_bar[slot]);
+                arm_full(&full_bar[slot], PAIR ? 4u * (P.ebp / 2) * 128u : 4u * PANEL_BYTES);
+                load2d(dst + 0 * PANEL, &map_sh, 0, row0, &full_bar[slot]);
+                load2d(dst + 1 * PANEL, &map_sh, 64, row0, &full_bar[slot]);
+                load2d(dst + 2 * PANEL, &map_sl, 0, row0, &full_bar[slot]);
+                load2d(dst + 3 * PANEL, &map_sl, 64, row0, &full_bar[slot]);
             }
             __syncwarp();
             ++it;
@@ -176,11 +207,12 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
             if (!wave_work(P, w, cta, ww)) continue;
             // new row tile: (re)load the resident u tile once the last S of the previous tile has read it
             mbar_wait(u_free, (seg & 1) ^ 1);
+            const int my_row0 = (PAIR ? ww.tile * 2 + static_cast<int>(rank) : ww.tile) * TM;
             if (elect_one()) {
-                mbar_arrive_expect_tx(u_full, P.kblocks * 2 * A_TILE_BYTES);
+                arm_full(u_full, P.kblocks * 2 * A_TILE_BYTES);
                 for (int kb = 0; kb < P.kblocks; ++kb) {
-                    tma_load_2d(u_region + (kb * 2 + 0) * A_TILE_BYTES, &map_ah, kb * 64, ww.tile * TM, u_full);
-                    tma_load_2d(u_region + (kb * 2 + 1) * A_TILE_BYTES, &map_al, kb * 64, ww.tile * TM, u_full);
+                    load2d(u_region + (kb * 2 + 0) * A_TILE_BYTES, &map_ah, kb * 64, my_row0, u_full);
+                    load2d(u_region + (kb * 2 + 1) * A_TILE_BYTES, &map_al, kb * 64, my_row0, u_full);
                 }
             }
             __syncwarp();
@@ -189,11 +221,12 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                 for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
                     const int slot = it % ST;
                     mbar_wait(&empty_bar[slot], ((it / ST) & 1) ^ 1);
-                    unsigned char* dst = ring + slot * SLOT_BYTES;
+                    unsigned char* dst = ring + slot * SLOT;
+                    const int src0 = sb * TNS + (PAIR ? static_cast<int>(rank) * (TNS / 2) : 0);   // pairs: this CTA's 64 sources
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(&full_bar[slot], 2 * A_TILE_BYTES);
-                        tma_load_2d(dst, &map_bh, kb * 64, sb * TNS, &full_bar[slot]);
-                        tma_load_2d(dst + A_TILE_BYTES, &map_bl, kb * 64, sb * TNS, &full_bar[slot]);
+                        arm_full(&full_bar[slot], SLOT);
+                        load2d(dst, &map_bh, kb * 64, src0, &full_bar[slot]);
+                        load2d(dst + SLOT / 2, &map_bl, kb * 64, src0, &full_bar[slot]);
                     }
                     __syncwarp();
                 }
@@ -202,13 +235,23 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
             }
         }
         if (prev >= 0) emit_signal(prev);
-    } else if (warp == 1) {
-        // ------------------------------------- MMA issuer -------------------------------------
+    } else if (warp == 1 && rank == 0) {
+        // ------------------------------------- MMA issuer (pairs: the leader CTA's) -------------------------------------
         // All 32 lanes walk the loop and wait on the barriers; one elected lane issues (see elect_one).
         // Order: S(0), S(1), PV(0), S(2), PV(1), ...
         uint32_t it = 0, n = 0, seg = 0;
         const uint32_t d_o = tmem_base + COL_O;
-        const uint32_t idesc_s = idesc_f16(TNS), idesc_o = idesc_f16(P.ebp);
+        constexpr uint32_t m_bits = PAIR ? (static_cast<uint32_t>(256 >> 4) << 24) : (static_cast<uint32_t>(TM >> 4) << 24);
+        const uint32_t idesc_s = (1u << 4) | (static_cast<uint32_t>(TNS >> 3) << 17) | m_bits;
+        const uint32_t idesc_o = (1u << 4) | (static_cast<uint32_t>(P.ebp >> 3) << 17) | m_bits;
+        auto mma_ss = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+            if constexpr (PAIR) pair::umma2_f16(d, a, b, idesc, acc);
+            else umma_f16_ss(d, a, b, idesc, acc);
+        };
+        auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+            if constexpr (PAIR) pair::umma2_f16_ts(d, a, b, idesc, acc);
+            else umma_f16_ts(d, a, b, idesc, acc);
+        };
 #ifdef KMB_PV16_TIMING
         long long macc[6] = {0, 0, 0, 0, 0, 0}, mprev = clock64();
 #define KMB_M(i) do { const long long t_ = clock64(); macc[i] += t_ - mprev; mprev = t_; } while (0)
@@ -225,22 +268,22 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
             ++it;
             tc_fence_after();
             KMB_M(2);
-            const unsigned char* sg = ring + slot * SLOT_BYTES;
+            const unsigned char* sg = ring + slot * SLOT;
             const uint32_t p_base = tmem_base + COL_S + a * TNS;
             if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < TNS / 16; ++k) {   // 16 sources per instruction; column group g = k / 2
                     const int g = k >> 1, panel = k >> 2, koff = (k & 3) * 32;
-                    const uint64_t bh = umma_desc_sw128(sg + panel * PANEL_BYTES, koff);
-                    const uint64_t bl = umma_desc_sw128(sg + (2 + panel) * PANEL_BYTES, koff);
+                    const uint64_t bh = umma_desc_sw128(sg + panel * PANEL, koff);
+                    const uint64_t bl = umma_desc_sw128(sg + (2 + panel) * PANEL, koff);
                     const uint32_t a_hi = p_base + g * CPT + (k & 1) * 8, a_lo = a_hi + CPT / 2;
                     const uint32_t d_g = d_o + g * MAX_EB;
-                    umma_f16_ts(d_g, a_lo, bh, idesc_o, !(first_of_tile && (k & 1) == 0));
-                    umma_f16_ts(d_g, a_hi, bl, idesc_o, 1);
-                    umma_f16_ts(d_g, a_hi, bh, idesc_o, 1);
+                    mma_ts(d_g, a_lo, bh, idesc_o, !(first_of_tile && (k & 1) == 0));
+                    mma_ts(d_g, a_hi, bl, idesc_o, 1);
+                    mma_ts(d_g, a_hi, bh, idesc_o, 1);
                 }
-                umma_commit(&empty_bar[slot]);
-                umma_commit(&pv_done[a]);
+                commit(&empty_bar[slot]);
+                commit(&pv_done[a]);
             }
             __syncwarp();
         };
@@ -260,7 +303,7 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                     mbar_wait(&full_bar[slot], (it / ST) & 1);
                     tc_fence_after();
                     KMB_M(4);
-                    const unsigned char* bt = ring + slot * SLOT_BYTES;
+                    const unsigned char* bt = ring + slot * SLOT;
                     const unsigned char* at = u_region + kb * 2 * A_TILE_BYTES;
                     const int ksteps = (kb == P.kblocks - 1) ? P.ksteps_last : 4;
                     if (elect_one()) {
@@ -270,20 +313,20 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                                 const uint64_t ah = umma_desc_sw128(at, k * 32);
                                 const uint64_t al = umma_desc_sw128(at + A_TILE_BYTES, k * 32);
                                 const uint64_t bh = umma_desc_sw128(bt, k * 32);
-                                const uint64_t bl = umma_desc_sw128(bt + A_TILE_BYTES, k * 32);
-                                umma_f16_ss(d_s, al, bh, idesc_s, (kb | k) != 0);
-                                umma_f16_ss(d_s, ah, bl, idesc_s, 1);
-                                umma_f16_ss(d_s, ah, bh, idesc_s, 1);
+                                const uint64_t bl = umma_desc_sw128(bt + SLOT / 2, k * 32);
+                                mma_ss(d_s, al, bh, idesc_s, (kb | k) != 0);
+                                mma_ss(d_s, ah, bl, idesc_s, 1);
+                                mma_ss(d_s, ah, bh, idesc_s, 1);
                             }
                         }
-                        umma_commit(&empty_bar[slot]);
+                        commit(&empty_bar[slot]);
                     }
                     __syncwarp();
                 }
                 const bool last_of_tile = (sb + 1 == ww.sb_hi);
                 if (elect_one()) {
-                    umma_commit(&acc_full[a]);
-                    if (last_of_tile) umma_commit(u_free);   // last S of this row tile
+                    commit(&acc_full[a]);
+                    if (last_of_tile) commit(u_free);   // last S of this row tile
                 }
                 __syncwarp();
                 if (pv_pending) issue_pv(n - 1, prev_first);
@@ -297,7 +340,7 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
             for (int i = 0; i < 5; ++i) P.out[8 + i] = static_cast<float>(macc[i]) / n;
         }
 #endif
-    } else {
+    } else if (warp >= 2) {
         // -------------------------------------- epilogue --------------------------------------
         const int et = tid - 64;
         const int lane_group = warp & 3;             // TMEM lane quarter this warp may touch
@@ -327,7 +370,7 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
         WaveWork ww;
         for (int w = 0; w < P.W; ++w) {
             if (!wave_work(P, w, cta, ww)) continue;
-            const int tile = ww.tile;
+            const int tile = PAIR ? ww.tile * 2 + static_cast<int>(rank) : ww.tile;
             const long long row = static_cast<long long>(tile) * TM + row_in_tile;
             const bool row_ok = row < P.N;
             const float un = row_ok ? __ldg(P.un + row) : 0.f;
@@ -433,7 +476,10 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&p_ready[a]);
+                if (lane == 0) {
+                    if (PAIR && rank != 0) pair::mbar_arrive_cluster(pair::map_to_cta(&p_ready[a], 0));
+                    else mbar_arrive(&p_ready[a]);
+                }
                 KMB_T(6);
             }
 #ifdef KMB_PV16_TIMING
@@ -458,8 +504,10 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
             }
             wait_pv(n - 1);   // the tile's last PV
             const bool complete = (ww.Cw == 1);
-            const size_t slot0 = static_cast<size_t>(w) * P.slots_per_wave + static_cast<size_t>(ww.tile_in_wave) * ww.Cw;
-            float* mine = P.partial + (slot0 + ww.c) * (TM * PS);
+            const bool ghost = tile >= P.n_tiles;   // pairs: an odd number of row tiles leaves the last peer without one
+            // partial records of one wave: [row tile or pair in wave][range c]([rank])
+            const size_t slot0 = static_cast<size_t>(w) * P.slots_per_wave + static_cast<size_t>(ww.tile_in_wave) * ww.Cw * NCTA + rank;
+            float* mine = P.partial + (slot0 + static_cast<size_t>(ww.c) * NCTA) * (TM * PS);
             // plain product: undo the reference exponent (2^ref may underflow exactly where FP32 K b would)
             const float row_scale = NORM ? 1.f / ktot : ((rmax == -INFINITY) ? 0.f : ex2_approx(rmax));
             for (int c0 = cg * 16; c0 < P.ebp; c0 += NG * 16) {   // this thread merges 16-column chunks c0 of all four O_g
@@ -473,6 +521,7 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
 #pragma unroll
                     for (int c = 0; c < 16; ++c) o[c] = fmaf(wg[g], og[c], o[c]);
                 }
+                if (ghost) continue;
                 if (complete) {
                     if (row_ok) {
 #pragma unroll
@@ -485,7 +534,7 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                 }
             }
             tc_fence_before();
-            if (!complete) {
+            if (!complete && !ghost) {
                 if (cg == 0) {
                     mine[MAX_EB * TM + row_in_tile] = ktot;
                     mine[(MAX_EB + 1) * TM + row_in_tile] = rmax;
@@ -505,11 +554,11 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
                     __threadfence();
                     float mx = -INFINITY;
                     for (int c = 0; c < ww.Cw; ++c)
-                        mx = fmaxf(mx, __ldcg(P.partial + (slot0 + c) * (TM * PS) + (MAX_EB + 1) * TM + row_in_tile));
+                        mx = fmaxf(mx, __ldcg(P.partial + (slot0 + static_cast<size_t>(c) * NCTA) * (TM * PS) + (MAX_EB + 1) * TM + row_in_tile));
                     for (int e = cg; e < P.eb; e += NG) {   // the groups share the signal columns of the row
                         float sum = 0.f, l = 0.f;
                         for (int c = 0; c < ww.Cw; ++c) {
-                            const float* ps = P.partial + (slot0 + c) * (TM * PS);
+                            const float* ps = P.partial + (slot0 + static_cast<size_t>(c) * NCTA) * (TM * PS);
                             const float m = __ldcg(ps + (MAX_EB + 1) * TM + row_in_tile);
                             const float wgt = (m == -INFINITY) ? 0.f : ex2_approx(m - mx);
                             sum = fmaf(wgt, __ldcg(ps + e * TM + row_in_tile), sum);
@@ -527,7 +576,28 @@ kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __gri
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) pair::cluster_sync_all();   // neither CTA frees tensor memory (or exits) while the other may signal it
+    if (warp == 1) {
+        if constexpr (PAIR) pair::tmem_dealloc2(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int KID, bool NORM>
+__global__ void __launch_bounds__(THREADS, 1)
+kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                         const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                         const __grid_constant__ CUtensorMap map_sh, const __grid_constant__ CUtensorMap map_sl,
+                         const Params P) {
+    pv16_body<KID, NORM, false>(map_ah, map_al, map_bh, map_bl, map_sh, map_sl, P);
+}
+template <int KID, bool NORM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+kprod_tensor_pv16_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                              const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                              const __grid_constant__ CUtensorMap map_sh, const __grid_constant__ CUtensorMap map_sl,
+                              const Params P) {
+    pv16_body<KID, NORM, true>(map_ah, map_al, map_bh, map_bl, map_sh, map_sl, P);
 }
 
 // ---- signal planes -----------------------------------------------------------------------------------
@@ -585,6 +655,7 @@ namespace {
 size_t align_up_pv16(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Pv16Plan {
+    bool pair;   // CTA pairs (cta_group::2): at least two row tiles
     int Dp, Ep, kblocks, ksteps_last, stages, grid, smem;
     long long n_tiles, nsb, Mp;
     tc::WavePlan waves;
@@ -604,12 +675,24 @@ int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
     KMB_CUDA_CHECK(cudaGetDevice(&dev));
     KMB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     KMB_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    pl->grid = sms;
+    static const bool pair_enabled = [] {   // tuning knob: KMB_TENSOR_PAIR=0 keeps the single-CTA kernel
+        const char* e = getenv("KMB_TENSOR_PAIR");
+        return !(e && e[0] == '0');
+    }();
+    pl->pair = pair_enabled && pl->n_tiles >= 2 && sms >= 2;
+    pl->grid = pl->pair ? sms / 2 * 2 : sms;
+    const int slot = pl->pair ? pv16::SLOT_BYTES / 2 : pv16::SLOT_BYTES;
     const int fixed = 1024 + pl->kblocks * 2 * pv16::A_TILE_BYTES + pv16::EPI_WARPS * 2 * 32 * 4 + 2 * pv16::NG * tc::TM * 4 + 512;
-    pl->stages = std::min(6, (smem_max - fixed) / pv16::SLOT_BYTES);
+    pl->stages = std::min(pl->pair ? 10 : 6, (smem_max - fixed) / slot);
     if (pl->stages < 3) return set_error(KMB_ERR_UNSUPPORTED, "not enough shared memory for D=%d", D);
-    pl->smem = fixed + pl->stages * pv16::SLOT_BYTES;
-    tc::plan_waves(pl->n_tiles, pl->nsb, pl->grid, static_cast<size_t>(tc::TM) * pl->Dp * 4, &pl->waves);
+    pl->smem = fixed + pl->stages * slot;
+    if (pl->pair) {   // the wave plan counts pairs of row tiles and clusters
+        tc::plan_waves((pl->n_tiles + 1) / 2, pl->nsb, pl->grid / 2, static_cast<size_t>(tc::TM) * pl->Dp * 8, &pl->waves);
+        pl->waves.slots_per_wave *= 2;
+        pl->waves.partial_slots *= 2;
+    } else {
+        tc::plan_waves(pl->n_tiles, pl->nsb, pl->grid, static_cast<size_t>(tc::TM) * pl->Dp * 4, &pl->waves);
+    }
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += align_up_pv16(bytes, 256); return at; };
     pl->off_center = take(sizeof(float) * pl->Dp);
@@ -633,14 +716,24 @@ int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
 }
 
 template <int KID, bool NORM>
-int launch_pv16(const CUtensorMap* m, const pv16::Params& P, int grid, int smem, cudaStream_t stream) {
-    auto fn = pv16::kprod_tensor_pv16_kernel<KID, NORM>;
-    static int attr_smem = 0;
-    if (attr_smem < smem) {
-        KMB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
+int launch_pv16(const CUtensorMap* m, const pv16::Params& P, int grid, int smem, bool pair, cudaStream_t stream) {
+    if (pair) {
+        auto fn = pv16::kprod_tensor_pv16_pair_kernel<KID, NORM>;
+        static int attr_smem = 0;
+        if (attr_smem < smem) {
+            KMB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_smem = smem;
+        }
+        fn<<<grid, pv16::THREADS, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
+    } else {
+        auto fn = pv16::kprod_tensor_pv16_kernel<KID, NORM>;
+        static int attr_smem = 0;
+        if (attr_smem < smem) {
+            KMB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_smem = smem;
+        }
+        fn<<<grid, pv16::THREADS, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
     }
-    fn<<<grid, pv16::THREADS, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
     KMB_CUDA_CHECK(cudaGetLastError());
     return KMB_OK;
 }
@@ -695,10 +788,9 @@ int tensor_pv16_product(const float* x, const float* y, const float* b, float* o
     CUtensorMap maps[6];
     if (int rc = tc::make_tensor_map_f16(&maps[0], uh, N, pl.Dp, tc::TM)) return rc;
     if (int rc = tc::make_tensor_map_f16(&maps[1], ul, N, pl.Dp, tc::TM)) return rc;
-    if (int rc = tc::make_tensor_map_f16(&maps[2], vh, M, pl.Dp, pv16::TNS)) return rc;
-    if (int rc = tc::make_tensor_map_f16(&maps[3], vl, M, pl.Dp, pv16::TNS)) return rc;
-    if (int rc = tc::make_tensor_map_f16(&maps[4], sh, pl.nsb * pl.Ep, pv16::TNS, pv16::MAX_EB)) return rc;
-    if (int rc = tc::make_tensor_map_f16(&maps[5], sl, pl.nsb * pl.Ep, pv16::TNS, pv16::MAX_EB)) return rc;
+    // CTA pairs: each CTA loads 64 of a block's 128 sources and half of the pass's signal columns
+    if (int rc = tc::make_tensor_map_f16(&maps[2], vh, M, pl.Dp, pl.pair ? pv16::TNS / 2 : pv16::TNS)) return rc;
+    if (int rc = tc::make_tensor_map_f16(&maps[3], vl, M, pl.Dp, pl.pair ? pv16::TNS / 2 : pv16::TNS)) return rc;
 
     const int n_passes = pl.Ep / pv16::MAX_EB;
     for (int pass = 0; pass < n_passes; ++pass) {
@@ -716,6 +808,11 @@ int tensor_pv16_product(const float* x, const float* y, const float* b, float* o
         P.e0 = pass * pv16::MAX_EB;
         P.eb = std::min(pv16::MAX_EB, E - P.e0);
         P.ebp = (P.eb + 31) / 32 * 32;
+        {
+            const int box_rows = pl.pair ? P.ebp / 2 : pv16::MAX_EB;
+            if (int rc = tc::make_tensor_map_f16(&maps[4], sh, pl.nsb * pl.Ep, pv16::TNS, box_rows)) return rc;
+            if (int rc = tc::make_tensor_map_f16(&maps[5], sl, pl.nsb * pl.Ep, pv16::TNS, box_rows)) return rc;
+        }
         P.n_tiles = static_cast<int>(pl.n_tiles);
         P.nsb = static_cast<int>(pl.nsb);
         P.kblocks = pl.kblocks;
@@ -731,10 +828,10 @@ int tensor_pv16_product(const float* x, const float* y, const float* b, float* o
         if (ev0 && pass == n_passes - 1) KMB_CUDA_CHECK(cudaEventRecord(ev0, stream));
         int rc;
         switch (kid * 2 + (norm ? 1 : 0)) {
-            case 0: rc = launch_pv16<KMB_KERNEL_GAUSSIAN, false>(maps, P, pl.grid, pl.smem, stream); break;
-            case 1: rc = launch_pv16<KMB_KERNEL_GAUSSIAN, true>(maps, P, pl.grid, pl.smem, stream); break;
-            case 2: rc = launch_pv16<KMB_KERNEL_ABSOLUTE_EXPONENTIAL, false>(maps, P, pl.grid, pl.smem, stream); break;
-            default: rc = launch_pv16<KMB_KERNEL_ABSOLUTE_EXPONENTIAL, true>(maps, P, pl.grid, pl.smem, stream); break;
+            case 0: rc = launch_pv16<KMB_KERNEL_GAUSSIAN, false>(maps, P, pl.grid, pl.smem, pl.pair, stream); break;
+            case 1: rc = launch_pv16<KMB_KERNEL_GAUSSIAN, true>(maps, P, pl.grid, pl.smem, pl.pair, stream); break;
+            case 2: rc = launch_pv16<KMB_KERNEL_ABSOLUTE_EXPONENTIAL, false>(maps, P, pl.grid, pl.smem, pl.pair, stream); break;
+            default: rc = launch_pv16<KMB_KERNEL_ABSOLUTE_EXPONENTIAL, true>(maps, P, pl.grid, pl.smem, pl.pair, stream); break;
         }
         if (rc) return rc;
         if (ev1 && pass == n_passes - 1) KMB_CUDA_CHECK(cudaEventRecord(ev1, stream));

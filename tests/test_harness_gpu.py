@@ -54,8 +54,17 @@ def test_product_through_runner(tmp_path, monkeypatch):
 def test_solver_through_runner(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     rows = _run("solver-ucubelam1-D3-E1-M2000-N2000-gaussian", "solver", 3)
-    assert len(rows) == 2  # two query-arg groups (rtol 1e-4, 1e-6)
+    assert len(rows) == 4  # (Nystrom-preconditioned, plain CG) x two query-arg groups (rtol 1e-4, 1e-6)
     best = min(m["rel-l2"] for m in rows)
     assert best <= 1e-4, rows
     assert all(m["props"]["cg_converged"] for m in rows)
-    assert len({m["props"]["name"] for m in rows}) == 2  # the name carries the swept rtol
+    assert len({m["props"]["name"] for m in rows}) == 4  # the name carries the preconditioner and the swept rtol
+    for m in rows:
+        pc = m["props"]["preconditioner"]
+        assert pc.startswith("nystrom") == ("nystrom" in m["props"]["name"]), m["props"]
+        if "rtol=1e-06" in m["props"]["name"]:
+            assert m["rel-l2"] <= 1e-4, m
+    its = {m["props"]["name"]: m["props"]["cg_iterations"] for m in rows}
+    pcg = min(v for k, v in its.items() if "nystrom" in k and "1e-06" in k)
+    cg = min(v for k, v in its.items() if "nystrom" not in k and "1e-06" in k)
+    assert pcg * 4 <= cg, its
