@@ -102,29 +102,77 @@ def measured_traffic(n, world, sym):
 # ------------------------------------------------------------------------------------ CPU arm
 
 
-def cpu_reference_sample(ds, rows, precision="float32", fast_sqdists=True):
-    """The reference algorithm (bruteforce.py:25-58 + :153) on `rows` target rows x all sources,
-    in its fastest configuration (float32, BLAS squared distances).  Returns seconds."""
-    from oracle import bruteforce_oracle as orc
+_REF_CLASS = "unset"
 
-    t0 = time.perf_counter()
-    orc.kernel_product(ds.kernel, ds.source_points, None, ds.source_signal, precision=precision,
-                       fast_sqdists=fast_sqdists, rows=rows, row_block=64)
-    return time.perf_counter() - t0
+
+def reference_class():
+    """The reference's own BruteForceProductBLAS (bruteforce.py:61-153), imported from the copy of the reference tree
+    that __graft_entry__.build() stages in the git-ignored baseline/_ref (it travels to the GPU box with the
+    snapshot; /root/reference is never read here).  None when the tree is not there: the NumPy port is timed instead."""
+    global _REF_CLASS
+    if _REF_CLASS == "unset":
+        try:
+            from kernel_matrix_benchmarks_b200.harness import bootstrap
+
+            if bootstrap.find_reference() is None:
+                raise ImportError("reference tree not staged")
+            bootstrap.activate()
+            from kernel_matrix_benchmarks.algorithms.bruteforce import BruteForceProductBLAS
+
+            _REF_CLASS = BruteForceProductBLAS
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] reference class unavailable ({e}); timing the NumPy port", file=sys.stderr)
+            _REF_CLASS = None
+    return _REF_CLASS
+
+
+def cpu_reference_sample(ds, rows, precision="float32", fast_sqdists=True, row_block=500):
+    """The reference algorithm (bruteforce.py:25-58 + :153) on `rows` target rows x all sources, in its fastest
+    configuration (float32, BLAS squared distances).  With the reference tree staged: the reference's own class,
+    fed blocks of `row_block` target rows (a 500 x 10^6 float32 kernel block is 2 GB), timing fit() + query() as its
+    harness does (runner.py:97-143); otherwise the NumPy port in oracle/.  Returns (seconds, kind)."""
+    cls = reference_class()
+    if cls is None:
+        from oracle import bruteforce_oracle as orc
+
+        t0 = time.perf_counter()
+        orc.kernel_product(ds.kernel, ds.source_points, None, ds.source_signal, precision=precision,
+                           fast_sqdists=fast_sqdists, rows=rows, row_block=64)
+        return time.perf_counter() - t0, "port"
+    secs = 0.0
+    for lo in range(0, len(rows), row_block):
+        algo = cls(kernel=ds.kernel, dimension=ds.D, normalize_rows=False, precision=precision, fast_sqdists=fast_sqdists)
+        algo.prepare_data(source_points=ds.source_points, target_points=ds.source_points[rows[lo:lo + row_block]],
+                          same_points=False, density_estimation=False)
+        algo.prepare_query(source_signal=ds.source_signal)
+        t0 = time.perf_counter()
+        algo.fit()
+        algo.query()
+        secs += time.perf_counter() - t0
+        algo.get_result()
+        del algo
+    return secs, "reference"
+
+
+def _cpu_sample_text(kind):
+    if kind == "reference":
+        return ("the reference's own BruteForceProductBLAS (baseline/_ref, float32, fast_sqdists=True), fit() + query() on blocks "
+                "of 500 target rows: OpenBLAS GEMM on all cores, exp/broadcast ufuncs single-threaded")
+    return ("NumPy port of bruteforce.py float32 fast_sqdists=True: OpenBLAS GEMM on all cores, exp/broadcast ufuncs "
+            "single-threaded")
 
 
 def cpu_baseline(ds, n_rows):
     rows = np.random.RandomState(1).choice(ds.N, n_rows, replace=False)
     rows.sort()
-    secs = cpu_reference_sample(ds, rows)
+    secs, kind = cpu_reference_sample(ds, rows)
     pairs = float(n_rows) * ds.M
     return {
         "value": pairs / secs / 1e9,
         "unit": UNIT,
         "cores": os.cpu_count(),
-        "kind": "port",
-        "sample": f"{n_rows} target rows x {ds.M} sources ({pairs:.2e} pairs, {secs:.1f} s), NumPy port of "
-                  f"bruteforce.py float32 fast_sqdists=True: OpenBLAS GEMM on all cores, exp/broadcast ufuncs single-threaded",
+        "kind": kind,
+        "sample": f"{n_rows} target rows x {ds.M} sources ({pairs:.2e} pairs, {secs:.1f} s), " + _cpu_sample_text(kind),
     }
 
 
@@ -147,18 +195,18 @@ def run_reference_arm(args):
     rows = np.sort(np.random.RandomState(1).choice(ds.N, n_rows, replace=False))
     for _ in range(args.warmup):
         cpu_reference_sample(ds, rows[: max(8, n_rows // 16)])
-    secs = [cpu_reference_sample(ds, rows) for _ in range(args.steps)]
+    runs = [cpu_reference_sample(ds, rows) for _ in range(args.steps)]
+    secs, kind = [r[0] for r in runs], runs[0][1]
     ms = 1e3 * sum(secs) / len(secs)
     pairs = float(n_rows) * ds.M
     value = pairs / (ms * 1e-3) / 1e9
-    sample = (f"each step = {n_rows} target rows x {ds.M} sources ({pairs:.2e} pairs) of the C2 workload; "
-              "NumPy port of bruteforce.py (float32, fast_sqdists=True), OpenBLAS on all cores")
+    sample = (f"each step = {n_rows} target rows x {ds.M} sources ({pairs:.2e} pairs) of the C2 workload; " + _cpu_sample_text(kind))
     print(json.dumps({
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args.n, args.gpus, args.path),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
