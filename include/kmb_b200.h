@@ -148,6 +148,13 @@ int kmb_product_f64(const double* x, const double* y, const double* b, double* o
 int kmb_kernel_block_f64(const double* x, const double* y, double* out, int64_t n, int64_t m, int D, int kernel_id,
                          void* stream);
 
+/* Diagnostics (host logic only, no GPU needed): the wave schedule the tensor-path kernels would use for n_tiles row
+ * tiles x n_source_blocks source blocks on `grid` CTAs (CTA pairs: pairs of row tiles on grid / 2 clusters).
+ * out7 = {R, C, W, R_last, C_last, slots_per_wave, partial_slots}: W - 1 waves of R row tiles x C CTAs per tile and a
+ * last wave of R_last x C_last; CTA b of a wave works on row tile b / C and on source blocks
+ * [n_source_blocks (b % C) / C, n_source_blocks (b % C + 1) / C). */
+int kmb_debug_plan_waves(int64_t n_tiles, int64_t n_source_blocks, int grid, size_t row_tile_bytes, int64_t* out7);
+
 /* Number of this library's kernels the last kmb_product_f32 / kmb_cg_* call on this
  * thread launched (bench.py's gpu_launches). */
 int kmb_last_launch_count(void);

@@ -422,6 +422,14 @@ int kmb_product_f64(const double* x, const double* y, const double* b, double* o
     return product_f64(x, y, b, out, N, M, D, E, kernel_id, flags, row_offset, static_cast<cudaStream_t>(stream_));
 }
 
+int kmb_debug_plan_waves(int64_t n_tiles, int64_t n_source_blocks, int grid, size_t row_tile_bytes, int64_t* out7) {
+    if (!out7 || n_tiles < 1 || n_source_blocks < 1 || grid < 1) return set_error(KMB_ERR_INVALID, "bad arguments");
+    long long o[7];
+    tensor_plan_waves_debug(n_tiles, n_source_blocks, grid, row_tile_bytes, o);
+    for (int i = 0; i < 7; ++i) out7[i] = o[i];
+    return KMB_OK;
+}
+
 int kmb_kernel_block_f64(const double* x, const double* y, double* out, int64_t n, int64_t m, int D, int kernel_id, void* stream_) {
     g_launches = 0;
     if (n < 0 || m < 1 || D < 1) return set_error(KMB_ERR_INVALID, "bad sizes n=%lld m=%lld D=%d", (long long)n, (long long)m, D);

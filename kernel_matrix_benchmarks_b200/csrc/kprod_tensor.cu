@@ -916,6 +916,7 @@ int tensor_prepass_f16(const float* x, const float* y, int64_t N, int64_t M, int
 void plan_waves(long long n_tiles, long long nsb, int grid, size_t row_tile_bytes, WavePlan* wp) {
     const size_t l2_budget = 48u << 20;
     long long rmax = static_cast<long long>(l2_budget / std::max<size_t>(row_tile_bytes, 1));
+    rmax = std::max<long long>(rmax, (grid + nsb - 1) / nsb);   // few source blocks: enough row tiles to keep every CTA busy
     rmax = std::max<long long>(1, std::min<long long>({rmax, static_cast<long long>(grid), n_tiles}));
     long long best_steps = -1;
     for (long long R = 1; R <= rmax; ++R) {
@@ -1071,6 +1072,13 @@ int launch_any(int kid, bool norm, int ep, const CUtensorMap* maps, const tc::Pa
 }
 
 }  // namespace
+
+void tensor_plan_waves_debug(long long n_tiles, long long nsb, int grid, size_t row_tile_bytes, long long out[7]) {
+    tc::WavePlan wp{};
+    tc::plan_waves(n_tiles, nsb, grid, row_tile_bytes, &wp);
+    out[0] = wp.R; out[1] = wp.C; out[2] = wp.W; out[3] = wp.R_last; out[4] = wp.C_last; out[5] = wp.slots_per_wave;
+    out[6] = wp.partial_slots;
+}
 
 int tensor_workspace_bytes(int64_t N, int64_t M, int D, int E, int kid, int flags, int elt, size_t* bytes) {
     (void)flags;

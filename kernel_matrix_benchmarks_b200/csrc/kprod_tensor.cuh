@@ -16,4 +16,8 @@ int tensor_product(const float* x, const float* y, const float* b, float* out, i
                    int kid, int flags, int elt, int64_t row_offset, void* workspace, size_t workspace_bytes,
                    cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1);
 
+// The wave schedule of the tensor kernels for a (row tiles x source blocks) problem on `grid` CTAs (or clusters):
+// out = {R, C, W, R_last, C_last, slots_per_wave, partial_slots}.  Host logic only (tests/test_abi_cpu.py).
+void tensor_plan_waves_debug(long long n_tiles, long long nsb, int grid, size_t row_tile_bytes, long long out[7]);
+
 }  // namespace kmb

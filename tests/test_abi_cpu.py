@@ -109,3 +109,56 @@ def test_datasets_follow_reference_generator():
     c4 = datasets.config_c4(n=64)
     assert c4.normalize_rows and c4.E == 64 and c4.D == 64 and not c4.same_points
     assert abs(datasets.scaled_radius(784) - (3 / 784) ** 0.5) < 1e-15
+
+
+def _wave_work(plan, w, unit):
+    """What the kernels' wave_work() gives unit (CTA or cluster) `unit` in wave w: (row tile, source blocks) or None."""
+    R, C, W, R_last, C_last = plan[:5]
+    Rw, Cw = (R_last, C_last) if w == W - 1 else (R, C)
+    if unit >= Rw * Cw:
+        return None
+    t, c = divmod(unit, Cw)
+    return w * R + t, range(plan_nsb * c // Cw, plan_nsb * (c + 1) // Cw), Cw
+
+
+@pytest.mark.parametrize("n_tiles, nsb, grid, tile_bytes", [
+    (79, 235, 148, 128 * 784 * 4), (40, 235, 74, 2 * 128 * 784 * 4),      # C3: single CTAs, CTA pairs
+    (2048, 2048, 148, 128 * 64 * 4), (1024, 2048, 74, 128 * 64 * 8),      # C4
+    (1, 1, 148, 1 << 20), (1, 500, 148, 1 << 20), (500, 1, 148, 1 << 12), (149, 3, 148, 1 << 16), (7813, 4, 148, 128 * 800 * 8),
+    (3, 7, 2, 1 << 10), (150, 2, 74, 1 << 30),
+])
+def test_wave_schedule_covers_every_unit_once(n_tiles, nsb, grid, tile_bytes):
+    """kmb_debug_plan_waves (the planner of the tensor kernels) + the kernels' wave_work rule: every (row tile, source
+    block) is evaluated exactly once, a wave never uses more than `grid` units, row tiles split over C > 1 units have
+    a partial record each, and the number of steps stays within a few percent of the ideal."""
+    import ctypes
+
+    from kernel_matrix_benchmarks_b200 import _lib
+
+    global plan_nsb
+    plan_nsb = nsb
+    out = (ctypes.c_int64 * 7)()
+    assert _lib.load().kmb_debug_plan_waves(n_tiles, nsb, grid, tile_bytes, out) == 0
+    plan = list(out)
+    R, C, W, R_last, C_last, slots_per_wave, partial_slots = plan
+    assert 1 <= R and R * C <= grid and R_last * C_last <= grid and (W - 1) * R + R_last == n_tiles
+    # the wave's row tiles stay L2-resident, unless there are too few source blocks to keep every unit busy otherwise
+    assert R * tile_bytes <= max(48 << 20, tile_bytes) or R <= -(-grid // nsb)
+    seen = np.zeros((n_tiles, nsb), dtype=np.int32)
+    steps = 0
+    for w in range(W):
+        longest = 0
+        for unit in range(grid):
+            ww = _wave_work(plan, w, unit)
+            if ww is None:
+                continue
+            tile, blocks, Cw = ww
+            assert 0 <= tile < n_tiles
+            seen[tile, blocks.start:blocks.stop] += 1
+            longest = max(longest, len(blocks))
+            if Cw > 1:   # this unit leaves a partial record
+                assert w * slots_per_wave + unit < partial_slots
+        steps += longest
+    assert (seen == 1).all()
+    ideal = n_tiles * nsb / grid
+    assert steps <= max(1.12 * ideal + 1, ideal + 2), (steps, ideal, plan)
