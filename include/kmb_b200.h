@@ -51,7 +51,8 @@ enum {
 /* query modes: BruteForceProductBLAS.query, bruteforce.py:130-153 */
 enum {
     KMB_FLAG_NORMALIZE_ROWS = 1, /* attention: (K @ [b,1])[:, :-1] / [:, -1:]     :139-145 */
-    KMB_FLAG_DENSITY = 2         /* b == 1, E == 1: K.sum(-1)                      :150    */
+    KMB_FLAG_DENSITY = 2,        /* b == 1, E == 1: K.sum(-1)                      :150    */
+    KMB_FLAG_PREPARED = 4        /* the points-only work was done by kmb_product_prepare_f32 on this workspace (below) */
 };
 
 /* evaluation paths */
@@ -110,6 +111,17 @@ int kmb_product_workspace_bytes(int64_t n_targets, int64_t n_sources, int D, int
 int kmb_product_f32(const float* x, const float* y, const float* b, float* out, int64_t n_targets,
                     int64_t n_sources, int D, int E, int kernel_id, int flags, int path,
                     int64_t row_offset, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The points-only part of a product: what the reference does in fit() (bruteforce.py:113-120 builds the kernel matrix
+ * from the points; query() only multiplies, :130-153).  For the FP16 tensor path (KMB_PATH_TENSOR_3XF16 / KMB_PATH_AUTO
+ * with D > 16) this is the prepass -- column statistics, centre, power-of-two scale, FP16 hi/lo operand planes, squared
+ * norms -- written to the head of `workspace`, whose layout does not depend on E.  A later kmb_product_f32 with the same
+ * x, y, sizes, kernel and path on the SAME workspace memory may then pass KMB_FLAG_PREPARED and skips it; the caller
+ * must prepare again if the workspace was reallocated (e.g. grown for a wider signal) or the points changed.  Other
+ * paths have nothing worth keeping: the call is a no-op and KMB_FLAG_PREPARED is ignored.  `flags` as for the product
+ * (KMB_FLAG_PREPARED itself is ignored here); workspace_bytes >= kmb_product_workspace_bytes(..., E = 1, ...). */
+int kmb_product_prepare_f32(const float* x, const float* y, int64_t n_targets, int64_t n_sources, int D, int kernel_id,
+                            int flags, int path, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Symmetric Gaussian product for targets == sources (same_points):
  *     out[i] = this part's share of  sum_j exp(-|y_i - y_j|^2) b[j]        (E == 1, D <= 3)

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libkmb_b200.so")
 KMB_OK, KMB_ERR_INVALID, KMB_ERR_UNSUPPORTED, KMB_ERR_WORKSPACE, KMB_ERR_CUDA = range(5)
 
 KERNEL_IDS = {"gaussian": 0, "absolute-exponential": 1, "inverse-distance": 2}
-FLAG_NORMALIZE_ROWS, FLAG_DENSITY = 1, 2
+FLAG_NORMALIZE_ROWS, FLAG_DENSITY, FLAG_PREPARED = 1, 2, 4
 PATH_IDS = {"auto": 0, "direct": 1, "tensor": 5, "tensor_tf32": 2, "tensor_f16": 5, "direct_diff": 3, "direct_sym": 4}
 
 
@@ -44,6 +44,7 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int64,
          c_void_p, c_size_t, c_void_p],
     ),
+    "kmb_product_prepare_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "kmb_product_sym_workspace_bytes": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_size_t)]),
     "kmb_product_sym_f32": (
         c_int,

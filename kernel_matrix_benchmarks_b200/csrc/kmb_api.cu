@@ -173,7 +173,7 @@ __global__ void fill_kernel(float* out, long long n, float v) {
 static int check_product_args(int64_t N, int64_t M, int D, int E, int kid, int flags, int path) {
     if (N < 0 || M < 1 || D < 1 || E < 1) return set_error(KMB_ERR_INVALID, "bad sizes N=%lld M=%lld D=%d E=%d", (long long)N, (long long)M, D, E);
     if (kid < 0 || kid > KMB_KERNEL_INVERSE_DISTANCE) return set_error(KMB_ERR_UNSUPPORTED, "unknown kernel id %d", kid);
-    if (flags & ~(KMB_FLAG_NORMALIZE_ROWS | KMB_FLAG_DENSITY)) return set_error(KMB_ERR_INVALID, "unknown flags 0x%x", flags);
+    if (flags & ~(KMB_FLAG_NORMALIZE_ROWS | KMB_FLAG_DENSITY | KMB_FLAG_PREPARED)) return set_error(KMB_ERR_INVALID, "unknown flags 0x%x", flags);
     if ((flags & KMB_FLAG_DENSITY) && E != 1) return set_error(KMB_ERR_INVALID, "density estimation implies E == 1 (got %d)", E);
     if (path < KMB_PATH_AUTO || path > KMB_PATH_TENSOR_3XF16) return set_error(KMB_ERR_INVALID, "unknown path %d", path);
     if (path == KMB_PATH_DIRECT_SYM) {
@@ -395,7 +395,8 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
             KMB_CUDA_CHECK(cudaEventCreate(&g_ev1));
         }
         const int rc = tensor_product(x, y, density ? nullptr : b, out, N, M, D, E, kernel_id, flags, p == KMB_PATH_TENSOR_3XF16 ? 1 : 0, row_offset, workspace,
-                                      workspace_bytes, stream, g_profile ? g_ev0 : nullptr, g_profile ? g_ev1 : nullptr);
+                                      workspace_bytes, stream, g_profile ? g_ev0 : nullptr, g_profile ? g_ev1 : nullptr,
+                                      (flags & KMB_FLAG_PREPARED) != 0);
         if (rc == KMB_OK && g_profile) g_ev_valid = true;
         return rc;
     }
@@ -410,6 +411,18 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
         return set_error(KMB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total_bytes, workspace_bytes);
     return run_direct(x, y, density ? nullptr : b, out, N, M, D, E, kernel_id, flags, row_offset, pl, nullptr, 0, 1,
                       static_cast<char*>(workspace), stream);
+}
+
+int kmb_product_prepare_f32(const float* x, const float* y, int64_t N, int64_t M, int D, int kernel_id, int flags, int path,
+                            void* workspace, size_t workspace_bytes, void* stream_) {
+    g_launches = 0;
+    if (int rc = check_product_args(N, M, D, 1, kernel_id, flags & ~KMB_FLAG_DENSITY, path)) return rc;
+    if (!x || !y) return set_error(KMB_ERR_INVALID, "x and y must not be NULL");
+    if (N == 0) return KMB_OK;
+    const int p = resolve_path(D, path);
+    if (p != KMB_PATH_TENSOR_3XF16) return KMB_OK;   // nothing worth keeping on the other paths
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) return set_error(KMB_ERR_INVALID, "workspace must be 256-byte aligned");
+    return tensor_prepare(x, y, N, M, D, kernel_id, 1, workspace, workspace_bytes, static_cast<cudaStream_t>(stream_));
 }
 
 int kmb_product_f64(const double* x, const double* y, const double* b, double* out, int64_t N, int64_t M, int D, int E,

@@ -944,6 +944,33 @@ void plan_waves(long long n_tiles, long long nsb, int grid, size_t row_tile_byte
 }  // namespace tc
 
 // ---- host side ---------------------------------------------------------------------------------------
+void f16_points_layout(int64_t N, int64_t M, int D, F16PointsLayout* L) {
+    auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
+    L->Dp = (D + 15) / 16 * 16;
+    L->Mv = (M + 255) / 256 * 256;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += up(bytes, 256); return at; };
+    L->off_center = take(sizeof(float) * L->Dp);
+    L->off_stats = take(sizeof(float) * tc::CENTER_BLOCKS * D * 6);
+    L->off_sscale = take(sizeof(float) * 2);
+    L->off_uh = take(2 * static_cast<size_t>(N) * L->Dp);
+    L->off_ul = take(2 * static_cast<size_t>(N) * L->Dp);
+    L->off_vh = take(2 * static_cast<size_t>(M) * L->Dp);
+    L->off_vl = take(2 * static_cast<size_t>(M) * L->Dp);
+    L->off_un = take(sizeof(float) * N);
+    L->off_vn = take(sizeof(float) * L->Mv);
+    L->end = o;
+}
+
+int f16_points_prepass(const float* x, const float* y, int64_t N, int64_t M, int D, int kid, const F16PointsLayout& L, char* ws,
+                       cudaStream_t stream) {
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    if (L.Mv > M)   // |v|^2 of padded sources: 0x7f7f7f7f = 3.4e38, their weights underflow to zero
+        KMB_CUDA_CHECK(cudaMemsetAsync(F(L.off_vn) + M, 0x7f, sizeof(float) * (L.Mv - M), stream));
+    return tc::tensor_prepass_f16(x, y, N, M, D, L.Dp, kid, F(L.off_center), F(L.off_stats), F(L.off_sscale), ws + L.off_uh,
+                                  ws + L.off_ul, ws + L.off_vh, ws + L.off_vl, F(L.off_un), F(L.off_vn), stream);
+}
+
 namespace {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -989,15 +1016,24 @@ int plan_tensor(int64_t N, int64_t M, int D, int E, int elt, TensorPlan* pl) {
     const int PS = tc::MAX_EP + 2;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
-    pl->off_center = take(sizeof(float) * pl->Dp);
-    pl->off_cpart = take(sizeof(float) * tc::CENTER_BLOCKS * D * (f16 ? 6 : 1));
-    pl->off_sscale = take(sizeof(float) * 2);
-    pl->off_uh = take(pl->esz * N * pl->Dp);
-    pl->off_ul = take(pl->esz * N * pl->Dp);
-    pl->off_vh = take(pl->esz * M * pl->Dp);
-    pl->off_vl = take(pl->esz * M * pl->Dp);
-    pl->off_un = take(sizeof(float) * N);
-    pl->off_vn = take(sizeof(float) * M);
+    if (f16) {   // the points-only head shared with kprod_tensor_pv16 (kmb_product_prepare_f32)
+        F16PointsLayout L;
+        f16_points_layout(N, M, D, &L);
+        pl->off_center = L.off_center; pl->off_cpart = L.off_stats; pl->off_sscale = L.off_sscale;
+        pl->off_uh = L.off_uh; pl->off_ul = L.off_ul; pl->off_vh = L.off_vh; pl->off_vl = L.off_vl;
+        pl->off_un = L.off_un; pl->off_vn = L.off_vn;
+        o = L.end;
+    } else {
+        pl->off_center = take(sizeof(float) * pl->Dp);
+        pl->off_cpart = take(sizeof(float) * tc::CENTER_BLOCKS * D);
+        pl->off_sscale = take(sizeof(float) * 2);
+        pl->off_uh = take(pl->esz * N * pl->Dp);
+        pl->off_ul = take(pl->esz * N * pl->Dp);
+        pl->off_vh = take(pl->esz * M * pl->Dp);
+        pl->off_vl = take(pl->esz * M * pl->Dp);
+        pl->off_un = take(sizeof(float) * N);
+        pl->off_vn = take(sizeof(float) * M);
+    }
     pl->off_partial = take(sizeof(float) * pl->waves.partial_slots * tc::TM * PS);
     pl->off_counter = take(sizeof(int) * pl->n_tiles);
     pl->total = o;
@@ -1090,11 +1126,21 @@ int tensor_workspace_bytes(int64_t N, int64_t M, int D, int E, int kid, int flag
     return KMB_OK;
 }
 
+int tensor_prepare(const float* x, const float* y, int64_t N, int64_t M, int D, int kid, int elt, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream) {
+    if (elt != tc::ELT_F16) return KMB_OK;
+    F16PointsLayout L;
+    f16_points_layout(N, M, D, &L);
+    if (!workspace || workspace_bytes < L.end)
+        return set_error(KMB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", L.end, workspace_bytes);
+    return f16_points_prepass(x, y, N, M, D, kid, L, static_cast<char*>(workspace), stream);
+}
+
 int tensor_product(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D, int E,
                    int kid, int flags, int elt, int64_t row_offset, void* workspace, size_t workspace_bytes,
-                   cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1) {
+                   cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1, bool prepared) {
     if (elt == tc::ELT_F16 && tensor_pv16_applicable(D, E, kid))
-        return tensor_pv16_product(x, y, b, out, N, M, D, E, kid, flags, workspace, workspace_bytes, stream, ev0, ev1);
+        return tensor_pv16_product(x, y, b, out, N, M, D, E, kid, flags, workspace, workspace_bytes, stream, ev0, ev1, prepared);
     if (tensor_pv_applicable(D, E))
         return tensor_pv_product(x, y, b, out, N, M, D, E, kid, flags, row_offset, workspace, workspace_bytes, stream, ev0, ev1);
     TensorPlan pl{};
@@ -1122,7 +1168,11 @@ int tensor_product(const float* x, const float* y, const float* b, float* out, i
     KMB_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(int) * pl.n_tiles, stream));
     CUtensorMap maps[4];
     if (f16) {
-        if (int rc = tc::tensor_prepass_f16(x, y, N, M, D, pl.Dp, kid, center, cpart, sscale, uh, ul, vh, vl, un, vn, stream)) return rc;
+        if (!prepared) {
+            F16PointsLayout L;
+            f16_points_layout(N, M, D, &L);
+            if (int rc = f16_points_prepass(x, y, N, M, D, kid, L, ws, stream)) return rc;
+        }
         if (int rc = tc::make_tensor_map_f16(&maps[0], uh, N, pl.Dp, tc::TM)) return rc;
         if (int rc = tc::make_tensor_map_f16(&maps[1], ul, N, pl.Dp, tc::TM)) return rc;
         // the pair kernel's CTAs each load half a source block (128 rows)

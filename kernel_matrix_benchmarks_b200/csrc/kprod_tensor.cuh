@@ -14,7 +14,12 @@ int tensor_workspace_bytes(int64_t N, int64_t M, int D, int E, int kid, int flag
 // ev0/ev1: optional events recorded around the last main kernel.
 int tensor_product(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D, int E,
                    int kid, int flags, int elt, int64_t row_offset, void* workspace, size_t workspace_bytes,
-                   cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1);
+                   cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1, bool prepared = false);
+
+// Points-only prepass of the FP16-plane kernels into the head of the workspace (E-independent layout; see
+// kmb_product_prepare_f32).  tensor_product skips it when `prepared` is set.  No-op for TF32 planes.
+int tensor_prepare(const float* x, const float* y, int64_t N, int64_t M, int D, int kid, int elt, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream);
 
 // The wave schedule of the tensor kernels for a (row tiles x source blocks) problem on `grid` CTAs (or clusters):
 // out = {R, C, W, R_last, C_last, slots_per_wave, partial_slots}.  Host logic only (tests/test_abi_cpu.py).

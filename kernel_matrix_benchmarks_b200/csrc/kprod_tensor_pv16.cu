@@ -693,17 +693,13 @@ int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
     } else {
         tc::plan_waves(pl->n_tiles, pl->nsb, pl->grid, static_cast<size_t>(tc::TM) * pl->Dp * 4, &pl->waves);
     }
-    size_t o = 0;
+    F16PointsLayout L;   // the points-only head shared with kprod_tensor (kmb_product_prepare_f32)
+    f16_points_layout(N, M, D, &L);
+    pl->off_center = L.off_center; pl->off_stats = L.off_stats; pl->off_sscale = L.off_sscale;
+    pl->off_uh = L.off_uh; pl->off_ul = L.off_ul; pl->off_vh = L.off_vh; pl->off_vl = L.off_vl;
+    pl->off_un = L.off_un; pl->off_vn = L.off_vn;
+    size_t o = L.end;
     auto take = [&](size_t bytes) { size_t at = o; o += align_up_pv16(bytes, 256); return at; };
-    pl->off_center = take(sizeof(float) * pl->Dp);
-    pl->off_stats = take(sizeof(float) * tc::CENTER_BLOCKS * D * 6);
-    pl->off_sscale = take(sizeof(float) * 2);
-    pl->off_uh = take(2 * static_cast<size_t>(N) * pl->Dp);
-    pl->off_ul = take(2 * static_cast<size_t>(N) * pl->Dp);
-    pl->off_vh = take(2 * static_cast<size_t>(M) * pl->Dp);
-    pl->off_vl = take(2 * static_cast<size_t>(M) * pl->Dp);
-    pl->off_un = take(sizeof(float) * N);
-    pl->off_vn = take(sizeof(float) * pl->Mp);   // padded: the epilogue reads whole 128-source blocks
     pl->off_sh = take(2 * static_cast<size_t>(pl->Ep) * pl->Mp);
     pl->off_sl = take(2 * static_cast<size_t>(pl->Ep) * pl->Mp);
     pl->off_bmax = take(sizeof(float) * tc::CENTER_BLOCKS * E);
@@ -753,7 +749,7 @@ int tensor_pv16_workspace_bytes(int64_t N, int64_t M, int D, int E, size_t* byte
 
 int tensor_pv16_product(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D, int E, int kid,
                         int flags, void* workspace, size_t workspace_bytes, cudaStream_t stream, cudaEvent_t ev0,
-                        cudaEvent_t ev1) {
+                        cudaEvent_t ev1, bool prepared) {
     Pv16Plan pl{};
     if (int rc = plan_pv16(N, M, D, E, &pl)) return rc;
     if (!workspace || workspace_bytes < pl.total)
@@ -768,11 +764,11 @@ int tensor_pv16_product(const float* x, const float* y, const float* b, float* o
     const bool norm = flags & KMB_FLAG_NORMALIZE_ROWS;
 
     KMB_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(int) * pl.n_tiles, stream));
-    if (int rc = tc::tensor_prepass_f16(x, y, N, M, D, pl.Dp, kid, F(pl.off_center), F(pl.off_stats), F(pl.off_sscale), uh, ul, vh, vl,
-                                        F(pl.off_un), F(pl.off_vn), stream))
-        return rc;
-    if (pl.Mp > M)   // |v|^2 of padded sources: 0x7f7f7f7f = 3.4e38, their weights underflow to zero
-        KMB_CUDA_CHECK(cudaMemsetAsync(F(pl.off_vn) + M, 0x7f, sizeof(float) * (pl.Mp - M), stream));
+    if (!prepared) {
+        F16PointsLayout L;
+        f16_points_layout(N, M, D, &L);
+        if (int rc = f16_points_prepass(x, y, N, M, D, kid, L, ws, stream)) return rc;
+    }
     {
         const int blocks = static_cast<int>(std::min<long long>(tc::CENTER_BLOCKS, (M + 7) / 8));
         pv16::signal_absmax_kernel<<<dim3(blocks, (E + 31) / 32), 256, 0, stream>>>(b, M, E, F(pl.off_bmax));

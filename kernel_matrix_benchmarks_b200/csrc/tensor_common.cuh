@@ -285,6 +285,17 @@ bool tensor_pv16_applicable(int D, int E, int kid);
 int tensor_pv16_workspace_bytes(int64_t N, int64_t M, int D, int E, size_t* bytes);
 int tensor_pv16_product(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D, int E, int kid,
                         int flags, void* workspace, size_t workspace_bytes, cudaStream_t stream, cudaEvent_t ev0,
-                        cudaEvent_t ev1);
+                        cudaEvent_t ev1, bool prepared);
+
+// Head of the workspace of both FP16-plane kernels: everything the prepass writes from the points alone.  The layout
+// depends on (N, M, D) only, so that it survives from fit() to query() whatever the signal width turns out to be.
+struct F16PointsLayout {
+    int Dp;          // D rounded up to 16
+    long long Mv;    // entries of |v|^2: M rounded up to 256, the tail filled with 3.4e38 (padded sources weigh nothing)
+    size_t off_center, off_stats, off_sscale, off_uh, off_ul, off_vh, off_vl, off_un, off_vn, end;
+};
+void f16_points_layout(int64_t N, int64_t M, int D, F16PointsLayout* L);
+int f16_points_prepass(const float* x, const float* y, int64_t N, int64_t M, int D, int kid, const F16PointsLayout& L,
+                       char* ws, cudaStream_t stream);
 
 }  // namespace kmb

@@ -55,12 +55,46 @@ def symmetric_applies(x, y, kernel, normalize_rows=False, density_estimation=Fal
             and E == 1 and x.shape[1] <= 3)
 
 
+def workspace_bytes(N, M, D, E, *, kernel="gaussian", normalize_rows=False, density_estimation=False, path="auto"):
+    """kmb_product_workspace_bytes for this shape."""
+    flags = (_lib.FLAG_NORMALIZE_ROWS if normalize_rows else 0) | (_lib.FLAG_DENSITY if density_estimation else 0)
+    need = ctypes.c_size_t(0)
+    _lib.check(_lib.load().kmb_product_workspace_bytes(int(N), int(M), int(D), int(E), _lib.KERNEL_IDS[kernel], flags,
+                                                       _lib.PATH_IDS[path], ctypes.byref(need)))
+    return int(need.value)
+
+
+def prepare_points(x, y, *, kernel="gaussian", path="auto", workspace=None, min_bytes=0):
+    """The points-only part of a product (kmb_product_prepare_f32): for the FP16 tensor path the prepass (centre, scale,
+    operand planes, squared norms) is written to the head of ``workspace``.  Returns the buffer it was written to: a
+    later ``kernel_product(..., prepared=token)`` on the same x, y, kernel, path and workspace skips the prepass as long
+    as the workspace has not been reallocated since (``token`` is compared with the buffer in use; otherwise the
+    product silently does the prepass itself).  No-op (returns None) on the other paths."""
+    lib = _lib.load()
+    _check_f32("target points", x)
+    _check_f32("source points", y, x.shape[1])
+    N, D = x.shape
+    M = y.shape[0]
+    if D <= 16 or _lib.PATH_IDS[path] not in (_lib.PATH_IDS["auto"], _lib.PATH_IDS["tensor_f16"]):
+        return None
+    kid, pid = _lib.KERNEL_IDS[kernel], _lib.PATH_IDS[path]
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.kmb_product_workspace_bytes(N, M, D, 1, kid, 0, pid, ctypes.byref(need)))
+    if workspace is None:
+        workspace = _default_ws.setdefault(x.device, Workspace())
+    ws = workspace.get(max(need.value, int(min_bytes)), x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.kmb_product_prepare_f32(_ptr(x), _ptr(y), N, M, D, kid, 0, pid, _ptr(ws), ws.numel(), _stream()))
+    return ws
+
+
 def kernel_product(x, y, b, *, kernel="gaussian", normalize_rows=False, density_estimation=False, path="auto",
-                   row_offset=0, out=None, workspace=None):
+                   row_offset=0, out=None, workspace=None, prepared=None):
     """a_i = sum_j k(x_i, y_j) b_j on the current CUDA device (kmb_product_f32).
 
     x (N, D), y (M, D), b (M, E) float32 CUDA tensors; b is ignored (may be None)
-    under ``density_estimation``.  Asynchronous on the current stream.
+    under ``density_estimation``.  Asynchronous on the current stream.  ``prepared``: the token of
+    ``prepare_points`` for these points (see there).
     """
     lib = _lib.load()
     if kernel not in _lib.KERNEL_IDS:
@@ -91,6 +125,8 @@ def kernel_product(x, y, b, *, kernel="gaussian", normalize_rows=False, density_
     if workspace is None:
         workspace = _default_ws.setdefault(x.device, Workspace())
     ws = workspace.get(need.value, x.device)
+    if prepared is not None and prepared is ws:   # same buffer as at prepare time: its head holds the operand planes
+        flags |= _lib.FLAG_PREPARED
     with torch.cuda.device(x.device):
         _lib.check(lib.kmb_product_f32(_ptr(x), _ptr(y), _ptr(b), _ptr(out), N, M, D, E, kid, flags, pid, int(row_offset),
                                        _ptr(ws), ws.numel(), _stream()))

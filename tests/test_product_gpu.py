@@ -304,6 +304,50 @@ def test_tensor_f16_scaling_range():
     assert err <= TOL_TENSOR, err
 
 
+def test_prepared_points_give_the_same_product():
+    """kmb_product_prepare_f32 + KMB_FLAG_PREPARED == the product doing its own prepass, bit for bit; the plugin does
+    the prepass in fit(), prepares again when the workspace has to grow for a wider signal, and reuses it afterwards."""
+    import torch
+    from kernel_matrix_benchmarks_b200 import product
+    from kernel_matrix_benchmarks_b200.algorithms.b200 import B200Product
+
+    rng = np.random.RandomState(21)
+    D = 96
+    r = (3.0 / D) ** 0.5
+    yh, xh = r * rng.rand(3000, D), r * rng.rand(700, D)
+    y = torch.tensor(yh, dtype=torch.float32, device="cuda")
+    x = torch.tensor(xh, dtype=torch.float32, device="cuda")
+    for E in (1, 40):
+        b = torch.tensor(rng.randn(3000, E), dtype=torch.float32, device="cuda")
+        plain = product.kernel_product(x, y, b, kernel="gaussian", workspace=product.Workspace())
+        ws = product.Workspace()
+        token = product.prepare_points(x, y, kernel="gaussian", workspace=ws,
+                                       min_bytes=product.workspace_bytes(700, 3000, D, E, kernel="gaussian"))
+        assert token is not None
+        again = product.kernel_product(x, y, b, kernel="gaussian", workspace=ws, prepared=token)
+        assert torch.equal(plain, again)
+        # a stale token (the workspace was reallocated) is ignored: the product does the prepass itself
+        stale = product.kernel_product(x, y, b, kernel="gaussian", workspace=product.Workspace(), prepared=token)
+        assert torch.equal(plain, stale)
+    assert product.prepare_points(x[:, :3].contiguous(), y[:, :3].contiguous(), kernel="gaussian") is None   # direct path: no-op
+
+    algo = B200Product(kernel="gaussian", dimension=D, precision="float32")
+    algo.prepare_data(source_points=yh, target_points=xh)
+    algo.fit()
+    first = algo._prepared
+    assert first is not None
+    outs = []
+    for E in (1, 40, 40, 1):
+        bh = np.random.RandomState(E).randn(3000, E)
+        algo.prepare_query(source_signal=bh)
+        algo.query()
+        outs.append((E, algo.get_result(), algo._prepared))
+        assert orc.rel_l2(outs[-1][1], c_oracle.kernel_product("gaussian", yh, xh, bh)) <= 1e-5
+    assert outs[0][2] is first and outs[1][2] is not first and outs[2][2] is outs[1][2] and outs[3][2] is outs[1][2]
+    assert np.array_equal(outs[1][1], outs[2][1])
+    algo.done()
+
+
 def test_config_c3_sampled():
     """BASELINE config 3 at full size (M = 60k sources, N = 10k targets, D = 784, E = 1):
     every 40th target row against the float64 oracle."""
