@@ -138,7 +138,7 @@ def test_solver_run_groups():
                                task="solver", hardware="GPU", kernel="gaussian")
         return sorted(d.arguments["lam"] for d in defs), [d.query_argument_groups for d in defs]
 
-    assert lams("solver-ucubelam1-D3-E1-M2000-N2000-gaussian")[0] == [1.0, 1.0]   # with and without the preconditioner
+    assert lams("solver-ucubelam1-D3-E1-M2000-N2000-gaussian")[0] == [1.0, 1.0]   # preconditioner "auto" and "nystrom"
     assert lams("solver-cube-D3-E1-M1000-N1000-gaussian")[0] == [0.0]
     assert all(len(g) == 2 for g in lams("solver-ucubelam1-D3-E1-M2000-N2000-gaussian")[1])
 

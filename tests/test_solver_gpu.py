@@ -112,9 +112,11 @@ def test_nystrom_preconditioner_cuts_iterations(kernel):
     n, lam = 6000, 1.0
     ds = datasets.uniform_cube(n, 3, 1.0, kernel, "solver")
     rhs = orc.regularised_matvec(kernel, ds.source_points, ds.source_signal, lam)
-    x_pc, e_pc = run_solver(kernel, ds.source_points, rhs, lam=lam, rtol=1e-6, precond_rank=512)
+    x_pc, e_pc = run_solver(kernel, ds.source_points, rhs, lam=lam, rtol=1e-6, preconditioner="nystrom", precond_rank=512)
     x_cg, e_cg = run_solver(kernel, ds.source_points, rhs, lam=lam, rtol=1e-6, preconditioner="none")
     assert e_pc["preconditioner"].startswith("nystrom") and e_cg["preconditioner"] == "none"
+    _, e_auto = run_solver(kernel, ds.source_points, rhs, lam=lam, rtol=1e-6)   # "auto": too few points to repay the build
+    assert e_auto["preconditioner"] == "none"
     assert e_pc["cg_converged"] and e_cg["cg_converged"]
     assert e_pc["cg_iterations"] * 4 <= e_cg["cg_iterations"], (e_pc, e_cg)
     assert orc.rel_l2(x_pc, ds.source_signal) <= 1e-4
