@@ -414,8 +414,11 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
 #pragma unroll
                     for (int c = 0; c < CPT / 4; ++c) {
                         const float4 vq = vnq[c];   // broadcast read of the warp's line
-                        const float2 ta = neg_log2_kernel2<KID>(t2[2 * c], nss2, add2(make_float2(vq.x, vq.y), un2));
-                        const float2 tb = neg_log2_kernel2<KID>(t2[2 * c + 1], nss2, add2(make_float2(vq.z, vq.w), un2));
+                        // Gaussian: |u|^2 is the same for the whole row, so it is left out of t here and added to the
+                        // block minimum / subtracted with the reference exponent below (one FADD2 per four values less)
+                        const float2 wa = make_float2(vq.x, vq.y), wb = make_float2(vq.z, vq.w);
+                        const float2 ta = neg_log2_kernel2<KID>(t2[2 * c], nss2, KID == KMB_KERNEL_GAUSSIAN ? wa : add2(wa, un2));
+                        const float2 tb = neg_log2_kernel2<KID>(t2[2 * c + 1], nss2, KID == KMB_KERNEL_GAUSSIAN ? wb : add2(wb, un2));
                         t2[2 * c] = ta;
                         t2[2 * c + 1] = tb;
                         tmin = fminf(fminf(tmin, ta.x), ta.y);
@@ -425,7 +428,8 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
 #pragma unroll
                     for (int c = 0; c < CPT / 2; ++c) t2[c] = make_float2(INFINITY, INFINITY);
                 }
-                const float cm = -tmin;   // largest log2 k of the block
+                constexpr bool kRowTermOut = (KID == KMB_KERNEL_GAUSSIAN);   // t2 lacks the row's |u|^2
+                const float cm = kRowTermOut ? -(tmin + un) : -tmin;   // largest log2 k of the block
                 KMB_T(3);
                 // lazy rescale: keep the reference exponent unless the maximum outgrew it by 2^8
                 {
@@ -454,7 +458,8 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 {
                     uint32_t ph[CPT / 2], pl[CPT / 2];
                     float2 kacc = make_float2(0.f, 0.f);   // two-level sum of the weights (see kprod_direct.cuh)
-                    const float nref = (ref == -INFINITY) ? 0.f : -ref;   // all -inf so far: every weight is 2^-inf = 0
+                    // all -inf so far: every weight is 2^-inf = 0
+                    const float nref = (ref == -INFINITY) ? 0.f : (kRowTermOut ? -ref - un : -ref);
                     const float2 nref2 = make_float2(nref, nref);
 #pragma unroll
                     for (int c = 0; c < CPT / 2; ++c) {
