@@ -14,7 +14,8 @@
 // agree on the row maximum through shared memory, and each one rescales / stores its own share of O.
 //
 // TMEM columns: S stage 0 [0,64) | S stage 1 [64,128) | P hi [128,192) | P lo [192,256) | O [256,256+E).
-// Warp roles and the stream-K work split are those of kprod_tensor.cu.
+// Warp roles and the wave schedule (every CTA of a wave walks the same source blocks at the same time) are those of
+// kprod_tensor.cu.  This is the first version of the E > 4 kernel; FP16 planes take kprod_tensor_pv16.cu.
 #include <algorithm>
 
 #include "tensor_common.cuh"
@@ -49,7 +50,24 @@ struct Params {
     int E, e0, eb;             // this pass covers signal columns e0 .. e0+eb-1; ebp = eb rounded up to 32
     int ebp;
     int n_tiles, nsb, kblocks, stages;
+    int R, C, W, R_last, C_last, slots_per_wave;   // wave schedule (tc::plan_waves, see kprod_tensor.cu)
 };
+
+// unit range [u0, u1) (units = row tile * nsb + source block) of CTA `cta` in wave w: one row tile, a contiguous range
+// of its source blocks; every CTA of a wave with the same range index walks the same source blocks at the same time
+struct WaveRange { long long u0, u1; int c, Cw, tile_in_wave; };
+__device__ __forceinline__ bool wave_range(const Params& P, int w, int cta, WaveRange& wr) {
+    const bool last = (w == P.W - 1);
+    const int Rw = last ? P.R_last : P.R, Cw = last ? P.C_last : P.C;
+    if (cta >= Rw * Cw) return false;
+    wr.Cw = Cw;
+    wr.tile_in_wave = cta / Cw;
+    wr.c = cta - wr.tile_in_wave * Cw;
+    const long long tile = static_cast<long long>(w) * P.R + wr.tile_in_wave;
+    wr.u0 = tile * P.nsb + static_cast<long long>(P.nsb) * wr.c / Cw;
+    wr.u1 = tile * P.nsb + static_cast<long long>(P.nsb) * (wr.c + 1) / Cw;
+    return true;
+}
 
 template <int KID, bool NORM>
 struct Cfg {
@@ -85,8 +103,8 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x;
     const long long nsb = P.nsb;
-    const long long U = static_cast<long long>(P.n_tiles) * nsb;
-    const long long u0 = U * blockIdx.x / G, u1 = U * (blockIdx.x + 1) / G;
+    const int cta = blockIdx.x;
+    (void)G;
     const int ST = P.stages;
 
     if (tid == 0) {
@@ -126,6 +144,10 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                 }
             };
             long long prev = -1;
+            WaveRange wr;
+            for (int w = 0; w < P.W; ++w) {
+            if (!wave_range(P, w, cta, wr)) continue;
+            const long long u0 = wr.u0, u1 = wr.u1;
             for (long long u = u0; u < u1; ++u) {
                 const int tile = static_cast<int>(u / nsb);
                 if (u == u0 || u % nsb == 0) {   // new row tile: (re)load the resident u tile
@@ -154,6 +176,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                 }
                 if (prev >= 0) emit_signal(prev);   // consumed by PV(n-1), issued after S(n)
                 prev = u;
+            }
             }
             if (prev >= 0) emit_signal(prev);
         }
@@ -193,6 +216,10 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                 __syncwarp();
             };
             bool prev_first = false, pv_pending = false;
+            WaveRange wr;
+            for (int w = 0; w < P.W; ++w) {
+            if (!wave_range(P, w, cta, wr)) continue;
+            const long long u0 = wr.u0, u1 = wr.u1;
             for (long long u = u0; u < u1; ++u, ++n) {
                 const bool first = (u == u0) || (u % nsb == 0);
                 if (first) {
@@ -234,6 +261,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                 pv_pending = true;
                 prev_first = first;
             }
+            }
             if (pv_pending) issue_pv(n - 1, prev_first);
         }
     } else {
@@ -258,8 +286,12 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
             }
             tc_fence_after();
         };
+        WaveRange wr;
+        for (int w = 0; w < P.W; ++w) {
+        if (!wave_range(P, w, cta, wr)) continue;
+        const long long u0 = wr.u0, u1 = wr.u1;
         long long u = u0;
-        float vn_next = 1.0e30f;   // |v|^2 of source (next tile's block) + et, for the threads that stage it
+        float vn_next = 1.0e30f;   // |v|^2 of source (next block) + et, for the threads that stage it
         if (et < TN && u0 < u1) {
             const long long j = (u0 % nsb) * TN + et;
             if (j < P.M) vn_next = __ldg(P.vn + j);
@@ -378,9 +410,10 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
             float ktot = 0.f;
 #pragma unroll
             for (int g = 0; g < NG; ++g) ktot += ksbuf[g * TM + row_in_tile];
-            const bool complete = (cnt == nsb);
-            const int slot = (u == u0) ? 0 : 1;
-            float* mine = P.partial + (static_cast<size_t>(blockIdx.x) * 2 + slot) * (TM * C::PS);
+            const bool complete = (wr.Cw == 1);
+            // one partial record per (wave, CTA); the last CTA of the row tile to arrive adds them in range order
+            const size_t slot0 = static_cast<size_t>(w) * P.slots_per_wave + static_cast<size_t>(wr.tile_in_wave) * wr.Cw;
+            float* mine = P.partial + (slot0 + wr.c) * (TM * C::PS);
             for (int c0 = cg * 16; c0 < P.ebp; c0 += NG * 16) {   // this group's 16-column chunks of O
                 float o[16];
                 tmem_ld_cols<16>(tmem_base + COL_O + c0 + lane_addr, o);
@@ -403,9 +436,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                 }
                 __threadfence();
                 named_bar_sync(2, EPI_THREADS);
-                const long long tile_u0 = static_cast<long long>(tile) * nsb;
-                const int c_first = static_cast<int>(((tile_u0 + 1) * G - 1) / U);
-                const int c_last = static_cast<int>(((tile_u0 + nsb) * G - 1) / U);
+                const int c_first = 0, c_last = wr.Cw - 1;
                 if (et == 0) {
                     const int old = atomicAdd(&P.tile_counter[tile], 1);
                     const int last = (old == c_last - c_first);
@@ -420,8 +451,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                     float mx = -INFINITY, l = 0.f;
                     if constexpr (C::ONLINE_MAX) {
                         for (int c = c_first; c <= c_last; ++c) {
-                            const int sl = (U * c / G) / nsb == tile ? 0 : 1;
-                            const float* ps = P.partial + (static_cast<size_t>(c) * 2 + sl) * (TM * C::PS);
+                            const float* ps = P.partial + (slot0 + c) * (TM * C::PS);
                             mx = fmaxf(mx, __ldcg(ps + (MAX_EB + 1) * TM + row_in_tile));
                         }
                     }
@@ -429,8 +459,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                         float sum = 0.f;
                         l = 0.f;
                         for (int c = c_first; c <= c_last; ++c) {
-                            const int sl = (U * c / G) / nsb == tile ? 0 : 1;
-                            const float* ps = P.partial + (static_cast<size_t>(c) * 2 + sl) * (TM * C::PS);
+                            const float* ps = P.partial + (slot0 + c) * (TM * C::PS);
                             float w = 1.f;
                             if constexpr (C::ONLINE_MAX) {
                                 const float m = __ldcg(ps + (MAX_EB + 1) * TM + row_in_tile);
@@ -446,6 +475,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                 named_bar_sync(2, EPI_THREADS);   // ksbuf is rewritten at the end of the next segment
             }
             u += cnt;
+        }
         }
     }
 
@@ -476,6 +506,7 @@ size_t align_up_pv(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct PvPlan {
     int Dp, Ep, kblocks, stages, grid_max, smem;
     long long n_tiles, nsb, Mp;
+    tc::WavePlan waves;
     size_t off_center, off_cpart, off_uh, off_ul, off_vh, off_vl, off_un, off_vn, off_sh, off_sl, off_partial, off_counter, total;
 };
 
@@ -507,7 +538,8 @@ int plan_pv(int64_t N, int64_t M, int D, int E, PvPlan* pl) {
     pl->off_vn = take(sizeof(float) * M);
     pl->off_sh = take(sizeof(float) * pl->Ep * pl->Mp);
     pl->off_sl = take(sizeof(float) * pl->Ep * pl->Mp);
-    pl->off_partial = take(sizeof(float) * pl->grid_max * 2 * tc::TM * (pv::MAX_EB + 2));
+    tc::plan_waves(pl->n_tiles, pl->nsb, pl->grid_max, static_cast<size_t>(tc::TM) * pl->Dp * 8, &pl->waves);
+    pl->off_partial = take(sizeof(float) * pl->waves.partial_slots * tc::TM * (pv::MAX_EB + 2));
     pl->off_counter = take(sizeof(int) * pl->n_tiles);
     pl->total = o;
     return KMB_OK;
@@ -571,8 +603,7 @@ int tensor_pv_product(const float* x, const float* y, const float* b, float* out
     if (int rc = tc::make_tensor_map(&maps[4], sh, pl.Ep, static_cast<int>(pl.Mp), pv::MAX_EB)) return rc;
     if (int rc = tc::make_tensor_map(&maps[5], sl, pl.Ep, static_cast<int>(pl.Mp), pv::MAX_EB)) return rc;
 
-    const long long units = pl.n_tiles * pl.nsb;
-    const int grid = static_cast<int>(std::min<long long>(pl.grid_max, units));
+    const int grid = pl.grid_max;
     const int n_passes = pl.Ep / pv::MAX_EB;
     for (int pass = 0; pass < n_passes; ++pass) {
         pv::Params P;
@@ -592,6 +623,12 @@ int tensor_pv_product(const float* x, const float* y, const float* b, float* out
         P.nsb = static_cast<int>(pl.nsb);
         P.kblocks = pl.kblocks;
         P.stages = pl.stages;
+        P.R = pl.waves.R;
+        P.C = pl.waves.C;
+        P.W = pl.waves.W;
+        P.R_last = pl.waves.R_last;
+        P.C_last = pl.waves.C_last;
+        P.slots_per_wave = pl.waves.slots_per_wave;
         if (ev0 && pass == n_passes - 1) KMB_CUDA_CHECK(cudaEventRecord(ev0, stream));
         int rc;
         switch (kid * 2 + (norm ? 1 : 0)) {
