@@ -326,35 +326,28 @@ class NystromPreconditioner:
 
 def pcg_solve(ops, comm, a_local, n_total, precond, *, lam=0.0, rtol=1e-6, max_iter=500):
     """Preconditioned CG on (K + lam I) x = a for the rows this rank owns; ``precond.apply`` is M^-1 on local rows.
-    Same ops / comm interfaces as cg_solve (only ``ops.matvec`` is used: the vector updates are a few
-    element-wise torch kernels on N floats, microseconds beside a 10^12-pair matvec).  Convergence is tested
-    on the true-residual recurrence |r| / |a| like cg_solve, with a blocking check every iteration (a
+    Same ops / comm interfaces as cg_solve and the same fused vector kernels: with z = M^-1 r the step length is
+    (r.z) / (p.Ap) and the new direction z + ((r.z)_new / (r.z)) p, so ``ops.update`` and ``ops.direction`` are handed
+    r.z where plain CG hands them r.r (the update still returns the new r.r for the convergence test).  Convergence
+    is tested on the recurrence residual |r| / |a| like cg_solve, with a blocking check every iteration (a
     preconditioned solve takes a handful of iterations)."""
-    x = torch.zeros_like(a_local)
-    r = a_local.clone()
-    rs0 = (r * r).sum(0)
-    comm.all_reduce(rs0)
+    x, r, p, rs = ops.init(a_local)          # x = 0, r = a, p = a (overwritten below), rs = partial r.r
+    comm.all_reduce(rs)
+    rs0 = rs.clone()
+    pAp, rs_new = torch.empty_like(rs), torch.empty_like(rs)
     tol2 = float(rtol) ** 2
-    it = 0
-    rs = rs0.clone()
-    done = bool((rs0 <= 0).all())
+    it, done = 0, bool((rs0 <= 0).all())
     if not done:
         z = precond.apply(r)
-        p = z.clone()
+        p.copy_(z)
         rz = (r * z).sum(0)
         comm.all_reduce(rz)
     while not done and it < max_iter:
         p_full = comm.all_gather(p, n_total)
         Ap = ops.matvec(p_full)
-        if lam:
-            Ap = Ap + float(lam) * p
-        pAp = (p * Ap).sum(0)
-        comm.all_reduce(pAp)
-        alpha = rz / pAp
-        x += alpha * p
-        r -= alpha * Ap
-        rs = (r * r).sum(0)
-        comm.all_reduce(rs)
+        comm.all_reduce(ops.shift_dot(Ap, p, float(lam), pAp))           # Ap += lam p; p.Ap
+        comm.all_reduce(ops.update(x, r, p, Ap, rz, pAp, rs_new))        # alpha = r.z / p.Ap; x, r; new r.r
+        rs, rs_new = rs_new, rs
         it += 1
         done = bool((rs <= tol2 * rs0).all())
         if done:
@@ -362,7 +355,7 @@ def pcg_solve(ops, comm, a_local, n_total, precond, *, lam=0.0, rtol=1e-6, max_i
         z = precond.apply(r)
         rz_new = (r * z).sum(0)
         comm.all_reduce(rz_new)
-        p = z + (rz_new / rz) * p
+        ops.direction(p, z, rz_new, rz)                                  # p = z + (r.z_new / r.z) p
         rz = rz_new
     safe = torch.where(rs0 > 0, rs0, torch.ones_like(rs0))
     rel = float(torch.sqrt(rs / safe).max()) if rs0.numel() else 0.0
