@@ -1,5 +1,6 @@
-// Tensor-core path (D > 16): squared distances through |x|^2 + |y|^2 - 2 x.y^T with the dot
-// products on tcgen05 (kind::tf32, FP32 accumulators in TMEM), 3xTF32 split for FP32-class accuracy.
+// Tensor-core path (D > 16): squared distances through |x|^2 + |y|^2 - 2 x.y with the dot products on tcgen05
+// (FP32 accumulators in TMEM) and a three-term hi/lo split of the operands for FP32-class accuracy: FP16 planes of
+// power-of-two scaled data (KMB_PATH_TENSOR_3XF16, the default) or TF32 planes (KMB_PATH_TENSOR_3XTF32).
 // Replaces kernel_matrix(..., fast_sqdists=True) + K @ b of the reference
 // (/root/reference/kernel_matrix_benchmarks/algorithms/bruteforce.py:36-49, 18-22, 130-153).
 #pragma once
