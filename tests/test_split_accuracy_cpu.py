@@ -76,3 +76,40 @@ def test_f16_planes_with_an_outlier_and_tiny_coordinates():
     exact = pts.astype(np.float64) @ pts.astype(np.float64).T
     bulk = slice(1, None)
     assert np.abs(got - exact)[bulk, bulk].max() <= big * np.abs(pts[1:]).max() * D * 2.0 ** -22
+
+
+def test_per_group_lazy_online_softmax_merges_exactly():
+    """The epilogue of kprod_tensor_pv16 restated: four column groups keep independent running sums with LAZY reference
+    exponents (rescaled only when the block maximum outgrows the reference by 2^8), weights split into FP16 hi + lo,
+    merged at the end with 2^(ref_g - ref).  Against the plain row-normalised product in float64."""
+    rng = np.random.RandomState(3)
+    n_rows, n_src, E, block, groups, lazy = 16, 2048, 8, 128, 4, 8.0
+    # log2 kernel values with a strong trend (far -> near sources) so that references must move, plus rows that only
+    # ever see tiny values (FP32 exp would underflow)
+    logk = -40.0 * rng.rand(n_rows, n_src) - np.linspace(300.0, 0.0, n_src)[None, :]
+    logk[3] -= 400.0
+    b = rng.randn(n_src, E)
+    want = (np.exp2(logk - logk.max(1, keepdims=True)) @ b) / np.exp2(logk - logk.max(1, keepdims=True)).sum(1, keepdims=True)
+
+    O = np.zeros((groups, n_rows, E)); ks = np.zeros((groups, n_rows)); ref = np.full((groups, n_rows), -np.inf)
+    for j0 in range(0, n_src, block):
+        for g in range(groups):
+            cols = slice(j0 + 32 * g, j0 + 32 * g + 32)
+            s = logk[:, cols]
+            cm = s.max(1)
+            first = np.isinf(ref[g])
+            need = ~first & (cm > ref[g] + lazy)
+            sc = np.where(need, np.exp2(ref[g] - cm), 1.0)
+            O[g] *= sc[:, None]; ks[g] *= sc
+            ref[g] = np.where(first | need, cm, ref[g])
+            p = np.float32(np.exp2(s - ref[g][:, None]))
+            assert p.max() <= 2.0 ** lazy * 1.0001          # fits FP16 with room to spare
+            hi = (p.view(np.uint32) & 0xFFFFE000).view(np.float32)   # 11 significant bits: exact in FP16
+            lo = (p - hi).astype(np.float16).astype(np.float64)
+            assert np.array_equal(hi.astype(np.float16).astype(np.float32), np.where(hi >= 2.0 ** -14, hi, hi.astype(np.float16).astype(np.float32)))
+            O[g] += (hi.astype(np.float16).astype(np.float64) + lo) @ b[cols]
+            ks[g] += p.astype(np.float64).sum(1)
+    rmax = ref.max(0)
+    w = np.exp2(ref - rmax[None, :])
+    got = (w[:, :, None] * O).sum(0) / (w * ks).sum(0)[:, None]
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
