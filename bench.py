@@ -22,8 +22,10 @@ no collective.  Rank 0 prints ONE JSON line.
             evaluation per TWO pairs, so its peak is 32 pairs/clk/SM; `frac` is against that and
             `frac_vs_one_eval_per_pair` against the 16 pairs/clk/SM figure of the general kernel
   cpu_baseline / --impl reference
-            the reference algorithm (NumPy port in oracle/, the reference itself is pure Python
-            and does not travel to the GPU box) on a bounded row sample, all host cores
+            the reference's own BruteForceProductBLAS (float32, fast_sqdists=True), imported from the copy
+            of the reference tree that __graft_entry__.build() stages in the git-ignored baseline/_ref
+            (kind "reference"), on a bounded row sample with all host cores; the NumPy port in oracle/
+            (kind "port") only when that tree is absent
 """
 import argparse
 import json
