@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <mutex>
+#include <vector>
 
 #include "kprod_direct.cuh"
 #include "kprod_sym.cuh"
@@ -93,15 +95,62 @@ struct DirectPlan {
     size_t stats_bytes, rec_bytes, partial_bytes, counter_bytes, total_bytes;
 };
 
-static int device_sm_count(int* sms) {
-    static int cached_dev = -1, cached = 0;
+// ---- per-(function, device) launch state (declared in kmb_common.cuh) ---------------------------
+namespace {
+struct FuncState { const void* fn; int dev, smem, threads, per_sm; };
+std::mutex g_func_mutex;
+std::vector<FuncState> g_func_state;
+int g_sm_count[64];   // 0 = not asked yet
+
+FuncState* func_state(const void* fn, int dev) {   // g_func_mutex held
+    for (FuncState& f : g_func_state)
+        if (f.fn == fn && f.dev == dev) return &f;
+    g_func_state.push_back(FuncState{fn, dev, 0, 0, 0});
+    return &g_func_state.back();
+}
+}  // namespace
+
+int ensure_dyn_smem(const void* fn, int smem_bytes) {
     int dev = 0;
     KMB_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev != cached_dev) {
-        KMB_CUDA_CHECK(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
-        cached_dev = dev;
+    std::lock_guard<std::mutex> lock(g_func_mutex);
+    FuncState* f = func_state(fn, dev);
+    if (f->smem < smem_bytes) {
+        KMB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        f->smem = smem_bytes;
+        f->per_sm = 0;
     }
-    *sms = cached;
+    return KMB_OK;
+}
+
+int resident_ctas(const void* fn, int threads, int smem_bytes, int* per_sm) {
+    if (int rc = ensure_dyn_smem(fn, smem_bytes)) return rc;
+    int dev = 0;
+    KMB_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_func_mutex);
+    FuncState* f = func_state(fn, dev);
+    if (f->per_sm == 0 || f->threads != threads) {
+        int n = 0;
+        KMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, threads, smem_bytes));
+        if (n < 1) return set_error(KMB_ERR_CUDA, "kernel does not fit on an SM (%d threads, smem %d B)", threads, smem_bytes);
+        f->threads = threads;
+        f->per_sm = n;
+    }
+    *per_sm = f->per_sm;
+    return KMB_OK;
+}
+
+int device_sm_count(int* sms) {
+    int dev = 0;
+    KMB_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_func_mutex);
+    if (dev < 0 || dev >= 64 || g_sm_count[dev] == 0) {
+        int n = 0;
+        KMB_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        if (dev < 0 || dev >= 64) { *sms = n; return KMB_OK; }
+        g_sm_count[dev] = n;
+    }
+    *sms = g_sm_count[dev];
     return KMB_OK;
 }
 
@@ -221,17 +270,10 @@ static int run_direct(const float* x, const float* y, const float* b, float* out
         count_launch();
     }
 
-    // resident CTAs per SM of each instantiation (cached per kernel function)
-    static const void* occ_func[128];
-    static int occ_val[128], occ_n = 0;
+    // resident CTAs per SM of each instantiation (cached per kernel function and device)
     auto resident = [&](const DirectEntry& ent, int* per_sm) -> int {
-        for (int i = 0; i < occ_n; ++i)
-            if (occ_func[i] == ent.func) { *per_sm = occ_val[i]; return KMB_OK; }
-        KMB_CUDA_CHECK(cudaFuncSetAttribute(ent.func, cudaFuncAttributeMaxDynamicSharedMemorySize, ent.SMEM));
-        KMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, ent.func, ent.THREADS, ent.SMEM));
-        if (*per_sm < 1) return set_error(KMB_ERR_CUDA, "kernel does not fit on an SM (smem %d B)", ent.SMEM);
+        if (int rc = resident_ctas(ent.func, ent.THREADS, ent.SMEM, per_sm)) return rc;
         if (*per_sm > 2) *per_sm = 2;
-        if (occ_n < 128) { occ_func[occ_n] = ent.func; occ_val[occ_n++] = *per_sm; }
         return KMB_OK;
     };
 
@@ -375,10 +417,10 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
     g_launches = 0;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (int rc = check_product_args(N, M, D, E, kernel_id, flags, path)) return rc;
+    if (N == 0) return KMB_OK;   // an empty row shard (x and out may then be NULL: empty tensors have no storage)
     if (!x || !y || !out) return set_error(KMB_ERR_INVALID, "x, y and out must not be NULL");
     const bool density = flags & KMB_FLAG_DENSITY;
     if (!density && !b) return set_error(KMB_ERR_INVALID, "b is NULL without KMB_FLAG_DENSITY");
-    if (N == 0) return KMB_OK;
 
     if ((flags & KMB_FLAG_NORMALIZE_ROWS) && density) {  // bruteforce.py:134-138
         fill_kernel<<<static_cast<unsigned>((N + 255) / 256), 256, 0, stream>>>(out, N, 1.0f);
@@ -429,9 +471,9 @@ int kmb_product_f64(const double* x, const double* y, const double* b, double* o
                     int kernel_id, int flags, int64_t row_offset, void* stream_) {
     g_launches = 0;
     if (int rc = check_product_args(N, M, D, E, kernel_id, flags, KMB_PATH_AUTO)) return rc;
+    if (N == 0) return KMB_OK;
     if (!x || !y || !out) return set_error(KMB_ERR_INVALID, "x, y and out must not be NULL");
     if (!(flags & KMB_FLAG_DENSITY) && !b) return set_error(KMB_ERR_INVALID, "b is NULL without KMB_FLAG_DENSITY");
-    if (N == 0) return KMB_OK;
     return product_f64(x, y, b, out, N, M, D, E, kernel_id, flags, row_offset, static_cast<cudaStream_t>(stream_));
 }
 

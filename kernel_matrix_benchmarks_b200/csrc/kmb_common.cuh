@@ -10,6 +10,12 @@ namespace kmb {
 // ---- host-side error plumbing (defined in kmb_api.cu) -------------------------------------
 int set_error(int code, const char* fmt, ...);
 void count_launch(int n = 1);
+// Per-(kernel function, device) launch state, thread-safe (kmb_api.cu).  cudaFuncSetAttribute is a per-device
+// setting and occupancy a per-device answer, so neither may be cached per process: one process may drive
+// several GPUs (B200Product(n_gpus=...), one host thread or many).
+int ensure_dyn_smem(const void* fn, int smem_bytes);                             // opt-in dynamic shared memory
+int resident_ctas(const void* fn, int threads, int smem_bytes, int* per_sm);     // also ensures the opt-in
+int device_sm_count(int* sms);
 
 #define KMB_CUDA_CHECK(expr)                                                                         \
     do {                                                                                             \

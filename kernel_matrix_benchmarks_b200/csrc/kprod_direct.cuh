@@ -550,13 +550,8 @@ struct DirectEntry {
 
 template <class C>
 cudaError_t launch_direct(const DirectParams& P, int grid, cudaStream_t stream) {
-    static bool attr_set = false;  // per instantiation; set once per process (single device family)
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kprod_direct_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             C::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (ensure_dyn_smem(reinterpret_cast<const void*>(&kprod_direct_kernel<C>), C::SMEM_BYTES) != KMB_OK)
+        return cudaErrorInvalidValue;   // message already set
     kprod_direct_kernel<C><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(P);
     return cudaGetLastError();
 }

@@ -7,15 +7,9 @@ namespace {
 
 template <class C>
 int sym_grid_of(int sms, int* grid) {
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        KMB_CUDA_CHECK(cudaFuncSetAttribute(kprod_sym_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        int n = 0;
-        KMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kprod_sym_kernel<C>, C::THREADS, C::SMEM_BYTES));
-        if (n < 1) return set_error(KMB_ERR_CUDA, "symmetric kernel does not fit on an SM (smem %d B)", C::SMEM_BYTES);
-        per_sm = n > 2 ? 2 : n;
-    }
-    *grid = sms * per_sm;
+    int per_sm = 0;
+    if (int rc = resident_ctas(reinterpret_cast<const void*>(&kprod_sym_kernel<C>), C::THREADS, C::SMEM_BYTES, &per_sm)) return rc;
+    *grid = sms * (per_sm > 2 ? 2 : per_sm);
     return KMB_OK;
 }
 

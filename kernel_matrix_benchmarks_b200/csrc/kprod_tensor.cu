@@ -1046,11 +1046,7 @@ template <int EP, int KID, bool NORM, int ELT>
 int launch_one(const CUtensorMap* maps, const tc::Params& P, int grid, cudaStream_t stream) {
     using C = tc::Cfg<EP, KID, NORM>;
     auto fn = tc::kprod_tensor_kernel<EP, KID, NORM, ELT>;
-    static bool attr = false;
-    if (!attr) {
-        KMB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr = true;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(fn), C::SMEM_BYTES)) return rc;
     fn<<<grid, tc::THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], P);
     KMB_CUDA_CHECK(cudaGetLastError());
     return KMB_OK;
@@ -1060,11 +1056,7 @@ template <int EP, int KID, bool NORM>
 int launch_pair_one(const CUtensorMap* maps, const tc::Params& P, int grid, cudaStream_t stream) {
     using C = tc::pair::Cfg2<EP, KID, NORM>;
     auto fn = tc::pair::kprod_tensor_pair_kernel<EP, KID, NORM>;
-    static bool attr = false;
-    if (!attr) {
-        KMB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr = true;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(fn), C::SMEM_BYTES)) return rc;
     fn<<<grid, tc::THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], P);
     KMB_CUDA_CHECK(cudaGetLastError());
     return KMB_OK;

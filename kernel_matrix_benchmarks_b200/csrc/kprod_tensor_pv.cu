@@ -548,11 +548,7 @@ int plan_pv(int64_t N, int64_t M, int D, int E, PvPlan* pl) {
 template <int KID, bool NORM>
 int launch_pv(const CUtensorMap* m, const pv::Params& P, int grid, int smem, cudaStream_t stream) {
     auto fn = pv::kprod_tensor_pv_kernel<KID, NORM>;
-    static int attr_smem = 0;
-    if (attr_smem < smem) {
-        KMB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(fn), smem)) return rc;
     fn<<<grid, pv::THREADS, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
     KMB_CUDA_CHECK(cudaGetLastError());
     return KMB_OK;

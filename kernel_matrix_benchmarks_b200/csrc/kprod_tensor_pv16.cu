@@ -720,19 +720,11 @@ template <int KID, bool NORM>
 int launch_pv16(const CUtensorMap* m, const pv16::Params& P, int grid, int smem, bool pair, cudaStream_t stream) {
     if (pair) {
         auto fn = pv16::kprod_tensor_pv16_pair_kernel<KID, NORM>;
-        static int attr_smem = 0;
-        if (attr_smem < smem) {
-            KMB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_smem = smem;
-        }
+        if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(fn), smem)) return rc;
         fn<<<grid, pv16::THREADS, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
     } else {
         auto fn = pv16::kprod_tensor_pv16_kernel<KID, NORM>;
-        static int attr_smem = 0;
-        if (attr_smem < smem) {
-            KMB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_smem = smem;
-        }
+        if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(fn), smem)) return rc;
         fn<<<grid, pv16::THREADS, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
     }
     KMB_CUDA_CHECK(cudaGetLastError());

@@ -117,6 +117,17 @@ def activate(reference=None, extra_datasets=True):
     if REPO not in sys.path:
         sys.path.insert(1, REPO)
     shimmed = install_import_shims()
+    if "h5py" in shimmed or os.environ.get("KMB_OFFLINE", "1") != "0":
+        # get_dataset (datasets.py:106-109) first fetches http://kernel-matrix-benchmarks.com/datasets/<name>.hdf5 over
+        # plain HTTP and opens whatever arrived.  The stand-in cannot read real HDF5 files and this harness is the offline
+        # one: refuse the download so that get_dataset falls through to creating the dataset locally (:113-117).
+        import kernel_matrix_benchmarks.datasets as ref_datasets
+
+        def _refuse_download(src, dst):
+            if not os.path.exists(dst):
+                raise OSError(f"offline harness: not downloading {src}")
+
+        ref_datasets.download = _refuse_download
     if extra_datasets:
         from . import datasets_ext
 

@@ -12,17 +12,104 @@ calls they make are few:
 * ``f.create_group(name)`` with its own ``attrs`` (plotting/metrics.py:47-58)
 
 ``File`` below keeps one tree of ``{"attrs": {}, "items": {}}`` nodes in memory and
-pickles it on ``close()`` when opened for writing.  The on-disk bytes are *not*
+writes it on ``close()`` when opened for writing.  The on-disk bytes are *not*
 HDF5 -- this is a compatibility layer for running the unmodified harness
 offline, installed only when the real ``h5py`` cannot be imported
 (``bootstrap.install_import_shims``).
+
+On-disk format: the 16-byte magic ``MAGIC`` followed by an ``.npz`` archive (``numpy.savez``) that holds
+every array under ``a<k>`` and one member ``tree`` with the group structure and attributes as JSON.  It
+is read back with ``numpy.load(allow_pickle=False)``: nothing in a file is ever unpickled or executed, a
+file without the magic (in particular a real HDF5 file, or anything a download may have put there) is
+rejected with a clear error.
 """
 from __future__ import annotations
 
+import io
+import json
 import os
-import pickle
 
 import numpy as np
+
+MAGIC = b"KMB-H5LITE-v2\n\0\0"
+HDF5_SIGNATURE = b"\x89HDF\r\n\x1a\n"
+assert len(MAGIC) == 16
+
+
+def _encode_attr(value):
+    if isinstance(value, np.generic):
+        value = value.item()
+    if isinstance(value, np.ndarray):
+        return {"__ndarray__": value.tolist(), "dtype": value.dtype.str}
+    if isinstance(value, bytes):
+        return {"__bytes__": value.decode("latin-1")}
+    if isinstance(value, (list, tuple)):
+        return [_encode_attr(v) for v in value]
+    if value is None or isinstance(value, (bool, int, float, str)):
+        return value
+    raise TypeError(f"h5lite: cannot store an attribute of type {type(value).__name__}")
+
+
+def _decode_attr(value):
+    if isinstance(value, dict):
+        if "__ndarray__" in value:
+            return np.array(value["__ndarray__"], dtype=np.dtype(value["dtype"]))
+        if "__bytes__" in value:
+            return value["__bytes__"].encode("latin-1")
+        raise ValueError("h5lite: malformed attribute")
+    if isinstance(value, list):
+        return [_decode_attr(v) for v in value]
+    return value
+
+
+def _dump(node, arrays):
+    """Tree -> JSON-able structure; arrays are moved to ``arrays`` and referenced by key."""
+    items = {}
+    for name, item in node["items"].items():
+        if isinstance(item, dict):
+            items[name] = {"group": _dump(item, arrays)}
+        else:
+            a = np.asarray(item)
+            if a.dtype == object:
+                raise TypeError(f"h5lite: cannot store an object array ({name})")
+            key = f"a{len(arrays)}"
+            arrays[key] = a
+            items[name] = {"array": key}
+    return {"attrs": {k: _encode_attr(v) for k, v in node["attrs"].items()}, "items": items}
+
+
+def _restore(desc, arrays):
+    node = _new_node()
+    for k, v in desc["attrs"].items():
+        node["attrs"][k] = _decode_attr(v)
+    for name, item in desc["items"].items():
+        node["items"][name] = _restore(item["group"], arrays) if "group" in item else arrays[item["array"]]
+    return node
+
+
+def _read_file(name):
+    with open(name, "rb") as fh:
+        head = fh.read(16)
+        if head[:8] == HDF5_SIGNATURE:
+            raise OSError(f"{name} is a real HDF5 file; the offline h5py stand-in cannot read it (install h5py)")
+        if head != MAGIC:
+            raise OSError(f"{name} is not an h5lite file (bad magic); refusing to parse it")
+        payload = io.BytesIO(fh.read())
+    with np.load(payload, allow_pickle=False) as z:
+        arrays = {k: z[k] for k in z.files if k != "tree"}
+        desc = json.loads(bytes(z["tree"]).decode("utf-8"))
+    return _restore(desc, arrays)
+
+
+def _write_file(name, node):
+    arrays = {}
+    desc = _dump(node, arrays)
+    arrays["tree"] = np.frombuffer(json.dumps(desc).encode("utf-8"), dtype=np.uint8)
+    tmp = name + ".tmp"
+    with open(tmp, "wb") as fh:
+        fh.write(MAGIC)
+        np.savez(fh, **arrays)
+    os.replace(tmp, name)
 
 
 class _Attrs(dict):
@@ -110,8 +197,7 @@ class File(Group):
         if mode == "w" or (mode == "a" and not os.path.exists(name)):
             node = _new_node()
         else:
-            with open(name, "rb") as fh:
-                node = pickle.load(fh)
+            node = _read_file(name)
         super().__init__(node)
 
     def _require_writable(self):
@@ -120,10 +206,7 @@ class File(Group):
 
     def flush(self):
         if self.mode != "r":
-            tmp = self.filename + ".tmp"
-            with open(tmp, "wb") as fh:
-                pickle.dump(self._node, fh, protocol=pickle.HIGHEST_PROTOCOL)
-            os.replace(tmp, self.filename)
+            _write_file(self.filename, self._node)
 
     def close(self):
         if self._open:

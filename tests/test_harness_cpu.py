@@ -42,6 +42,43 @@ def test_h5lite_roundtrip(tmp_path):
     assert "metrics" not in h5lite.File(fn, "r")
 
 
+def test_h5lite_never_unpickles_and_rejects_foreign_files(tmp_path):
+    """The stand-in parses only its own format (magic + npz read with allow_pickle=False): a pickle, a real HDF5
+    file or a download that happens to sit at the dataset path is refused, never executed."""
+    import pickle
+
+    evil = tmp_path / "evil.hdf5"
+    evil.write_bytes(pickle.dumps({"attrs": {}, "items": {}}))
+    with pytest.raises(OSError, match="not an h5lite file"):
+        h5lite.File(str(evil), "r")
+    real = tmp_path / "real.hdf5"
+    real.write_bytes(h5lite.HDF5_SIGNATURE + b"\0" * 64)
+    with pytest.raises(OSError, match="real HDF5 file"):
+        h5lite.File(str(real), "r")
+    # object arrays (the one way to smuggle a pickle into an npz) cannot be written either
+    with pytest.raises(TypeError):
+        with h5lite.File(str(tmp_path / "o.hdf5"), "w") as f:
+            f["x"] = np.array([{"a": 1}], dtype=object)
+    # attributes survive as plain scalars / strings / arrays
+    fn = str(tmp_path / "a.hdf5")
+    with h5lite.File(fn, "w") as f:
+        f.attrs["k"], f.attrs["n"], f.attrs["flag"], f.attrs["v"] = "gaussian", np.int64(3), np.bool_(True), np.arange(3.0)
+        g = f.create_group("metrics")
+        g.attrs["rmse"] = np.float64(0.5)
+    f = h5lite.File(fn, "r")
+    assert f.attrs["k"] == "gaussian" and f.attrs["n"] == 3 and f.attrs["flag"] is True
+    assert np.array_equal(f.attrs["v"], np.arange(3.0)) and f["metrics"].attrs["rmse"] == 0.5
+
+
+def test_offline_harness_refuses_to_download(tmp_path):
+    """get_dataset (datasets.py:106-109) tries an HTTP download first; the offline harness must not."""
+    bootstrap.activate()
+    import kernel_matrix_benchmarks.datasets as ref_datasets
+
+    with pytest.raises(OSError, match="not downloading"):
+        ref_datasets.download("http://kernel-matrix-benchmarks.com/datasets/x.hdf5", str(tmp_path / "x.hdf5"))
+
+
 def test_shims_do_not_shadow_real_modules():
     shimmed = bootstrap.install_import_shims()
     import numpy  # noqa: F401  (a real module is never replaced)
