@@ -26,6 +26,12 @@ no collective.  Rank 0 prints ONE JSON line.
             of the reference tree that __graft_entry__.build() stages in the git-ignored baseline/_ref
             (kind "reference"), on a bounded row sample with all host cores; the NumPy port in oracle/
             (kind "port") only when that tree is absent
+  parity    sampled target rows of the TIMED output (and of the e2e result) against the float64 C oracle
+            (oracle/kprod_ref.c -- the checker, never the thing measured), at every N: rel_l2, rows, tol
+  configs   the other BASELINE.json configs on the same line (skip with --no-configs): C1 (N=M=10^4), C3 (D=784,
+            tensor path), C4 (D=E=64 attention, tensor path), C5 (CG solve, N=10^6) through the plugin API, each
+            with ms, its roofline (SURVEY.md section 8d formulas) and oracle parity on sampled rows; under
+            torchrun C3/C4 shard target rows and C5 runs the solver across the ranks
 """
 import argparse
 import json
@@ -39,6 +45,7 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
+sys.path.insert(1, os.path.join(REPO, "tools"))
 
 METRIC = "gaussian_kernel_product_gpairs_per_s"
 UNIT = "Gpairs/s"
@@ -57,6 +64,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--path", default="auto", choices=["auto", "direct"],
                     help="auto: symmetric kernel (targets == sources); direct: general kernel, rows sharded")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1/C3/C4/C5 block")
+    ap.add_argument("--configs", default="c1,c3,c4,c5", help="which of c1,c3,c4,c5 to run beside the headline")
+    ap.add_argument("--parity-rows", type=int, default=256, help="sampled rows checked against the C oracle")
     return ap.parse_args()
 
 
@@ -95,10 +105,28 @@ def measured_traffic(n, world, sym):
         with open(os.path.join(REPO, "profiles", name)) as f:
             t = json.load(f)
         if t["N"] == n and world == 1:
-            return t["dram_bytes_per_launch"]
+            return t["dram_bytes_per_launch"], f"ncu-captured ({t['source']}), not measured in this run"
     except Exception:
         pass
-    return None
+    return None, "none: no ncu capture of this kernel on this workload"
+
+
+def oracle_parity(kernel, y, x, b, got_rows, rows, tol, normalize_rows=False):
+    """Sampled target rows of a GPU result against the float64 C oracle (oracle/kprod_ref.c, pinned to the reference's
+    golden vectors by tests/test_oracle_c.py).  The oracle is the checker here, outside every timed region."""
+    from oracle import c_oracle
+
+    t0 = time.perf_counter()
+    want = c_oracle.kernel_product(kernel, y, x, b, normalize_rows=normalize_rows, rows=rows)
+    got = np.asarray(got_rows, dtype=np.float64).reshape(want.shape)
+    rel = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    return {"rel_l2": rel, "rows": int(len(rows)), "tol": tol, "ok": bool(rel <= tol),
+            "checker": "oracle/kprod_ref.c float64, all sources", "seconds": round(time.perf_counter() - t0, 2)}
+
+
+def sample_rows(n, k, seed=2):
+    k = int(min(n, k))
+    return np.sort(np.random.RandomState(seed).choice(n, k, replace=False))
 
 
 # ------------------------------------------------------------------------------------ CPU arm
@@ -164,7 +192,30 @@ def _cpu_sample_text(kind):
             "single-threaded")
 
 
+def host_threads():
+    """Threads the BLAS pool actually has (what `cores` reports)."""
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = [p["num_threads"] for p in threadpool_info() if p.get("user_api") == "blas"]
+        return int(max(n)) if n else os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
+def use_all_host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would hold the reference's OpenBLAS calls to
+    one thread (round 1: 0.247 instead of 0.317 Gpairs/s).  The CPU arm is meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count())
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] could not raise the BLAS thread limit ({e})", file=sys.stderr)
+
+
 def cpu_baseline(ds, n_rows):
+    use_all_host_threads()
     rows = np.random.RandomState(1).choice(ds.N, n_rows, replace=False)
     rows.sort()
     secs, kind = cpu_reference_sample(ds, rows)
@@ -172,7 +223,7 @@ def cpu_baseline(ds, n_rows):
     return {
         "value": pairs / secs / 1e9,
         "unit": UNIT,
-        "cores": os.cpu_count(),
+        "cores": host_threads(),
         "kind": kind,
         "sample": f"{n_rows} target rows x {ds.M} sources ({pairs:.2e} pairs, {secs:.1f} s), " + _cpu_sample_text(kind),
     }
@@ -192,6 +243,7 @@ def run_reference_arm(args):
         return
     from kernel_matrix_benchmarks_b200 import datasets
 
+    use_all_host_threads()
     ds = datasets.config_c2(args.n)
     n_rows = pick_cpu_rows(ds, args.cpu_rows)
     rows = np.sort(np.random.RandomState(1).choice(ds.N, n_rows, replace=False))
@@ -207,8 +259,12 @@ def run_reference_arm(args):
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args.n, args.gpus, args.path),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "sample": sample},
+        "data": "synthetic",
+        "config": dict(workload_config(args.n, args.gpus, args.path),
+                       path="reference CPU: BruteForceProductBLAS(float32, fast_sqdists=True), dense blocks of 500 target rows"
+                       if kind == "reference" else "NumPy port of bruteforce.py (oracle/), float32, fast_sqdists=True",
+                       sharding="host cores only (rank 0); no GPU on this arm", l2="n/a (CPU arm)"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -362,11 +418,29 @@ def run_b200_arm(args):
         g1.record()
         barrier()
         g_ms = max_over_ranks(g0.elapsed_time(g1) / 2)
-        general = {"value": pairs_total / (g_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": g_ms,
+        g_main_ms = max_over_ranks(product.last_main_kernel_ms())
+        general = {"value": pairs_total / (g_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": g_ms, "kernel_ms": g_main_ms,
+                   "timed": "2 whole calls (bounding-box statistics + source packing + main kernel), L2 warm; kernel_ms = the main kernel alone",
                    "kernel": "kprod_direct_kernel<D=3,E=1,R=4,gaussian,product form,512 thr>, target rows sharded"}
         # parity of the two kernels on this rank's rows (the tests hold both to the oracle)
         diff = (out[lo:hi] - out_g).double().norm() / out_g.double().norm()
         general["rel_l2_symmetric_vs_general"] = float(diff)
+
+    # ---- parity of the timed output against the float64 C oracle on sampled rows (every N) -----------
+    prows = sample_rows(N, args.parity_rows)
+    if sym or world == 1:
+        timed_rows = out[torch.as_tensor(prows, device=dev)].cpu().numpy()
+    else:   # row shards: bring the sampled rows together (untimed)
+        mine = torch.zeros((len(prows), 1), dtype=torch.float32, device=dev)
+        sel = torch.as_tensor(prows, device=dev)
+        inside = (sel >= lo) & (sel < hi)
+        mine[inside] = out[sel[inside] - lo]
+        dist.all_reduce(mine)
+        timed_rows = mine.cpu().numpy()
+    parity = None
+    if rank == 0:
+        parity = oracle_parity("gaussian", ds.source_points, None, ds.source_signal, timed_rows, prows, tol=1e-5)
+        parity["of"] = "the device-resident output of the last timed step"
 
     # ---- end-to-end arm: plugin API, host float64 arrays in, host float64 result out ------------
     e2e = None
@@ -408,6 +482,9 @@ def run_b200_arm(args):
             "api": "B200Product.prepare_data/fit/prepare_query/query/get_result, host float64 in/out",
         }
         assert res.shape == (n_out, 1)
+        if rank == 0:
+            sel = prows if (sym or world == 1) else prows[prows < hi]
+            e2e["parity"] = oracle_parity("gaussian", ds.source_points, None, ds.source_signal, res[sel], sel, tol=1e-5)
 
     if rank == 0:
         peaks, peaks_src = read_peaks()
@@ -428,7 +505,8 @@ def run_b200_arm(args):
             "frac": achieved / peak,
             "frac_vs_one_eval_per_pair": achieved / peak_evals,
             "kernel_evals_per_pair": evals_per_pair,
-            "traffic": measured_traffic(args.n, world, sym),
+            "traffic": measured_traffic(args.n, world, sym)[0],
+            "traffic_source": measured_traffic(args.n, world, sym)[1],
             "kernel": kernel_name,
             "kernel_ms": main_ms,
             "peak_basis": f"16 kernel evaluations (MUFU.EX2)/clk/SM x {info['sm_count']} SMs x {sm_max:.0f} MHz (clocks.max.sm) "
@@ -442,10 +520,21 @@ def run_b200_arm(args):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args.n, world, args.path),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": roofline,
+            "roofline": roofline, "parity": parity,
         }
         if general is not None:
             line["general_kernel"] = general
+    # ---- the other BASELINE configs, same process group, same line ---------------------------------
+    del out, ws, flush
+    configs = None
+    if not args.no_configs:
+        from bench_configs import run_config_block   # tools/bench_configs.py
+
+        configs = run_config_block([c.strip() for c in args.configs.split(",") if c.strip()], local_rank=local_rank, rank=rank,
+                                   world=world, parity_rows=args.parity_rows, peaks=read_peaks())
+    if rank == 0:
+        if configs is not None:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(ds, pick_cpu_rows(ds, args.cpu_rows))
         print(json.dumps(line))

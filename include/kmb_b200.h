@@ -128,7 +128,7 @@ int kmb_product_prepare_f32(const float* x, const float* y, int64_t n_targets, i
  *
  * Same arithmetic as kmb_product_f32(y, y, b, ...) -- kernel_matrix + K @ b of bruteforce.py:25-58,
  * 153 with target_points = None (:27-28, :113-120) -- but K's symmetry is used: the n x n pair matrix
- * is cut into (2048 rows x 512 sources) units, only units on or above the block diagonal are
+ * is cut into (4096 rows x 512 sources) units, only units on or above the block diagonal are
  * evaluated, and each kernel value is added to both its row's and its column's sum.  The unit list is
  * split into `n_parts` equal contiguous ranges; this call evaluates range `part` and writes the sums it
  * produced to ALL n entries of out (zero where it contributed nothing).  With n_parts > 1 (one part

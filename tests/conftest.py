@@ -21,6 +21,11 @@ def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 
 
+def product_golden_names():
+    """Fixtures of product / attention / density tasks (the others pin the solver: solver_*, refsolve_*)."""
+    return [n for n in golden_names() if not n.startswith(("solver_", "refsolve_"))]
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     g = {k: z[k] for k in z.files}

@@ -61,8 +61,18 @@ def reference_solver(kernel, points, rhs, precision="float64"):
     return algo.get_result()
 
 
+FORCE = "--force" in sys.argv   # default: only write fixtures that do not exist yet (committed ones stay byte-identical)
+
+
+def exists(name):
+    return os.path.exists(os.path.join(HERE, name + ".npz")) and not FORCE
+
+
 def save(name, ds, **outputs):
     path = os.path.join(HERE, name + ".npz")
+    if exists(name):
+        print(f"{name:45s} kept")
+        return
     np.savez_compressed(
         path,
         kernel=ds.kernel,
@@ -159,6 +169,25 @@ def main():
             lam=np.float64(lam),
             spd_solution=orc.kernel_solve_spd(kernel, ds.source_points, rhs, lam),
         )
+
+    # 10. attention with E = 64 -- the signal width of config C4 (the kernel with both contractions on the tensor
+    #     cores, kprod_tensor_pv16), from the reference class
+    for kernel in ("gaussian", "absolute-exponential"):
+        name = f"attention_{kernel.replace('-', '')}_d64_e64"
+        if not exists(name):
+            ds = gen.uniform_cube(320, 64, gen.scaled_radius(64), kernel, "attention", normalize_rows=True, n_targets=160, signal_dim=64)
+            save(name, ds, truth=reference_product(ds))
+
+    # 11. the reference's OWN solve: K b = a with no regularisation (bruteforce.py:205-207, lstsq), on the point sets
+    #     its solver datasets use (datasets.py:391-413: Fibonacci-sphere points for "solver-sphere-*-inverse-distance"
+    #     AND for "solver-cube-*-gaussian"), right-hand side a = K b as write_output stores it (datasets.py:180-195)
+    for label, kernel in (("sphere_invdist", "inverse-distance"), ("cube_gaussian", "gaussian")):
+        name = f"refsolve_{label}_d3"
+        if not exists(name):
+            ds = gen.uniform_sphere(600, 1.0, kernel, "solver", seed=11)
+            Kb = reference_product(ds)
+            save(name, ds, rhs=Kb, lam=np.float64(0.0), ref_lstsq=reference_solver(kernel, ds.source_points, Kb),
+                 ref_lstsq_f32=reference_solver(kernel, ds.source_points, Kb, "float32"))
 
 
 if __name__ == "__main__":

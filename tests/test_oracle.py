@@ -8,9 +8,9 @@ import numpy as np
 import pytest
 
 from oracle import bruteforce_oracle as orc
-from conftest import golden_names, load_golden
+from conftest import golden_names, load_golden, product_golden_names
 
-PRODUCT_CASES = [n for n in golden_names() if not n.startswith("solver_")]
+PRODUCT_CASES = product_golden_names()
 SOLVER_CASES = [n for n in golden_names() if n.startswith("solver_")]
 
 
@@ -125,3 +125,20 @@ def test_solver_oracle(name):
     # rhs = K b + lam b  =>  the SPD solution is the generator's signal
     cond_limited = 1e-6 if lam >= 1 else 1e-3
     assert orc.rel_l2(x_spd, g["source_signal"]) <= cond_limited
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith("refsolve_")])
+def test_oracle_reproduces_the_reference_solve(name):
+    """The reference's own system K b = a, no regularisation (bruteforce.py:205-207), on its solver datasets' point
+    sets (datasets.py:391-413).  Inverse-distance: indefinite but well conditioned, lstsq returns the generating b;
+    Gaussian: numerically singular, only the residual is reproducible."""
+    g = load_golden(name)
+    a, x_ref = g["rhs"], g["ref_lstsq"]
+    assert orc.rel_l2(orc.kernel_product(g["kernel"], g["source_points"], None, g["source_signal"]), a) <= 1e-13
+    x_orc = orc.kernel_solve_lstsq(g["kernel"], g["source_points"], a)
+    for x in (x_ref, x_orc):
+        assert orc.rel_l2(orc.regularised_matvec(g["kernel"], g["source_points"], x, 0.0), a) <= 1e-9
+    if g["kernel"] == "inverse-distance":
+        assert orc.rel_l2(x_ref, g["source_signal"]) <= 1e-9 and orc.rel_l2(x_orc, x_ref) <= 1e-9
+    else:
+        assert orc.rel_l2(x_ref, g["source_signal"]) >= 0.1   # the ill-posedness itself is part of what is pinned

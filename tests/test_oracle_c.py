@@ -4,9 +4,9 @@ import pytest
 
 from oracle import bruteforce_oracle as orc
 from oracle import c_oracle
-from conftest import golden_names, load_golden
+from conftest import golden_names, load_golden, product_golden_names
 
-CASES = [n for n in golden_names() if not n.startswith("solver_")]
+CASES = product_golden_names()
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -8,7 +8,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden
+from conftest import golden_names, load_golden, product_golden_names
 from oracle import bruteforce_oracle as orc
 from oracle import c_oracle
 
@@ -16,8 +16,8 @@ pytestmark = pytest.mark.gpu
 
 TOL_DIRECT = 1e-5
 TOL_TENSOR = 1e-4
-PRODUCT_CASES = [n for n in golden_names() if not n.startswith("solver_")]
-TENSOR_PATH_BUILT = True  # flipped when kmb_product_f32 grows KMB_PATH_TENSOR_3XTF32
+PRODUCT_CASES = product_golden_names()
+TENSOR_PATH_BUILT = True  # both tensor paths (3xFP16 planes, 3xTF32 planes) are built; False would xfail the D > 16 goldens
 
 
 def run_plugin(kernel, y, x, b, *, same_points=False, normalize_rows=False, density=False, path="auto"):
@@ -377,6 +377,45 @@ def test_config_c4_reduced():
     assert err <= TOL_TENSOR
     const, _ = run_plugin(ds.kernel, ds.source_points, ds.target_points, np.full((ds.M, 1), -2.5), normalize_rows=True)
     assert np.abs(const + 2.5).max() <= 2.5e-5
+
+
+def test_config_c4_full_size_sampled():
+    """BASELINE config 4 at FULL size (N = M = 262 144, D = 64, E = 64, row-normalised exponential kernel): 2048 row
+    tiles in 14 waves of CTA pairs -- the schedule the reduced case never reaches.  256 sampled target rows (every
+    1024th, shifted so that first/last tiles and both CTAs of a pair are hit) against the float64 C oracle."""
+    from kernel_matrix_benchmarks_b200 import datasets
+
+    ds = datasets.config_c4()
+    assert (ds.N, ds.M, ds.D, ds.E) == (262144, 262144, 64, 64)
+    rows = np.unique(np.concatenate((np.arange(0, ds.N, 1024) + (np.arange(256) * 37) % 1024, [0, 127, 128, 255, ds.N - 1])))
+    want = c_oracle.kernel_product(ds.kernel, ds.source_points, ds.target_points, ds.source_signal, normalize_rows=True, rows=rows)
+    for kernel in (ds.kernel, "gaussian"):
+        if kernel != ds.kernel:
+            want = c_oracle.kernel_product(kernel, ds.source_points, ds.target_points, ds.source_signal, normalize_rows=True, rows=rows)
+        out, extra = run_plugin(kernel, ds.source_points, ds.target_points, ds.source_signal, normalize_rows=True)
+        assert out.shape == (ds.N, ds.E) and np.isfinite(out).all()
+        err = orc.rel_l2(out[rows], want)
+        worst = np.max(np.linalg.norm(out[rows] - want, axis=1) / np.linalg.norm(want, axis=1))
+        print(f"C4 full size {kernel}: sampled rel-L2 {err:.2e} (worst row {worst:.2e}) over {len(rows)} rows {extra}")
+        assert err <= TOL_TENSOR and worst <= 5 * TOL_TENSOR
+
+
+def test_empty_row_shard_is_a_no_op():
+    """shard_bounds gives the last ranks empty shards when ceil(n / world) * rank >= n (n = 9 on 8 ranks): the C ABI
+    must treat N == 0 as a no-op even though an empty tensor has a NULL data pointer (every other rank would
+    otherwise hang in the next collective)."""
+    import torch
+    from kernel_matrix_benchmarks_b200 import product
+    from kernel_matrix_benchmarks_b200.solver import shard_bounds
+
+    y = torch.rand(9, 3, device="cuda")
+    b = torch.rand(9, 1, device="cuda")
+    lo, hi, _ = shard_bounds(9, 7, 8)
+    assert lo == hi
+    out = product.kernel_product(y[lo:hi], y, b)
+    assert out.shape == (0, 1)
+    out64 = product.kernel_product_f64(y[lo:hi].double(), y.double(), b.double())
+    assert out64.shape == (0, 1)
 
 
 # ------------------------------------------- tensor path with the second contraction on tcgen05 (E > 4)

@@ -40,6 +40,68 @@ def test_cg_matches_dense_spd_solve(name):
     assert orc.rel_l2(x, g["spd_solution"]) <= tol, extra
 
 
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith("refsolve_")])
+def test_reference_system_without_regularisation(name):
+    """lam = 0: the reference's OWN system K b = a (bruteforce.py:205-207) on the point sets of its registered solver
+    datasets (datasets.py:391-413), inputs and lstsq solution from the reference classes (tests/golden/make_golden.py).
+    Residual-pinned: |K x - a| / |a| with the float64 oracle product.  For the inverse-distance
+    kernel the system is well conditioned and x must equal the reference's lstsq answer; for the Gaussian kernel the
+    matrix is singular to working precision (the reference's own answer is 85 % away from the generating b), so
+    only the residual -- and the product K x, which is what the data determine -- can agree."""
+    g = load_golden(name)
+    assert float(g["lam"]) == 0.0
+    x, extra = run_solver(g["kernel"], g["source_points"], g["rhs"], lam=0.0, rtol=1e-6, max_iter=2000)
+    assert x.shape == g["ref_lstsq"].shape and extra["cg_converged"], extra
+    Kx = orc.regularised_matvec(g["kernel"], g["source_points"], x, 0.0)
+    res = orc.rel_l2(Kx, g["rhs"])
+    res_ref32 = orc.rel_l2(orc.regularised_matvec(g["kernel"], g["source_points"], g["ref_lstsq_f32"], 0.0), g["rhs"])
+    print(f"{name}: residual {res:.2e} (reference float32 lstsq: {res_ref32:.2e}) {extra}")
+    assert res <= 1e-5, (res, extra)
+    if g["kernel"] == "inverse-distance":
+        assert orc.rel_l2(x, g["ref_lstsq"]) <= 1e-3, extra
+    # the same through the query-args route of algos.yaml's `cg` group (lam stays 0)
+    from kernel_matrix_benchmarks_b200.algorithms.b200 import B200Solver
+
+    algo = B200Solver(kernel=g["kernel"], dimension=3, precision="float32", lam=0.0)
+    algo.set_query_arguments(rtol=1e-4, max_iter=500)
+    algo.prepare_data(source_points=g["source_points"])
+    algo.fit()
+    algo.prepare_query(target_signal=g["rhs"])
+    algo.query()
+    x4 = algo.get_result()
+    algo.done()
+    assert orc.rel_l2(orc.regularised_matvec(g["kernel"], g["source_points"], x4, 0.0), g["rhs"]) <= 5e-4
+
+
+def test_config_c5_full_size():
+    """BASELINE config 5 at FULL size: (K + I) b = a, N = 10^6, D = 3, Gaussian.  The right-hand side needs one
+    10^12-pair product, so it is built by the product under test and checked -- like the solution's residual -- on
+    512 sampled rows against the float64 C oracle (5e8 pairs each)."""
+    import torch
+    from oracle import c_oracle
+    from kernel_matrix_benchmarks_b200 import datasets, product
+
+    lam = 1.0
+    ds = datasets.config_c5(1_000_000, lam)
+    y = torch.tensor(ds.source_points, dtype=torch.float32, device="cuda")
+    b = torch.tensor(ds.source_signal, dtype=torch.float32, device="cuda")
+    rhs = (product.kernel_product(y, y, b) + lam * b).cpu().numpy().astype(np.float64)
+    del y, b
+    rows = np.sort(np.random.RandomState(5).choice(ds.N, 512, replace=False))
+    want_rhs = c_oracle.kernel_product("gaussian", ds.source_points, None, ds.source_signal, rows=rows) + lam * ds.source_signal[rows]
+    assert orc.rel_l2(rhs[rows], want_rhs) <= 1e-5
+    x, extra = run_solver("gaussian", ds.source_points, rhs, lam=lam, rtol=1e-6, max_iter=200)
+    print(f"C5 full size: {extra}")
+    assert extra["cg_converged"] and extra["cg_iterations"] <= 12, extra
+    assert extra["preconditioner"].startswith("nystrom") and extra["matvec"] == "symmetric"
+    resid = c_oracle.kernel_product("gaussian", ds.source_points, None, x, rows=rows) + lam * x[rows] - rhs[rows]
+    rel = np.linalg.norm(resid) / np.linalg.norm(rhs[rows])
+    err = orc.rel_l2(x, ds.source_signal)
+    print(f"C5 full size: oracle residual on {len(rows)} rows {rel:.2e}, rel-L2 vs generating b {err:.2e}")
+    assert rel <= 2e-5, rel
+    assert err <= 2e-3, err          # cond(K + I) ~ 1e3..1e4 times eps32
+
+
 def test_cg_multiple_right_hand_sides_and_query_args():
     from kernel_matrix_benchmarks_b200 import datasets
     from kernel_matrix_benchmarks_b200.algorithms.b200 import B200Solver
