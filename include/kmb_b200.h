@@ -142,9 +142,56 @@ int kmb_product_sym_workspace_bytes(int64_t n, int D, int part, int n_parts, siz
 int kmb_product_sym_f32(const float* y, const float* b, float* out, int64_t n, int D, int kernel_id,
                         int part, int n_parts, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- several GPUs driven by one host thread --------------------------------------------------------
+ * The reference's caller is ONE Python process that calls query() and waits (runner.py:118-148,
+ * main.py:299-308), so a plugin that uses G GPUs has to drive them from that one thread.  The calls below
+ * take one kmb_device_shard per GPU, launch every shard's product on its own device and stream, and
+ * fork/join on shard 0's stream: all work starts after what shard 0's stream held at the call and
+ * shard 0's stream continues after every shard is done -- for the caller it is as if the product had
+ * run on shard 0's stream (synchronise that one).  No host synchronisation, no NCCL: partial results
+ * cross GPUs through NVLink peer memory (kmb_enable_peer_access first).  Pointers in a shard are
+ * resident on shard.device unless stated otherwise; b and out MAY point into a peer GPU's memory.
+ */
+typedef struct {
+    int device;             /* CUDA device ordinal of this shard */
+    int flags;              /* extra per-shard flags (KMB_FLAG_PREPARED: this shard's workspace holds its prepass) */
+    const float* x;         /* rows mode: this shard's block of target rows (n_targets, D), on shard.device */
+    const float* y;         /* all source points (n_sources, D), replicated on shard.device */
+    const float* b;         /* source signal (n_sources, E); may live on shard 0's device (read once per pass by the packing /
+                               transposing kernel, over NVLink); NULL with KMB_FLAG_DENSITY */
+    float* out;             /* rows mode: where this shard's rows go -- typically a peer pointer into the gathered
+                               (N, E) result on shard 0's device (plain stores over NVLink: the gather costs nothing);
+                               symmetric mode: this shard's partial N-vector, on shard.device */
+    int64_t n_targets;      /* rows mode: rows in this shard (0 allowed) */
+    int64_t row_offset;     /* rows mode: global index of the shard's first row */
+    void* workspace;        /* on shard.device, 256-byte aligned */
+    size_t workspace_bytes;
+    void* stream;           /* a stream of shard.device */
+} kmb_device_shard;
+
+/* Peer access in both directions between all listed devices (idempotent).  KMB_ERR_UNSUPPORTED if a pair has no peer path. */
+int kmb_enable_peer_access(const int* devices, int n_devices);
+
+/* Rows mode (any kernel / path / query mode of kmb_product_f32): shard s computes its n_targets rows against all sources
+ * and stores them at shard.out.  No collective at all. */
+int kmb_product_rows_multi_f32(const kmb_device_shard* shards, int n_shards, int64_t n_sources, int D, int E, int kernel_id,
+                               int flags, int path);
+
+/* Symmetric mode (kmb_product_sym_f32 with n_parts = n_shards): shard s evaluates range s of the triangular unit list
+ * into its own partial vector shard.out (n floats on shard.device; workspace_bytes >= kmb_product_sym_workspace_bytes(n, D,
+ * s, n_shards)), then shard 0's device adds the parts in shard order (deterministic) into `out` (n floats on shard 0's
+ * device), reading the other parts through peer memory: the path's one exchange step, N floats per GPU over NVLink.
+ * With n_shards == 1 the product is written to `out` directly. */
+int kmb_product_sym_multi_f32(const kmb_device_shard* shards, int n_shards, float* out, int64_t n, int D, int kernel_id);
+
+/* out[i] = parts[0][i] + ... + parts[n_parts-1][i], fixed order; parts[k] may be peer-device pointers (16-byte aligned,
+ * n_parts <= 16).  Runs on the current device / `stream`. */
+int kmb_reduce_parts_f32(float* out, const float* const* parts, int n_parts, int64_t n, void* stream);
+
 /* out[i, :] = sum_j k(x_i, y_j) b[j, :] in double precision: the `precision=float64` variant of the
  * reference's plugin (bruteforce.py:64-87, 100-106; algos.yaml:156-162), same arithmetic as its float64
- * difference-form path (bruteforce.py:53-54).  All pointers are float64 device arrays; D <= 16; flags and
+ * difference-form path (bruteforce.py:53-54).  All pointers are float64 device arrays; any D (one row per thread for
+ * D <= 16, a tiled kernel above: what the D = 784 / D = 64 ground truth is written with); flags and
  * row_offset as kmb_product_f32.  No workspace.  Row normalisation divides by the plain row sum as the
  * reference does (a row whose kernels all underflow is 0/0 = NaN there and here).
  */
@@ -201,6 +248,18 @@ int kmb_cg_update_f32(float* x, float* r, const float* p_shard, const float* Ap,
                       void* stream);
 /* beta = rs_new/rs ; p = r + beta p */
 int kmb_cg_direction_f32(float* p_shard, const float* r, const float* rs_new, const float* rs,
+                         int64_t n_local, int E, void* stream);
+
+/* The same four steps in double precision: the `precision: float64` variant of the solver (the reference's
+ * algos.yaml:164-181 sweeps float16 / float32 / float64 for BruteForceSolverLAPACK); the matvec is kmb_product_f64. */
+int kmb_cg_init_f64(const double* a, double* x, double* r, double* p_shard, double* rs_local,
+                    int64_t n_local, int E, void* scratch, void* stream);
+int kmb_cg_shift_dot_f64(double* Ap, const double* p_shard, double lambda, double* pAp_local,
+                         int64_t n_local, int E, void* scratch, void* stream);
+int kmb_cg_update_f64(double* x, double* r, const double* p_shard, const double* Ap, const double* rs,
+                      const double* pAp, double* rs_new_local, int64_t n_local, int E, void* scratch,
+                      void* stream);
+int kmb_cg_direction_f64(double* p_shard, const double* r, const double* rs_new, const double* rs,
                          int64_t n_local, int E, void* stream);
 
 #ifdef __cplusplus

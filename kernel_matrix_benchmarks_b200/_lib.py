@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkmb_b200.so")
@@ -32,6 +32,24 @@ class DeviceInfo(ctypes.Structure):
     ]
 
 
+class DeviceShard(ctypes.Structure):
+    """kmb_device_shard (include/kmb_b200.h)."""
+
+    _fields_ = [
+        ("device", c_int),
+        ("flags", c_int),
+        ("x", c_void_p),
+        ("y", c_void_p),
+        ("b", c_void_p),
+        ("out", c_void_p),
+        ("n_targets", c_int64),
+        ("row_offset", c_int64),
+        ("workspace", c_void_p),
+        ("workspace_bytes", c_size_t),
+        ("stream", c_void_p),
+    ]
+
+
 # every symbol include/kmb_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "kmb_abi_version": (c_int, []),
@@ -50,6 +68,10 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p],
     ),
+    "kmb_enable_peer_access": (c_int, [POINTER(c_int), c_int]),
+    "kmb_product_rows_multi_f32": (c_int, [POINTER(DeviceShard), c_int, c_int64, c_int, c_int, c_int, c_int, c_int]),
+    "kmb_product_sym_multi_f32": (c_int, [POINTER(DeviceShard), c_int, c_void_p, c_int64, c_int, c_int]),
+    "kmb_reduce_parts_f32": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int64, c_void_p]),
     "kmb_product_f64": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int64, c_void_p],
@@ -66,6 +88,13 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p],
     ),
     "kmb_cg_direction_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "kmb_cg_init_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "kmb_cg_shift_dot_f64": (c_int, [c_void_p, c_void_p, c_double, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "kmb_cg_update_f64": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p],
+    ),
+    "kmb_cg_direction_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
 }
 
 _lib = None

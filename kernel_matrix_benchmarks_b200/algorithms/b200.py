@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from .. import multigpu as _multigpu
 from .. import product as _product
 from ..product import Workspace, device_info, kernel_product, kernel_product_sym_part, last_launch_count
 from ..solver import (CudaShardOps, CudaSymmetricOps, LocalComm, NystromPreconditioner, TorchDistComm, cg_solve,
@@ -96,8 +97,15 @@ class B200Product(BaseProduct):
     """On-the-fly kernel product / density / attention on one B200."""
 
     def __init__(self, *, kernel, dimension, normalize_rows=False, precision="float32", path="auto", device=0,
-                 distributed=False):
-        """``distributed=True``: one process per GPU under torch.distributed (NCCL).  Every rank is handed
+                 distributed=False, n_gpus=1):
+        """``n_gpus=G`` (constructor argument, or ``query-args: [{n_gpus: G}]`` through ``set_query_arguments``): this ONE
+        process drives devices ``device .. device+G-1`` -- the harness calls the plugin from a single thread
+        (runner.py:118-148), so this is how ``run.py --local --hardware GPU`` sweeps 1/2/4/8 GPUs.  With ``same_points``
+        Gaussian data the devices split the symmetric unit list and the first device adds the partial vectors through
+        NVLink peer memory; otherwise they split the target rows and store them straight into the first device's result
+        (multigpu.DeviceGroup; no NCCL).
+
+        ``distributed=True``: one process per GPU under torch.distributed (NCCL).  Every rank is handed
         the same arrays; with ``same_points`` data the ranks split the symmetric unit list and all-reduce
         the result, otherwise they split the target rows and ``get_result`` gathers them.  Every rank
         returns the whole (N, E) result."""
@@ -107,25 +115,59 @@ class B200Product(BaseProduct):
         if path not in _lib.PATH_IDS:
             raise ValueError(f"unknown path {path!r} (expected one of {sorted(_lib.PATH_IDS)})")
         self.dtype = _check_precision(precision, "B200Product", (np.float32, np.float64, np.float16))
-        if self.dtype == np.float64 and dimension > 16:
-            raise NotImplementedError("B200Product float64 path supports dimension <= 16.")
         _lib.load()  # fail here, loudly, if the CUDA library is absent
         if not torch.cuda.is_available():
             raise RuntimeError("B200Product needs a CUDA device; there is no CPU fallback.")
         self.path = path
         self.device = torch.device("cuda", int(device))
-        self.name = f"B200Product({np.dtype(precision).name}, path={path})"
         self.comm = TorchDistComm() if distributed else LocalComm()
-        if self.comm.world > 1:
-            self.name = f"B200Product({np.dtype(precision).name}, path={path}, gpus={self.comm.world})"
+        if distributed and int(n_gpus) > 1:
+            raise ValueError("distributed=True (one process per GPU) and n_gpus > 1 (one process, several GPUs) exclude each other")
+        self.n_gpus = _multigpu.clamp_gpus(n_gpus, self.device.index)
+        self._group = None
+        self._set_name()
         self.path_used = None
         self.workspace = Workspace()
         self.query_ms = None
         self.launches = 0
         self.res = None
 
+    def _set_name(self):
+        gpus = self.comm.world if self.comm.world > 1 else self.n_gpus
+        extra = f", gpus={gpus}" if gpus > 1 else ""
+        self.name = f"B200Product({self.dtype.name}, path={self.path}{extra})"
+
+    def set_query_arguments(self, n_gpus=None, **kwargs):
+        """``query-args`` of algos.yaml (runner.py:123, after fit() and before prepare_query()): ``n_gpus`` re-targets the
+        same fitted object at another number of GPUs; the replicas are made in prepare_query() (untimed, like every
+        host->device copy), points-only prepasses of the tensor path inside the first query with that GPU count."""
+        if n_gpus is not None:
+            if self.comm.world > 1:
+                raise ValueError("n_gpus cannot be combined with distributed=True")
+            self.n_gpus = _multigpu.clamp_gpus(n_gpus, self.device.index)
+            self._set_name()   # the name labels the stored result (runner.py:155)
+
+    def _multi(self):
+        return self.n_gpus > 1 and self.dtype != np.float64
+
+    def _setup_group(self):
+        """Replicas of the points on the group's devices (peer copies from the first device), row blocks of the targets."""
+        g = self._group
+        if g is None or g.n != self.n_gpus:
+            g = _multigpu.DeviceGroup(self.device.index, self.n_gpus)
+            self._ys = g.replicate(self.source_points)
+            if self.same_points:
+                self._bounds = [shard_bounds(self.source_points.shape[0], i, g.n)[:2] for i in range(g.n)]
+                self._xs = [self._ys[i][lo:hi] for i, (lo, hi) in enumerate(self._bounds)]
+            else:
+                self._xs, self._bounds = g.shard_rows(self.target_points)
+            g.synchronize()
+            self._group = g
+        return g
+
     def prepare_data(self, *, source_points, target_points, same_points=False, density_estimation=False):
         """Untimed host->device copy (base.py:64-67), cast to float32 as bruteforce.py:100-106 casts."""
+        self._group = None
         self.source_points = _to_device(source_points, self.device, self.dtype)
         self.same_points = bool(same_points)
         self.target_points = self.source_points if self.same_points else _to_device(target_points, self.device, self.dtype)
@@ -139,7 +181,11 @@ class B200Product(BaseProduct):
         N = self.target_points.shape[0]
         self._out_rows = N
         self._prepared = None
-        if self.dtype != np.float64:
+        if self._multi():   # n_gpus given to the constructor: replicate and prepare every device's row block here
+            g = self._setup_group()
+            g.prepare_rows(self._xs, self._ys, kernel=self.kernel, path=self.path)
+            g.synchronize()
+        elif self.dtype != np.float64:
             with torch.cuda.device(self.device):
                 self._prepared = _product.prepare_points(self._my_rows(), self.source_points, kernel=self.kernel,
                                                          path=self.path, workspace=self.workspace)
@@ -169,7 +215,31 @@ class B200Product(BaseProduct):
     def prepare_query(self, *, source_signal):
         """Untimed host->device copy of the signal (bruteforce.py:122-128)."""
         self.source_signal = None if self.density_estimation else _to_device(source_signal, self.device, self.dtype)
+        if self._multi():
+            g = self._setup_group()
+            self._bs = None if self.density_estimation else g.replicate(self.source_signal)
+            g.synchronize()
         torch.cuda.synchronize(self.device)
+
+    def _query_multi(self):
+        """n_gpus > 1 in this process (multigpu.DeviceGroup): symmetric unit list or target rows split over the devices;
+        the result is complete on the first device when its stream gets there."""
+        g = self._group
+        y0 = self.source_points
+        E = 1 if self.density_estimation else self.source_signal.shape[1]
+        N = self.target_points.shape[0]
+        self.res_device = torch.empty((N, E), dtype=torch.float32, device=self.device)
+        if self.same_points and g.symmetric_applies(y0, self.kernel, bool(self.normalize_rows), self.density_estimation, E, self.path):
+            g.product_sym(self._ys, self._bs, self.res_device)
+            self.path_used = "direct_sym"
+        else:
+            if g.prepared is None:   # n_gpus arrived as a query argument: the first query with this GPU count prepares
+                g.prepare_rows(self._xs, self._ys, kernel=self.kernel, path=self.path)
+            g.product_rows(self._xs, self._bounds, self._ys, self._bs, self.res_device, kernel=self.kernel,
+                           normalize_rows=bool(self.normalize_rows), density_estimation=self.density_estimation, path=self.path,
+                           prepared=g.prepared)
+            self.path_used = self.path
+        self.launches = g.launches
 
     def query(self):
         """Timed: the whole product, ending with a device synchronise."""
@@ -185,6 +255,8 @@ class B200Product(BaseProduct):
                     self.res_device = mine if self.comm.world == 1 else self.comm.all_gather(mine, self.target_points.shape[0])
                 elif self.comm.world > 1:
                     self._query_distributed()
+                elif self._multi():
+                    self._query_multi()
                 else:
                     E = 1 if self.density_estimation else self.source_signal.shape[1]
                     self.res_device = kernel_product(
@@ -242,6 +314,7 @@ class B200Product(BaseProduct):
             "path": self.path,
             "path_used": str(self.path_used),
             "form": self._form(),
+            "n_gpus": int(self.comm.world if self.comm.world > 1 else (self.n_gpus if self._multi() else 1)),
         }
 
     def _form(self):
@@ -249,15 +322,16 @@ class B200Product(BaseProduct):
             return "n/a"
         from ..product import direct_stats
 
-        return direct_stats(self.workspace)["form"]
+        return direct_stats(self._group.workspaces[0] if self._multi() else self.workspace)["form"]
 
     def get_memory_usage(self):
         """Host RSS as the reference reports, plus device bytes in kB."""
         return super().get_memory_usage() + torch.cuda.memory_allocated(self.device) / 1024
 
     def done(self):
-        for k in ("source_points", "target_points", "source_signal", "res_device", "_prepared"):
+        for k in ("source_points", "target_points", "source_signal", "res_device", "_prepared", "_group", "_ys", "_xs", "_bs"):
             self.__dict__.pop(k, None)
+        self._group = None
         self.workspace = Workspace()
 
     def __del__(self):  # runner.py keeps only the fastest-fit instance; the others are just dropped
@@ -276,20 +350,27 @@ class B200Solver(BaseSolver):
     """
 
     def __init__(self, *, kernel, dimension, normalize_rows=False, precision="float32", lam=0.0, rtol=1e-6,
-                 max_iter=500, path="auto", device=0, distributed=False, preconditioner="auto", precond_rank=1024):
+                 max_iter=500, path="auto", device=0, distributed=False, preconditioner="auto", precond_rank=1024, n_gpus=1):
+        """``n_gpus`` / ``distributed`` as for B200Product.  With ``n_gpus=G`` all CG vectors and the preconditioner live on
+        the first device; only the matvec (10^12 pairs at config C5) is spread over the G devices of this process
+        (multigpu.MultiDeviceSymmetricOps / MultiDeviceRowOps)."""
         super().__init__(kernel=kernel, dimension=dimension, normalize_rows=normalize_rows, precision=precision)
         if kernel not in _lib.KERNEL_IDS:
             raise NotImplementedError(f"B200Solver doesn't support kernel {kernel}.")
         if preconditioner not in ("auto", "nystrom", "none"):
             raise ValueError(f"unknown preconditioner {preconditioner!r} (expected 'auto', 'nystrom' or 'none')")
         self.preconditioner, self.precond_rank = preconditioner, int(precond_rank)
-        _check_precision(precision, "B200Solver")
+        self.dtype = _check_precision(precision, "B200Solver", (np.float32, np.float64, np.float16))
         _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("B200Solver needs a CUDA device; there is no CPU fallback.")
         self.lam, self.rtol, self.max_iter, self.path = float(lam), float(rtol), int(max_iter), path
         self.comm = TorchDistComm() if distributed else LocalComm()
         self.device = torch.device("cuda", int(device))
+        if distributed and int(n_gpus) > 1:
+            raise ValueError("distributed=True (one process per GPU) and n_gpus > 1 (one process, several GPUs) exclude each other")
+        self.n_gpus = _multigpu.clamp_gpus(n_gpus, self.device.index)
+        self._group = None
         self.precision_name = np.dtype(precision).name
         self._set_name()
         self.info = None
@@ -299,6 +380,8 @@ class B200Solver(BaseSolver):
 
     def _set_name(self):
         pc = f", nystrom{self.precond_rank}" if self.preconditioner == "nystrom" else ", plain" if self.preconditioner == "none" else ""
+        gpus = self.comm.world if self.comm.world > 1 else self.n_gpus
+        pc += f", gpus={gpus}" if gpus > 1 else ""
         self.name = f"B200Solver({self.precision_name}, lam={self.lam:g}, rtol={self.rtol:g}{pc})"
 
     def set_query_arguments(self, **kwargs):
@@ -308,11 +391,23 @@ class B200Solver(BaseSolver):
                 setattr(self, k, float(kwargs[k]))
         if "max_iter" in kwargs:
             self.max_iter = int(kwargs["max_iter"])
+        if kwargs.get("n_gpus") is not None:
+            if self.comm.world > 1:
+                raise ValueError("n_gpus cannot be combined with distributed=True")
+            n = _multigpu.clamp_gpus(kwargs["n_gpus"], self.device.index)
+            if n != self.n_gpus:
+                self.n_gpus = n
+                self._ops = {}   # matvec objects are per GPU count; the preconditioner (first device) is kept
         self._set_name()  # the name labels the result (runner.py:155)
 
     def prepare_data(self, *, source_points):
-        self.source_points = _to_device(source_points, self.device)
+        """float32: the production path.  float64: double-precision matvec (kmb_product_f64) and vector kernels.  float16: the
+        inputs are rounded to half precision as the reference's astype does (bruteforce.py:186-203), arithmetic in FP32."""
+        self.source_points = _to_device(source_points, self.device, self.dtype)
         torch.cuda.synchronize(self.device)
+
+    def _multi(self):
+        return self.n_gpus > 1 and self.dtype != np.float64
 
     def fit(self):
         """Timed (the harness books it as build time).  The system itself is never factorised -- it is applied
@@ -341,6 +436,8 @@ class B200Solver(BaseSolver):
     def _precond_for(self, key):
         """Symmetric matvec: every rank holds all rows (no collective inside the preconditioner); row-sharded
         matvec: each rank holds its rows of U and the small products are all-reduced."""
+        if self._multi():
+            key = "symmetric"   # all CG vectors on the first device: the preconditioner holds all rows there
         if key not in self._precond:
             n = self.source_points.shape[0]
             idx = landmark_indices(n, min(self.precond_rank, n // 2)).to(self.device)   # small data sets: half the points
@@ -350,7 +447,7 @@ class B200Solver(BaseSolver):
             else:
                 lo, hi, _ = shard_bounds(n, self.comm.rank, self.comm.world)
                 pts, comm = self.source_points[lo:hi], self.comm
-            self._precond[key] = NystromPreconditioner(pts, landmarks, self.kernel, self.lam, comm)
+            self._precond[key] = NystromPreconditioner(pts, landmarks, self.kernel, self.lam, comm, dtype=self.source_points.dtype)
         pc = self._precond[key]
         pc.set_shift(self.lam)   # lam may have been changed by set_query_arguments
         return pc
@@ -363,7 +460,12 @@ class B200Solver(BaseSolver):
         key = self._mode(E)
         symmetric = key == "symmetric"
         if key not in self._ops:
-            if symmetric:
+            if self._multi():
+                g = self._setup_group()
+                self.rows = (0, n)
+                self._ops[key] = (_multigpu.MultiDeviceSymmetricOps(g, self._ys, self.kernel) if symmetric
+                                  else _multigpu.MultiDeviceRowOps(g, self._ys, self.kernel, path=self.path))
+            elif symmetric:
                 self._ops[key] = CudaSymmetricOps(self.source_points, self.kernel, self.comm)
             else:
                 lo, hi, _ = shard_bounds(n, self.comm.rank, self.comm.world)
@@ -372,8 +474,18 @@ class B200Solver(BaseSolver):
         self.symmetric, self.ops = symmetric, self._ops[key]
         return self.ops
 
+    def _setup_group(self):
+        g = self._group
+        if g is None or g.n != self.n_gpus:
+            g = self._group = _multigpu.DeviceGroup(self.device.index, self.n_gpus)
+            self._ys = g.replicate(self.source_points)
+            g.synchronize()
+        return g
+
     def prepare_query(self, *, target_signal):
-        self.target_signal = _to_device(target_signal, self.device)
+        self.target_signal = _to_device(target_signal, self.device, self.dtype)
+        if self._multi():
+            self._setup_group()   # replicas of the points on the other devices: an untimed copy like the one above
         torch.cuda.synchronize(self.device)
 
     def query(self):
@@ -383,7 +495,7 @@ class B200Solver(BaseSolver):
                 self._ops_for(self.target_signal.shape[1])
                 pc = self._precond_for("symmetric" if self.symmetric else "rows") if self._use_precond() else None
                 self.precond_rank_used = pc.rank if pc is not None else 0
-                if self.symmetric:  # replicated vectors; the only collective is inside ops.matvec
+                if self.symmetric or self._multi():  # vectors replicated / on the first device; the exchange is inside ops.matvec
                     comm, rhs = LocalComm(), self.target_signal
                 else:
                     lo, hi = self.rows
@@ -392,7 +504,7 @@ class B200Solver(BaseSolver):
                     self.info = pcg_solve(self.ops, comm, rhs, n, pc, lam=self.lam, rtol=self.rtol, max_iter=self.max_iter)
                 else:
                     self.info = cg_solve(self.ops, comm, rhs, n, lam=self.lam, rtol=self.rtol, max_iter=self.max_iter)
-                self.x_full = self.info.x if self.symmetric else self.comm.all_gather(self.info.x, n)
+                self.x_full = self.info.x if (self.symmetric or self._multi()) else self.comm.all_gather(self.info.x, n)
             torch.cuda.synchronize(self.device)
         self.query_ms = t.ms()
 
@@ -412,14 +524,16 @@ class B200Solver(BaseSolver):
             "preconditioner": f"nystrom(rank={self.precond_rank_used})" if self.precond_rank_used else "none",
             "gpu_fit_ms": float(getattr(self, "fit_ms", 0.0)),
             "gpu_launches": int(self.ops.launches),
+            "n_gpus": int(self.comm.world if self.comm.world > 1 else (self.n_gpus if self._multi() else 1)),
         }
 
     def get_memory_usage(self):
         return super().get_memory_usage() + torch.cuda.memory_allocated(self.device) / 1024
 
     def done(self):
-        for k in ("source_points", "target_signal", "ops", "_ops", "_precond", "x_full"):
+        for k in ("source_points", "target_signal", "ops", "_ops", "_precond", "x_full", "_group", "_ys"):
             self.__dict__.pop(k, None)
+        self._group = None
 
     def __del__(self):
         try:

@@ -28,6 +28,8 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 void count_launch(int n) { g_launches += n; }
+int launch_count() { return g_launches; }
+void set_launch_count(int n) { g_launches = n; }
 
 #define KMB_DECLARE_TABLE(NAME)      \
     extern const DirectEntry NAME[]; \

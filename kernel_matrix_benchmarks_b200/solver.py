@@ -30,8 +30,8 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from .product import (SYM_MIN_POINTS, Workspace, _ptr, _stream, kernel_block_f64, kernel_product, kernel_product_sym_part,
-                      symmetric_applies)
+from .product import (SYM_MIN_POINTS, Workspace, _ptr, _stream, kernel_block_f64, kernel_product, kernel_product_f64,
+                      kernel_product_sym_part, symmetric_applies)
 
 
 def shard_bounds(n, rank, world):
@@ -85,25 +85,33 @@ class CudaShardOps:
     """The CUDA side of one rank: product kernel for the matvec + fused CG vector kernels."""
 
     def __init__(self, points, kernel, row_lo, row_hi, path="auto"):
+        """``points`` float32: the production path.  ``points`` float64: the `precision: float64` variant of the solver
+        (the reference sweeps float16/32/64, algos.yaml:164-181) -- kmb_product_f64 as the matvec, kmb_cg_*_f64 steps."""
         self.lib = _lib.load()
         self.y = points  # (N, D) all source points, replicated
         self.x = points[row_lo:row_hi]  # this rank's target rows (a view: same memory)
         self.kernel, self.path, self.row_lo = kernel, path, row_lo
         self.n_local = row_hi - row_lo
+        self.dtype = points.dtype
+        self.f64 = points.dtype == torch.float64
+        sfx = "f64" if self.f64 else "f32"
+        self._init, self._shift_dot = getattr(self.lib, f"kmb_cg_init_{sfx}"), getattr(self.lib, f"kmb_cg_shift_dot_{sfx}")
+        self._update, self._direction = getattr(self.lib, f"kmb_cg_update_{sfx}"), getattr(self.lib, f"kmb_cg_direction_{sfx}")
+        self._scalar = ctypes.c_double if self.f64 else ctypes.c_float
         self.ws = Workspace()
         self.scratch = torch.zeros(int(self.lib.kmb_cg_scratch_bytes()), dtype=torch.uint8, device=points.device)
         self.launches = 0
 
     def _new(self, E):
-        return torch.empty((self.n_local, E), dtype=torch.float32, device=self.y.device)
+        return torch.empty((self.n_local, E), dtype=self.dtype, device=self.y.device)
 
     def init(self, a):
         E = a.shape[1]
         x, r, p = self._new(E), self._new(E), self._new(E)
-        rs = torch.empty(E, dtype=torch.float32, device=a.device)
+        rs = torch.empty(E, dtype=self.dtype, device=a.device)
         self.Ap = self._new(E)
-        _lib.check(self.lib.kmb_cg_init_f32(_ptr(a), _ptr(x), _ptr(r), _ptr(p), _ptr(rs), self.n_local, E,
-                                            _ptr(self.scratch), _stream()))
+        _lib.check(self._init(_ptr(a), _ptr(x), _ptr(r), _ptr(p), _ptr(rs), self.n_local, E,
+                              _ptr(self.scratch), _stream()))
         self.launches += 1
         return x, r, p, rs
 
@@ -115,26 +123,28 @@ class CudaShardOps:
 
     def matvec(self, p_full):
         self._ap(p_full.shape[1])
-        kernel_product(self.x, self.y, p_full, kernel=self.kernel, path=self.path, row_offset=self.row_lo,
-                       out=self.Ap, workspace=self.ws)
+        if self.f64:
+            kernel_product_f64(self.x, self.y, p_full.contiguous(), kernel=self.kernel, row_offset=self.row_lo, out=self.Ap)
+        else:
+            kernel_product(self.x, self.y, p_full, kernel=self.kernel, path=self.path, row_offset=self.row_lo,
+                           out=self.Ap, workspace=self.ws)
         self.launches += int(self.lib.kmb_last_launch_count())
         return self.Ap
 
     def shift_dot(self, Ap, p, lam, out):
-        _lib.check(self.lib.kmb_cg_shift_dot_f32(_ptr(Ap), _ptr(p), ctypes.c_float(lam), _ptr(out), self.n_local,
-                                                 p.shape[1], _ptr(self.scratch), _stream()))
+        _lib.check(self._shift_dot(_ptr(Ap), _ptr(p), self._scalar(lam), _ptr(out), self.n_local,
+                                   p.shape[1], _ptr(self.scratch), _stream()))
         self.launches += 1
         return out
 
     def update(self, x, r, p, Ap, rs, pAp, rs_new):
-        _lib.check(self.lib.kmb_cg_update_f32(_ptr(x), _ptr(r), _ptr(p), _ptr(Ap), _ptr(rs), _ptr(pAp), _ptr(rs_new),
-                                              self.n_local, p.shape[1], _ptr(self.scratch), _stream()))
+        _lib.check(self._update(_ptr(x), _ptr(r), _ptr(p), _ptr(Ap), _ptr(rs), _ptr(pAp), _ptr(rs_new),
+                                self.n_local, p.shape[1], _ptr(self.scratch), _stream()))
         self.launches += 1
         return rs_new
 
     def direction(self, p, r, rs_new, rs):
-        _lib.check(self.lib.kmb_cg_direction_f32(_ptr(p), _ptr(r), _ptr(rs_new), _ptr(rs), self.n_local, p.shape[1],
-                                                 _stream()))
+        _lib.check(self._direction(_ptr(p), _ptr(r), _ptr(rs_new), _ptr(rs), self.n_local, p.shape[1], _stream()))
         self.launches += 1
 
 
@@ -157,7 +167,8 @@ class CudaSymmetricOps(CudaShardOps):
 
     @staticmethod
     def applies(points, kernel, E=1):
-        return points.shape[0] >= SYM_MIN_POINTS and symmetric_applies(points, points, kernel, E=E)
+        return (points.dtype == torch.float32 and points.shape[0] >= SYM_MIN_POINTS
+                and symmetric_applies(points, points, kernel, E=E))
 
     def matvec(self, p_full):
         if p_full.shape[1] != 1:

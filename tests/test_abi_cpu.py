@@ -72,10 +72,12 @@ def test_plugin_rejects_what_the_reference_rejects():
             cls(kernel="laplace", dimension=3)
         with pytest.raises(NotImplementedError):
             cls(kernel="gaussian", dimension=3, precision=np.int32)
-    with pytest.raises(NotImplementedError):   # the solver iterates in float32 only
-        B200Solver(kernel="gaussian", dimension=3, precision=np.float64)
-    with pytest.raises(NotImplementedError):   # the float64 product kernel covers D <= 16
-        B200Product(kernel="gaussian", dimension=784, precision="float64")
+    for cls in (B200Product, B200Solver):      # the reference's precision sweep (algos.yaml:156-181): all three accepted
+        for precision in ("float16", "float32", "float64", np.float64):
+            try:
+                cls(kernel="gaussian", dimension=784, precision=precision)
+            except RuntimeError as e:          # no GPU here: the only acceptable refusal
+                assert "no CPU fallback" in str(e)
 
 
 def test_no_cpu_fallback():

@@ -564,9 +564,10 @@ def run_plugin_precision(precision, g, **kw):
         algo.done()
 
 
-@pytest.mark.parametrize("name", [n for n in PRODUCT_CASES if load_golden(n)["source_points"].shape[1] <= 16])
+@pytest.mark.parametrize("name", PRODUCT_CASES)
 def test_float64_precision_matches_reference_float64(name):
-    """precision=float64: the reference's own float64 outputs (tests/golden) to round-off."""
+    """precision=float64: the reference's own float64 outputs (tests/golden) to round-off -- every golden case, also
+    D = 64 / D = 784 (the tiled float64 kernel: what the ground truth of the C3 / C4 datasets is written with)."""
     g = load_golden(name)
     out, extra, label = run_plugin_precision("float64", g)
     assert out.dtype == np.float64 and out.shape == g["truth"].shape and "float64" in label
@@ -587,6 +588,30 @@ def test_float64_precision_properties_at_size():
     rows = np.arange(0, 20000, 100)
     want = orc.kernel_product("gaussian", ds.source_points, None, ds.source_signal, rows=rows)
     assert orc.rel_l2(out[rows], want) <= 1e-13
+
+
+def test_float64_wide_kernel_ragged_shapes():
+    """The tiled float64 kernel (D > 16): tile edges in N, M, D and E, more than 64 signal columns (two passes), all three
+    kernels incl. the inverse-distance zeroing rule with a row offset that is not a multiple of the tile."""
+    import torch
+    from kernel_matrix_benchmarks_b200 import product
+
+    rng = np.random.RandomState(8)
+    for kernel, N, M, D, E, norm in (("gaussian", 65, 130, 17, 1, False), ("absolute-exponential", 200, 63, 100, 70, True),
+                                     ("inverse-distance", 150, 37, 33, 3, False), ("gaussian", 1, 1, 784, 1, False)):
+        r = (3.0 / D) ** 0.5
+        y, x, b = r * rng.rand(M, D), r * rng.rand(N, D), rng.randn(M, E)
+        want = orc.kernel_product(kernel, y, x, b, normalize_rows=norm)
+        got = product.kernel_product_f64(torch.tensor(x, device="cuda"), torch.tensor(y, device="cuda"), torch.tensor(b, device="cuda"),
+                                         kernel=kernel, normalize_rows=norm).cpu().numpy()
+        assert got.shape == want.shape and orc.rel_l2(got, want) <= 1e-12, (kernel, N, M, D, E)
+    # sharded rows: the zeroing rule follows the global row index
+    y, x, b = rng.rand(37, 20), rng.rand(150, 20), rng.randn(37, 2)
+    want = orc.kernel_product("inverse-distance", y, x, b)
+    lo = 70
+    got = product.kernel_product_f64(torch.tensor(x[lo:], device="cuda"), torch.tensor(y, device="cuda"), torch.tensor(b, device="cuda"),
+                                     kernel="inverse-distance", row_offset=lo).cpu().numpy()
+    assert orc.rel_l2(got, want[lo:]) <= 1e-12
 
 
 def test_float16_precision_rounds_the_inputs_like_the_reference():

@@ -73,6 +73,29 @@ def test_reference_system_without_regularisation(name):
     assert orc.rel_l2(orc.regularised_matvec(g["kernel"], g["source_points"], x4, 0.0), g["rhs"]) <= 5e-4
 
 
+@pytest.mark.parametrize("precision,tol", [("float64", 1e-9), ("float32", 1e-4), ("float16", 1e-1)])
+def test_solver_precision_variants(precision, tol):
+    """The reference sweeps float16 / float32 / float64 for its solver (algos.yaml:164-181).  float64: double-precision matvec
+    and vector kernels reach the dense float64 solution to round-off x cond; float16: inputs (points AND right-hand side) rounded to half -- an error of 5e-4 in the data, amplified by cond(K + I)."""
+    from kernel_matrix_benchmarks_b200.algorithms.b200 import B200Solver
+
+    g = load_golden("solver_gaussian_cube_d3_lam1")
+    results = {}
+    for pc in ("none", "nystrom"):
+        algo = B200Solver(kernel=g["kernel"], dimension=3, precision=precision, lam=float(g["lam"]), rtol=1e-12 if precision == "float64" else 1e-6,
+                          max_iter=500, preconditioner=pc, precond_rank=128)
+        algo.prepare_data(source_points=g["source_points"])
+        algo.fit()
+        algo.prepare_query(target_signal=g["rhs"])
+        algo.query()
+        x, extra, name = algo.get_result(), algo.get_additional(), str(algo)
+        algo.done()
+        assert precision in name and extra["cg_converged"], (name, extra)
+        assert x.dtype == np.float64 and orc.rel_l2(x, g["spd_solution"]) <= tol, (pc, orc.rel_l2(x, g["spd_solution"]), extra)
+        results[pc] = extra["cg_iterations"]
+    assert results["nystrom"] < results["none"]
+
+
 def test_config_c5_full_size():
     """BASELINE config 5 at FULL size: (K + I) b = a, N = 10^6, D = 3, Gaussian.  The right-hand side needs one
     10^12-pair product, so it is built by the product under test and checked -- like the solution's residual -- on
