@@ -71,7 +71,7 @@ enum {
                                   bits as the TF32 split does, kind::f16 MMAs run at twice the TF32 rate and the
                                   operand planes are half as large.  What KMB_PATH_AUTO picks for D > 16. */
     KMB_PATH_DIRECT_SYM = 4    /* targets == sources (the reference's same_points, base.py:56-79): x must be the
-                                  same pointer as y.  Plain Gaussian product or density, D <= 3, E == 1: every kernel
+                                  same pointer as y.  Plain product or density of any kernel, D <= 3, E == 1: every kernel
                                   value is evaluated once and feeds a_i += k b_j and a_j += k b_i (K is
                                   symmetric), see kmb_product_sym_f32.  Never chosen by KMB_PATH_AUTO (the
                                   library cannot see aliasing in kmb_product_workspace_bytes) */
@@ -123,20 +123,23 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
 int kmb_product_prepare_f32(const float* x, const float* y, int64_t n_targets, int64_t n_sources, int D, int kernel_id,
                             int flags, int path, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Symmetric Gaussian product for targets == sources (same_points):
- *     out[i] = this part's share of  sum_j exp(-|y_i - y_j|^2) b[j]        (E == 1, D <= 3)
+/* Symmetric product for targets == sources (same_points):
+ *     out[i] = this part's share of  sum_j k(y_i, y_j) b[j]        (E == 1, D <= 3, any kernel_id)
  *
  * Same arithmetic as kmb_product_f32(y, y, b, ...) -- kernel_matrix + K @ b of bruteforce.py:25-58,
- * 153 with target_points = None (:27-28, :113-120) -- but K's symmetry is used: the n x n pair matrix
- * is cut into (4096 rows x 512 sources) units, only units on or above the block diagonal are
- * evaluated, and each kernel value is added to both its row's and its column's sum.  The unit list is
- * split into `n_parts` equal contiguous ranges; this call evaluates range `part` and writes the sums it
- * produced to ALL n entries of out (zero where it contributed nothing).  With n_parts > 1 (one part
- * per GPU) the caller adds the parts' outputs -- one all-reduce of n floats; with n_parts == 1 out is
- * the product.  Deterministic for a given (n, n_parts, device).  If the data are too spread out for the
- * product form (see KMB_PATH_DIRECT_F32; decided on the device) the difference-form kernel computes
- * rows [n*part/n_parts, n*(part+1)/n_parts) instead and the other rows of out are zero.
+ * 153 with target_points = None (:27-28, :113-120) -- but K's symmetry is used (every kernel of
+ * bruteforce.py:18-22 is a function of |x - y|; the inverse-distance zeroing rule :12-14 zeroes the
+ * diagonal when N == M): the n x n pair matrix is cut into (4096 rows x 512 sources) units, only units
+ * on or above the block diagonal are evaluated, and each kernel value is added to both its row's and
+ * its column's sum.  The unit list (ordered in strips of source blocks so that a CTA works on a
+ * compact patch of the matrix, csrc/kprod_sym.cuh) is split into `n_parts` equal contiguous ranges;
+ * this call evaluates range `part` and writes the sums it produced to ALL n entries of out (zero where
+ * it contributed nothing).  With n_parts > 1 (one part per GPU) the caller adds the parts' outputs --
+ * one all-reduce of n floats; with n_parts == 1 out is the product.  Deterministic for a given
+ * (n, n_parts, device).  The Gaussian kernel uses the product form when the data allow it and the
+ * difference form otherwise (see KMB_PATH_DIRECT_F32; decided on the device), symmetric either way.
  * b == NULL means b == 1 (density estimation, bruteforce.py:150).
+ * Workspace: O(n sqrt(CTAs)) floats (77 MB at n = 10^6 on one GPU), the same for every kernel_id.
  */
 int kmb_product_sym_workspace_bytes(int64_t n, int D, int part, int n_parts, size_t* bytes);
 int kmb_product_sym_f32(const float* y, const float* b, float* out, int64_t n, int D, int kernel_id,
@@ -213,6 +216,12 @@ int kmb_kernel_block_f64(const double* x, const double* y, double* out, int64_t 
  * last wave of R_last x C_last; CTA b of a wave works on row tile b / C and on source blocks
  * [n_source_blocks (b % C) / C, n_source_blocks (b % C + 1) / C). */
 int kmb_debug_plan_waves(int64_t n_tiles, int64_t n_source_blocks, int grid, size_t row_tile_bytes, int64_t* out7);
+
+/* Diagnostics (host logic only, no GPU needed): where unit `u` of the strip-ordered unit list of the symmetric path
+ * sits when n points are worked on by `total_ctas` CTAs over all parts (kprod_sym.cuh).
+ * out8 = {total units, strips, strip width in source blocks, strip, row tile, source block, first unit of the
+ * (strip, row tile) segment, units in the segment}; u outside [0, total units) only fills the first three. */
+int kmb_debug_sym_unit(int64_t n, int64_t total_ctas, int64_t u, int64_t* out8);
 
 /* Number of this library's kernels the last kmb_product_f32 / kmb_cg_* call on this
  * thread launched (bench.py's gpu_launches). */

@@ -78,6 +78,7 @@ SIGNATURES = {
     ),
     "kmb_kernel_block_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     "kmb_debug_plan_waves": (c_int, [c_int64, c_int64, c_int, c_size_t, POINTER(c_int64)]),
+    "kmb_debug_sym_unit": (c_int, [c_int64, c_int64, c_int64, POINTER(c_int64)]),
     "kmb_set_profiling": (c_int, [c_int]),
     "kmb_last_main_kernel_ms": (c_int, [POINTER(c_float)]),
     "kmb_cg_scratch_bytes": (c_size_t, []),

@@ -27,7 +27,7 @@ from .. import _lib
 from .. import multigpu as _multigpu
 from .. import product as _product
 from ..product import Workspace, device_info, kernel_product, kernel_product_sym_part, last_launch_count
-from ..solver import (CudaShardOps, CudaSymmetricOps, LocalComm, NystromPreconditioner, TorchDistComm, cg_solve,
+from ..solver import (CudaShardOps, CudaSymmetricOps, LocalComm, NystromPreconditioner, ReplicatedComm, TorchDistComm, cg_solve,
                       landmark_indices, pcg_solve, shard_bounds)
 from .base import BaseProduct, BaseSolver
 
@@ -41,8 +41,32 @@ def _check_precision(precision, who, allowed=(np.float32,)):
     return dt
 
 
-def _to_device(array, device, precision=np.float32):
+_CAST_THREADS = 4            # host threads of one cast (numpy releases the GIL inside copyto)
+_CAST_MIN_BYTES = 4 << 20    # below this a single pass is faster than handing out slices
+_cast_pool = None
+
+
+def _cast_into(dst, src):
+    """dst[...] = src (float64 -> working precision) in one pass over the data, large arrays on a few host threads: the
+    cast is memory-bound and single-threaded in NumPy (4-5 ms for the 24 MB of C2's points -- as long as 3 % of the product)."""
+    global _cast_pool
+    if src.nbytes < _CAST_MIN_BYTES or src.shape[0] < _CAST_THREADS:
+        np.copyto(dst, src, casting="unsafe")
+        return
+    if _cast_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _cast_pool = ThreadPoolExecutor(max_workers=_CAST_THREADS)
+    step = -(-src.shape[0] // _CAST_THREADS)
+    list(_cast_pool.map(lambda lo: np.copyto(dst[lo:lo + step], src[lo:lo + step], casting="unsafe"), range(0, src.shape[0], step)))
+
+
+def _to_device(array, device, precision=np.float32, comm=None):
     """float64 host array (owned by the runner, never mutated) -> device tensor in the working precision.
+
+    ``comm`` with world > 1 (one process per GPU, every rank handed the same array): each rank casts and copies only its
+    1 / world slice of the rows and the slices are all-gathered on the devices (NVLink) -- the host cast and the PCIe copy of
+    the replicated array do not grow with the number of ranks sharing the host.
 
     float32: cast as bruteforce.py:100-106 casts.  float64: kept.  float16: the inputs are rounded to half
     precision exactly as the reference's ``astype(float16)`` rounds them, then widened to float32 -- the
@@ -55,9 +79,19 @@ def _to_device(array, device, precision=np.float32):
     work = np.float64 if dt == np.float64 else np.float32
     if a.ndim == 1:
         a = a[:, None]
+    world = comm.world if comm is not None else 1
+    if world > 1 and a.nbytes >= _CAST_MIN_BYTES and dt != np.float16:
+        lo, hi, per = shard_bounds(a.shape[0], comm.rank, world)
+        stage = _staging((per,) + a.shape[1:], work)
+        _cast_into(stage.numpy()[: hi - lo], a[lo:hi])
+        mine = stage[: hi - lo].to(device, non_blocking=True)
+        with torch.cuda.device(device):
+            out = comm.all_gather(mine, a.shape[0]).clone()   # the communicator's gather buffer is reused by the next call
+        torch.cuda.current_stream(device).synchronize()
+        return out
     # cast straight into a cached pinned staging buffer (one pass over the data, no per-call pinning)
     stage = _staging(a.shape, work)
-    np.copyto(stage.numpy(), a, casting="unsafe")
+    _cast_into(stage.numpy(), a)
     out = stage.to(device, non_blocking=True)
     torch.cuda.current_stream(device).synchronize()   # the staging buffer is reused by the next call
     return out
@@ -168,9 +202,9 @@ class B200Product(BaseProduct):
     def prepare_data(self, *, source_points, target_points, same_points=False, density_estimation=False):
         """Untimed host->device copy (base.py:64-67), cast to float32 as bruteforce.py:100-106 casts."""
         self._group = None
-        self.source_points = _to_device(source_points, self.device, self.dtype)
+        self.source_points = _to_device(source_points, self.device, self.dtype, self.comm)
         self.same_points = bool(same_points)
-        self.target_points = self.source_points if self.same_points else _to_device(target_points, self.device, self.dtype)
+        self.target_points = self.source_points if self.same_points else _to_device(target_points, self.device, self.dtype, self.comm)
         self.density_estimation = bool(density_estimation)
         torch.cuda.synchronize(self.device)
 
@@ -214,7 +248,7 @@ class B200Product(BaseProduct):
 
     def prepare_query(self, *, source_signal):
         """Untimed host->device copy of the signal (bruteforce.py:122-128)."""
-        self.source_signal = None if self.density_estimation else _to_device(source_signal, self.device, self.dtype)
+        self.source_signal = None if self.density_estimation else _to_device(source_signal, self.device, self.dtype, self.comm)
         if self._multi():
             g = self._setup_group()
             self._bs = None if self.density_estimation else g.replicate(self.source_signal)
@@ -230,7 +264,7 @@ class B200Product(BaseProduct):
         N = self.target_points.shape[0]
         self.res_device = torch.empty((N, E), dtype=torch.float32, device=self.device)
         if self.same_points and g.symmetric_applies(y0, self.kernel, bool(self.normalize_rows), self.density_estimation, E, self.path):
-            g.product_sym(self._ys, self._bs, self.res_device)
+            g.product_sym(self._ys, self._bs, self.res_device, kernel=self.kernel)
             self.path_used = "direct_sym"
         else:
             if g.prepared is None:   # n_gpus arrived as a query argument: the first query with this GPU count prepares
@@ -284,7 +318,7 @@ class B200Product(BaseProduct):
         sym = (self.path == "auto" and self.same_points and y.shape[0] >= _product.SYM_MIN_POINTS and
                _product.symmetric_applies(y, y, self.kernel, bool(self.normalize_rows), self.density_estimation, E))
         if sym:
-            self.res_device = kernel_product_sym_part(y, b, rank, world, workspace=self.workspace)
+            self.res_device = kernel_product_sym_part(y, b, rank, world, kernel=self.kernel, workspace=self.workspace)
             self.launches = last_launch_count()
             self.comm.all_reduce(self.res_device)
             self.path_used = "direct_sym"
@@ -403,7 +437,9 @@ class B200Solver(BaseSolver):
     def prepare_data(self, *, source_points):
         """float32: the production path.  float64: double-precision matvec (kmb_product_f64) and vector kernels.  float16: the
         inputs are rounded to half precision as the reference's astype does (bruteforce.py:186-203), arithmetic in FP32."""
-        self.source_points = _to_device(source_points, self.device, self.dtype)
+        self.source_points = _to_device(source_points, self.device, self.dtype, self.comm)
+        if self.comm.world > 1:
+            self.comm.warm(self.device)
         torch.cuda.synchronize(self.device)
 
     def _multi(self):
@@ -442,12 +478,11 @@ class B200Solver(BaseSolver):
             n = self.source_points.shape[0]
             idx = landmark_indices(n, min(self.precond_rank, n // 2)).to(self.device)   # small data sets: half the points
             landmarks = self.source_points[idx]
-            if key == "symmetric":
-                pts, comm = self.source_points, LocalComm()
-            else:
-                lo, hi, _ = shard_bounds(n, self.comm.rank, self.comm.world)
-                pts, comm = self.source_points[lo:hi], self.comm
-            self._precond[key] = NystromPreconditioner(pts, landmarks, self.kernel, self.lam, comm, dtype=self.source_points.dtype)
+            # built from this rank's rows (1 / world of the landmark block, the triangular solve and the Gram matrix; one
+            # all-reduce of m x m doubles); the symmetric matvec then wants every row of U on every rank: one all-gather
+            lo, hi, _ = shard_bounds(n, self.comm.rank, self.comm.world)
+            pc = NystromPreconditioner(self.source_points[lo:hi], landmarks, self.kernel, self.lam, self.comm, dtype=self.source_points.dtype)
+            self._precond[key] = pc.replicate(n) if key == "symmetric" else pc
         pc = self._precond[key]
         pc.set_shift(self.lam)   # lam may have been changed by set_query_arguments
         return pc
@@ -483,7 +518,7 @@ class B200Solver(BaseSolver):
         return g
 
     def prepare_query(self, *, target_signal):
-        self.target_signal = _to_device(target_signal, self.device, self.dtype)
+        self.target_signal = _to_device(target_signal, self.device, self.dtype, self.comm)
         if self._multi():
             self._setup_group()   # replicas of the points on the other devices: an untimed copy like the one above
         torch.cuda.synchronize(self.device)
@@ -496,7 +531,7 @@ class B200Solver(BaseSolver):
                 pc = self._precond_for("symmetric" if self.symmetric else "rows") if self._use_precond() else None
                 self.precond_rank_used = pc.rank if pc is not None else 0
                 if self.symmetric or self._multi():  # vectors replicated / on the first device; the exchange is inside ops.matvec
-                    comm, rhs = LocalComm(), self.target_signal
+                    comm, rhs = ReplicatedComm(self.comm), self.target_signal
                 else:
                     lo, hi = self.rows
                     comm, rhs = self.comm, self.target_signal[lo:hi].contiguous()

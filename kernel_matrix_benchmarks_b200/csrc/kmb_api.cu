@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 #include <mutex>
 #include <vector>
@@ -51,9 +52,10 @@ int kernel_block_f64(const double* x, const double* y, double* out, int64_t n, i
 bool sym_supported(int D);
 int sym_tile_rows();
 int sym_block_sources();
-long long sym_total_units(long long n_tiles, long long nsb);
-int sym_grid(int D, int sms, int* grid);
-int sym_launch(int D, const SymParams& P, cudaStream_t stream);
+int sym_grid(int sms, int* grid);
+void sym_geometry(long long n_tiles, long long nsb, long long total_ctas, SymGeom* g);
+SymSeg sym_segment_of(const SymGeom& g, long long u);
+int sym_launch(int D, int kernel_id, int form, const SymParams& P, cudaStream_t stream);
 
 static const DirectEntry* find_direct(int D, int e_chunk, int kid, bool norm, int form) {
     const DirectEntry* tab = nullptr;
@@ -159,7 +161,18 @@ int device_sm_count(int* sms) {
 static int plan_direct(int64_t N, int64_t M, int D, int E, int kid, int flags, int path, DirectPlan* pl) {
     const bool norm = flags & KMB_FLAG_NORMALIZE_ROWS;
     if (D > 16) return set_error(KMB_ERR_UNSUPPORTED, "direct FP32 path supports D <= 16 (got D=%d)", D);
-    pl->e_chunk = E >= 4 ? 4 : E;
+    // signal columns per pass: every pass re-evaluates the kernel (~8 FMA-pipe slots' worth per pair, MUFU included) and
+    // adds one FMA per column; pick the width that minimises passes x (8 + width)
+    static const int max_chunk = [] {   // tuning knob: KMB_DIRECT_MAX_EP=4 restores one pass per 4 columns
+        const char* e = getenv("KMB_DIRECT_MAX_EP");
+        const int v = e ? atoi(e) : 16;
+        return v < 1 ? 1 : v > 16 ? 16 : v;
+    }();
+    pl->e_chunk = 1;
+    for (int c = 1, best = 0; c <= max_chunk; c *= 2) {
+        const int cost = ((E + c - 1) / c) * (8 + c);
+        if (best == 0 || cost < best) { best = cost; pl->e_chunk = c; }
+    }
     pl->n_passes = (E + pl->e_chunk - 1) / pl->e_chunk;
     pl->form[0].ent = find_direct(D, pl->e_chunk, kid, norm, 0);
     if (!pl->form[0].ent) return set_error(KMB_ERR_UNSUPPORTED, "no direct kernel for D=%d E=%d kernel=%d", D, E, kid);
@@ -183,36 +196,47 @@ static int plan_direct(int64_t N, int64_t M, int D, int E, int kid, int flags, i
     return KMB_OK;
 }
 
-// Symmetric (same_points) Gaussian product: the difference-form plan of this part's row shard (the
-// fallback when the data rule out the product form) + the buffers of kprod_sym.
+// Symmetric (same_points) product: the record / statistics buffers of the direct pipeline (the symmetric kernels read
+// the same packed records) + the strip geometry and the hand-over buffers of kprod_sym.
 struct SymPlan {
-    DirectPlan direct;          // rows [lo, hi) x all sources, difference form + product-form record layout
-    int64_t lo, hi;
-    long long n_tiles, nsb, N_pad, units;
-    int grid;
-    size_t rowsum_bytes, rowpart_bytes, colpart_bytes, total_bytes;
+    DirectPlan direct;          // record layout of both evaluation forms (32-byte records, 512-record blocks)
+    SymGeom geom;
+    long long unit_begin, unit_end;   // this part's share of the unit list
+    int grid, seg_base, strip_base;
+    size_t rowseg_bytes, rowpart_bytes, colpart_bytes, total_bytes;
 };
 
-static int plan_sym(int64_t n, int D, int part, int n_parts, SymPlan* sp) {
+static int plan_sym(int64_t n, int D, int kernel_id, int part, int n_parts, SymPlan* sp) {
     if (!sym_supported(D)) return set_error(KMB_ERR_UNSUPPORTED, "symmetric path supports D <= 3 (got D=%d)", D);
     if (n_parts < 1 || part < 0 || part >= n_parts) return set_error(KMB_ERR_INVALID, "bad part %d of %d", part, n_parts);
-    sp->lo = n * part / n_parts;
-    sp->hi = n * (part + 1) / n_parts;
-    if (int rc = plan_direct(std::max<int64_t>(sp->hi - sp->lo, 1), n, D, 1, KMB_KERNEL_GAUSSIAN, 0, KMB_PATH_DIRECT_F32, &sp->direct)) return rc;
-    const DirectEntry* pe = sp->direct.form[1].ent;
-    if (!pe || pe->SB != sym_block_sources() || pe->RECV != 2)
-        return set_error(KMB_ERR_UNSUPPORTED, "no product-form record layout for D=%d", D);
-    sp->nsb = (n + sym_block_sources() - 1) / sym_block_sources();
-    sp->N_pad = sp->nsb * sym_block_sources();
-    sp->n_tiles = (n + sym_tile_rows() - 1) / sym_tile_rows();
-    sp->units = sym_total_units(sp->n_tiles, sp->nsb);
+    if (kernel_id < KMB_KERNEL_GAUSSIAN || kernel_id > KMB_KERNEL_INVERSE_DISTANCE) return set_error(KMB_ERR_UNSUPPORTED, "unknown kernel id %d", kernel_id);
+    if (int rc = plan_direct(n, n, D, 1, kernel_id, 0, KMB_PATH_DIRECT_F32, &sp->direct)) return rc;
+    for (const FormPlan& f : sp->direct.form)
+        if (f.ent && (f.ent->SB != sym_block_sources() || f.ent->RECV != 2))
+            return set_error(KMB_ERR_UNSUPPORTED, "no 32-byte record layout for D=%d", D);
+    const long long nsb = (n + sym_block_sources() - 1) / sym_block_sources();
+    const long long n_tiles = (n + sym_tile_rows() - 1) / sym_tile_rows();
     int sms = 0;
     if (int rc = device_sm_count(&sms)) return rc;
-    if (int rc = sym_grid(D, sms, &sp->grid)) return rc;
-    sp->rowsum_bytes = align_up(static_cast<size_t>(sp->n_tiles) * sym_tile_rows() * 4, 256);
+    if (int rc = sym_grid(sms, &sp->grid)) return rc;
+    sym_geometry(n_tiles, nsb, static_cast<long long>(sp->grid) * n_parts, &sp->geom);
+    const long long units = sp->geom.strip_prefix[sp->geom.n_strips];
+    sp->unit_begin = units * part / n_parts;
+    sp->unit_end = units * (part + 1) / n_parts;
+    int n_segs = 1, n_strips_part = 1;
+    sp->seg_base = sp->strip_base = 0;
+    if (sp->unit_end > sp->unit_begin) {
+        const SymSeg first = sym_segment_of(sp->geom, sp->unit_begin), last = sym_segment_of(sp->geom, sp->unit_end - 1);
+        sp->seg_base = sp->geom.seg_prefix[first.strip] + first.tile;
+        sp->strip_base = first.strip;
+        n_segs = sp->geom.seg_prefix[last.strip] + last.tile - sp->seg_base + 1;
+        n_strips_part = last.strip - first.strip + 1;
+    }
+    const size_t piece_bytes = static_cast<size_t>(sp->geom.Wb) * sym_block_sources() * 4;
+    sp->rowseg_bytes = align_up(static_cast<size_t>(n_segs) * sym_tile_rows() * 4, 256);
     sp->rowpart_bytes = align_up(static_cast<size_t>(sp->grid) * 2 * sym_tile_rows() * 4, 256);
-    sp->colpart_bytes = align_up(static_cast<size_t>(sp->n_tiles) * sp->N_pad * 4, 256);
-    sp->total_bytes = sp->direct.total_bytes + sp->rowsum_bytes + sp->rowpart_bytes + sp->colpart_bytes;
+    sp->colpart_bytes = align_up(static_cast<size_t>(sp->grid + n_strips_part) * piece_bytes, 256);
+    sp->total_bytes = sp->direct.total_bytes + sp->rowseg_bytes + sp->rowpart_bytes + sp->colpart_bytes;
     return KMB_OK;
 }
 
@@ -229,8 +253,8 @@ static int check_product_args(int64_t N, int64_t M, int D, int E, int kid, int f
     if (path < KMB_PATH_AUTO || path > KMB_PATH_TENSOR_3XF16) return set_error(KMB_ERR_INVALID, "unknown path %d", path);
     if (path == KMB_PATH_DIRECT_SYM) {
         if (N != M) return set_error(KMB_ERR_INVALID, "the symmetric path needs targets == sources (N=%lld, M=%lld)", (long long)N, (long long)M);
-        if (kid != KMB_KERNEL_GAUSSIAN || (flags & KMB_FLAG_NORMALIZE_ROWS) || E != 1 || !sym_supported(D))
-            return set_error(KMB_ERR_UNSUPPORTED, "the symmetric path covers the plain Gaussian product / density with D <= 3, E = 1");
+        if ((flags & KMB_FLAG_NORMALIZE_ROWS) || E != 1 || !sym_supported(D))
+            return set_error(KMB_ERR_UNSUPPORTED, "the symmetric path covers the plain product / density with D <= 3, E = 1");
     }
     return KMB_OK;
 }
@@ -242,14 +266,13 @@ static int resolve_path(int D, int path) {
 
 // Enqueue the direct pipeline on `stream`: bounding-box statistics -> source packing -> main kernels.
 //   sym == nullptr  out (N x E) = product of the N targets x with all M sources.
-//   sym != nullptr  targets == sources == y (x is y, N == M, E == 1).  The product form runs as the
-//                   symmetric kernel over this part's share of the unit list and writes this part's
-//                   contribution to all N rows of out; if the data rule the product form out, the
-//                   difference form writes rows [lo, hi) of out and the other rows stay zero.  Either
-//                   way the parts' outputs add up to the product.
+//   sym != nullptr  targets == sources == y (x is y, N == M, E == 1).  The symmetric kernel (Gaussian: product form
+//                   and difference form both enqueued, the data decide) runs over this part's share of the unit
+//                   list and writes this part's contribution to all N rows of out: the parts' outputs add up to
+//                   the product.
 static int run_direct(const float* x, const float* y, const float* b, float* out, int64_t N, int64_t M, int D, int E,
-                      int kernel_id, int flags, int64_t row_offset, const DirectPlan& pl, const SymPlan* sym, int part,
-                      int n_parts, char* ws, cudaStream_t stream) {
+                      int kernel_id, int flags, int64_t row_offset, const DirectPlan& pl, const SymPlan* sym, char* ws,
+                      cudaStream_t stream) {
     const bool density = b == nullptr;
     (void)flags;
     DirectStats* stats = reinterpret_cast<DirectStats*>(ws);
@@ -259,7 +282,6 @@ static int run_direct(const float* x, const float* y, const float* b, float* out
     int* counters = reinterpret_cast<int*>(ws + pl.stats_bytes + pl.rec_bytes + pl.partial_bytes);
     KMB_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(DirectStats), stream));
     KMB_CUDA_CHECK(cudaMemsetAsync(counters, 0, pl.counter_bytes, stream));
-    if (sym) KMB_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * N, stream));
 
     // bounding box -> centre, radius, evaluation form (stays on the device)
     {
@@ -304,28 +326,32 @@ static int run_direct(const float* x, const float* y, const float* b, float* out
             KMB_CUDA_CHECK(cudaEventRecord(g_ev0, stream));
         }
         if (sym) {
-            // this part's share of the triangular unit list -> kprod_sym + combine (product form only)
+            // this part's share of the strip-ordered unit list -> kprod_sym + combine, once per evaluation form
             char* sb = ws + pl.total_bytes;
             SymParams S;
             S.stats = stats;
             S.rec = reinterpret_cast<const float4*>(rec);
-            S.rowsum = reinterpret_cast<float*>(sb);
-            S.rowpart = reinterpret_cast<float*>(sb + sym->rowsum_bytes);
-            S.colpart = reinterpret_cast<float*>(sb + sym->rowsum_bytes + sym->rowpart_bytes);
+            S.rowseg = reinterpret_cast<float*>(sb);
+            S.rowpart = reinterpret_cast<float*>(sb + sym->rowseg_bytes);
+            S.colpart = reinterpret_cast<float*>(sb + sym->rowseg_bytes + sym->rowpart_bytes);
             S.out = out;
             S.N = N;
-            S.N_pad = sym->N_pad;
-            S.unit_begin = sym->units * part / n_parts;
-            S.unit_end = sym->units * (part + 1) / n_parts;
-            S.n_tiles = static_cast<int>(sym->n_tiles);
-            S.nsb = static_cast<int>(sym->nsb);
+            S.M = M;
+            S.unit_begin = sym->unit_begin;
+            S.unit_end = sym->unit_end;
+            S.piece_floats = static_cast<long long>(sym->geom.Wb) * sym_block_sources();
             S.grid = sym->grid;
-            if (int rc = sym_launch(D, S, stream)) return rc;
+            S.seg_base = sym->seg_base;
+            S.strip_base = sym->strip_base;
+            S.g = sym->geom;
+            for (int f = 1; f >= 0; --f) {
+                if (!pl.form[f].ent) continue;
+                if (int rc = sym_launch(D, kernel_id, f, S, stream)) return rc;
+            }
         }
         // both forms are enqueued; the one the data did not select returns at once
-        for (int f = 1; f >= 0; --f) {
+        for (int f = 1; f >= 0 && !sym; --f) {
             if (!pl.form[f].ent) continue;
-            if (sym && (f == 1 || sym->hi == sym->lo)) continue;
             const DirectEntry& ent = *pl.form[f].ent;
             int per_sm = 0;
             if (int rc = resident(ent, &per_sm)) return rc;
@@ -333,15 +359,15 @@ static int run_direct(const float* x, const float* y, const float* b, float* out
             long long grid = static_cast<long long>(pl.grid_max / 2) * per_sm;
             if (grid > units) grid = units;
             DirectParams P;
-            P.x = sym ? y + sym->lo * D : x;
+            P.x = x;
             P.stats = stats;
             P.rec = reinterpret_cast<const float4*>(rec);
-            P.out = sym ? out + sym->lo : out;
+            P.out = out;
             P.partial = partial;
             P.tile_counter = counters;
-            P.N = sym ? sym->hi - sym->lo : N;
+            P.N = N;
             P.M = M;
-            P.row_offset = sym ? sym->lo : row_offset;
+            P.row_offset = row_offset;
             P.D = D;
             P.E = E;
             P.e0 = e0;
@@ -453,7 +479,7 @@ int kmb_product_f32(const float* x, const float* y, const float* b, float* out, 
     if (int rc = plan_direct(N, M, D, E, kernel_id, flags, p, &pl)) return rc;
     if (!workspace || workspace_bytes < pl.total_bytes)
         return set_error(KMB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total_bytes, workspace_bytes);
-    return run_direct(x, y, density ? nullptr : b, out, N, M, D, E, kernel_id, flags, row_offset, pl, nullptr, 0, 1,
+    return run_direct(x, y, density ? nullptr : b, out, N, M, D, E, kernel_id, flags, row_offset, pl, nullptr,
                       static_cast<char*>(workspace), stream);
 }
 
@@ -487,6 +513,24 @@ int kmb_debug_plan_waves(int64_t n_tiles, int64_t n_source_blocks, int grid, siz
     return KMB_OK;
 }
 
+int kmb_debug_sym_unit(int64_t n, int64_t total_ctas, int64_t u, int64_t* out8) {
+    if (!out8 || n < 1 || total_ctas < 1) return set_error(KMB_ERR_INVALID, "bad arguments");
+    SymGeom g;
+    sym_geometry((n + sym_tile_rows() - 1) / sym_tile_rows(), (n + sym_block_sources() - 1) / sym_block_sources(), total_ctas, &g);
+    out8[0] = g.strip_prefix[g.n_strips];
+    out8[1] = g.n_strips;
+    out8[2] = g.Wb;
+    for (int i = 3; i < 8; ++i) out8[i] = -1;
+    if (u < 0 || u >= out8[0]) return KMB_OK;
+    const SymSeg sg = sym_segment_of(g, u);
+    out8[3] = sg.strip;
+    out8[4] = sg.tile;
+    out8[5] = sg.jb0 + (u - sg.begin);
+    out8[6] = sg.begin;
+    out8[7] = sg.len;
+    return KMB_OK;
+}
+
 int kmb_kernel_block_f64(const double* x, const double* y, double* out, int64_t n, int64_t m, int D, int kernel_id, void* stream_) {
     g_launches = 0;
     if (n < 0 || m < 1 || D < 1) return set_error(KMB_ERR_INVALID, "bad sizes n=%lld m=%lld D=%d", (long long)n, (long long)m, D);
@@ -500,7 +544,7 @@ int kmb_product_sym_workspace_bytes(int64_t n, int D, int part, int n_parts, siz
     if (!bytes) return set_error(KMB_ERR_INVALID, "bytes is NULL");
     if (n < 1) return set_error(KMB_ERR_INVALID, "bad size n=%lld", (long long)n);
     SymPlan sp;
-    if (int rc = plan_sym(n, D, part, n_parts, &sp)) return rc;
+    if (int rc = plan_sym(n, D, KMB_KERNEL_GAUSSIAN, part, n_parts, &sp)) return rc;   // the Gaussian plan (two forms) is the largest
     *bytes = sp.total_bytes;
     return KMB_OK;
 }
@@ -510,15 +554,14 @@ int kmb_product_sym_f32(const float* y, const float* b, float* out, int64_t n, i
     g_launches = 0;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (n < 1 || D < 1) return set_error(KMB_ERR_INVALID, "bad sizes n=%lld D=%d", (long long)n, D);
-    if (kernel_id != KMB_KERNEL_GAUSSIAN) return set_error(KMB_ERR_UNSUPPORTED, "the symmetric path covers the Gaussian kernel only");
     if (!y || !out) return set_error(KMB_ERR_INVALID, "y and out must not be NULL");   // b == NULL: density (b == 1)
     SymPlan sp;
-    if (int rc = plan_sym(n, D, part, n_parts, &sp)) return rc;
+    if (int rc = plan_sym(n, D, kernel_id, part, n_parts, &sp)) return rc;
     if (!workspace || workspace_bytes < sp.total_bytes)
         return set_error(KMB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", sp.total_bytes, workspace_bytes);
     if (reinterpret_cast<uintptr_t>(workspace) % 256)
         return set_error(KMB_ERR_INVALID, "workspace must be 256-byte aligned");
-    return run_direct(y, y, b, out, n, n, D, 1, kernel_id, 0, 0, sp.direct, &sp, part, n_parts, static_cast<char*>(workspace), stream);
+    return run_direct(y, y, b, out, n, n, D, 1, kernel_id, 0, 0, sp.direct, &sp, static_cast<char*>(workspace), stream);
 }
 
 }  // extern "C"

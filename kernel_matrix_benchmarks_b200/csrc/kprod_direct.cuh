@@ -139,6 +139,8 @@ __device__ __forceinline__ float product_row_scale(const DirectParams& P, long l
     return exp2f(-n2);
 }
 
+// (17 warps = 5 on one SM sub-partition of 16384 registers: 96 registers per thread is the hardware limit for one CTA per
+// SM, 48 for two -- __maxnreg__(120) compiles and then fails to launch)
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
 kprod_direct_kernel(const DirectParams P) {
@@ -579,9 +581,11 @@ constexpr int direct_rows(int DP, int EP, bool online_max) {
     kmb::make_direct_entry<kmb::DirectCfg<DP, EP,                                                          \
         kmb::direct_rows(DP, EP, (NORM) && (KID) != KMB_KERNEL_INVERSE_DISTANCE && (FORM) == 0), KID, NORM, FORM, \
         512, ((FORM) == 1 ? 8 : 4), 0, 4, ((FORM) == 1 ? 16 : 0)>>()
+// EP = 8 and 16 (two rows per thread): wide signals re-evaluate the kernel once per 8 / 16 columns instead of once per 4
 #define KMB_DIRECT_ENTRIES_FOR_DP(DP, KID, NORM, FORM)                                  \
     KMB_DIRECT_ENTRY(DP, 1, KID, NORM, FORM), KMB_DIRECT_ENTRY(DP, 2, KID, NORM, FORM), \
-        KMB_DIRECT_ENTRY(DP, 4, KID, NORM, FORM)
+        KMB_DIRECT_ENTRY(DP, 4, KID, NORM, FORM), KMB_DIRECT_ENTRY(DP, 8, KID, NORM, FORM), \
+        KMB_DIRECT_ENTRY(DP, 16, KID, NORM, FORM)
 #define KMB_DIRECT_TABLE(NAME, KID, NORM, FORM)                                                                      \
     namespace kmb {                                                                                                  \
     extern const DirectEntry NAME[];                                                                                 \

@@ -50,6 +50,14 @@ constexpr int COL_S = 0, COL_O = 256;
 constexpr int MAX_EB = 64;             // signal columns per pass
 constexpr float kLazyRescale = 8.f;    // rescale O only when the row maximum outgrew the reference by 2^8
 constexpr int PS = MAX_EB + 2;         // partial record: O row, sum of weights, reference exponent
+// The tensor cores add into the FP32 accumulator with truncation, not round-to-nearest: every accumulating MMA shrinks
+// O_g by ~2^-25 of its magnitude, and a row tile at M = 262144 makes 12288 of them per group -- measured 2.4e-4 relative
+// (every row alike, the sum of weights on the CUDA cores does not shrink with it) against the 1e-4 the path is held to.
+// So O_g only collects kFlushBlocks source blocks; then the epilogue adds it (round-to-nearest, L2 reductions the thread
+// does not wait for) to a per-(CTA, group) FP32 accumulator in global memory and the next P.B starts from zero.
+// Measured at C4 (M = 262144): flush every 2048 blocks (= never) 2.4e-4, every 32 blocks 3.6e-6 at +6 % time (the L2
+// reductions of 148 CTAs arrive together).
+constexpr int kFlushBlocks = 128;      // default of Params::flush_blocks: 768 accumulating MMAs per flush, ~1.5e-5
 
 struct Params {
     const float* un;
@@ -58,10 +66,11 @@ struct Params {
     const float* binv;         // (Ep) 2^-q_e: undoes the per-column scale of the signal planes
     float* out;
     float* partial;
+    float* olong;              // grid x NG x MAX_EB x TM: long accumulators of the O_g, [column][row] (see kFlushBlocks)
     int* tile_counter;
     long long N, M;
     int E, e0, eb, ebp;        // this pass covers signal columns e0 .. e0+eb-1; ebp = eb rounded up to 32
-    int n_tiles, nsb, kblocks, ksteps_last, stages, ep_rows;
+    int n_tiles, nsb, kblocks, ksteps_last, stages, ep_rows, flush_blocks;
     int R, C, W, R_last, C_last, slots_per_wave;
 };
 
@@ -258,7 +267,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
 #else
 #define KMB_M(i) do { } while (0)
 #endif
-        auto issue_pv = [&](uint32_t m, bool first_of_tile) {
+        auto issue_pv = [&](uint32_t m, bool from_zero) {   // from_zero: the O_g were flushed (or the tile starts)
             const int a = m & 1;
             KMB_M(0);
             mbar_wait(&p_ready[a], (m >> 1) & 1);
@@ -278,7 +287,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     const uint64_t bl = umma_desc_sw128(sg + (2 + panel) * PANEL, koff);
                     const uint32_t a_hi = p_base + g * CPT + (k & 1) * 8, a_lo = a_hi + CPT / 2;
                     const uint32_t d_g = d_o + g * MAX_EB;
-                    mma_ts(d_g, a_lo, bh, idesc_o, !(first_of_tile && (k & 1) == 0));
+                    mma_ts(d_g, a_lo, bh, idesc_o, !(from_zero && (k & 1) == 0));
                     mma_ts(d_g, a_hi, bl, idesc_o, 1);
                     mma_ts(d_g, a_hi, bh, idesc_o, 1);
                 }
@@ -294,7 +303,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
             mbar_wait(u_full, seg & 1);
             ++seg;
             for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++n) {
-                const bool first = (sb == ww.sb_lo);
+                const bool first = ((sb - ww.sb_lo) % P.flush_blocks == 0);
                 const int a = n & 1;   // stage a held P(n-2): PV(n-2) was issued in the previous iteration
                 const uint32_t d_s = tmem_base + COL_S + a * TNS;
                 for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
@@ -375,6 +384,17 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
             const bool row_ok = row < P.N;
             const float un = row_ok ? __ldg(P.un + row) : 0.f;
             float ksum = 0.f, ref = -INFINITY;   // this group's stream
+            // long accumulator of this thread's O_g row: zero, then only ever touched by this thread until the merge
+            float* olong = P.olong + (static_cast<size_t>(blockIdx.x) * NG + cg) * (MAX_EB * TM) + row_in_tile;
+            for (int c = 0; c < P.ebp; ++c) __stcg(olong + c * TM, 0.f);
+            auto flush_o = [&]() {   // olong += O_g (after the last P.B into it has completed)
+                for (int c0 = 0; c0 < P.ebp; c0 += 16) {
+                    float o[16];
+                    tmem_ld_cols<16>(o_mine + c0, o);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) atomicAdd(olong + (c0 + c) * TM, o[c]);   // RED: nothing to wait for
+                }
+            };
             if (!primed) {
                 vn_next = __ldg(P.vn + static_cast<long long>(ww.sb_lo) * TNS + col0 + lane);   // padded to whole blocks with 3.4e38
                 primed = true;
@@ -448,6 +468,8 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                                 tmem_st_cols<16>(o_mine + c0, o);
                             }
                             tmem_st_wait();
+                            if (sb - ww.sb_lo >= P.flush_blocks && sc != 1.f)   // something was flushed already
+                                for (int c = 0; c < P.ebp; ++c) __stcg(olong + c * TM, sc * __ldcg(olong + c * TM));
                         }
                         ksum *= sc;
                         if (need) ref = cm;
@@ -479,6 +501,10 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 }
                 KMB_T(5);
                 tmem_st_wait();
+                if (sb > ww.sb_lo && (sb - ww.sb_lo) % P.flush_blocks == 0) {   // P.B(n) starts the O_g from zero
+                    wait_pv(n - 1);
+                    flush_o();
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -497,6 +523,9 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
             // ------------------------------ row tile done: merge the four streams ------------------------------
             refbuf[cg * TM + row_in_tile] = ref;
             ksbuf[cg * TM + row_in_tile] = ksum;
+            wait_pv(n - 1);   // the tile's last PV
+            flush_o();        // the long accumulators now hold the whole tile
+            __threadfence();
             named_bar_sync(2, EPI_THREADS);
             float rmax = -INFINITY, wg[NG], ktot = 0.f;
 #pragma unroll
@@ -507,7 +536,6 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 wg[g] = (rg == -INFINITY) ? 0.f : ex2_approx(rg - rmax);
                 ktot = fmaf(wg[g], ksbuf[g * TM + row_in_tile], ktot);   // fixed order
             }
-            wait_pv(n - 1);   // the tile's last PV
             const bool complete = (ww.Cw == 1);
             const bool ghost = tile >= P.n_tiles;   // pairs: an odd number of row tiles leaves the last peer without one
             // partial records of one wave: [row tile or pair in wave][range c]([rank])
@@ -521,10 +549,9 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 for (int c = 0; c < 16; ++c) o[c] = 0.f;
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    float og[16];
-                    tmem_ld_cols<16>(tmem_base + COL_O + g * MAX_EB + c0 + lane_addr, og);
+                    const float* og = P.olong + (static_cast<size_t>(blockIdx.x) * NG + g) * (MAX_EB * TM) + row_in_tile;
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) o[c] = fmaf(wg[g], og[c], o[c]);
+                    for (int c = 0; c < 16; ++c) o[c] = fmaf(wg[g], __ldcg(og + (c0 + c) * TM), o[c]);
                 }
                 if (ghost) continue;
                 if (complete) {
@@ -665,7 +692,7 @@ struct Pv16Plan {
     long long n_tiles, nsb, Mp;
     tc::WavePlan waves;
     size_t off_center, off_stats, off_sscale, off_uh, off_ul, off_vh, off_vl, off_un, off_vn, off_sh, off_sl, off_bmax, off_bscale,
-        off_binv, off_partial, off_counter, total;
+        off_binv, off_partial, off_olong, off_counter, total;
 };
 
 int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
@@ -711,6 +738,7 @@ int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
     pl->off_bscale = take(sizeof(float) * pl->Ep);
     pl->off_binv = take(sizeof(float) * pl->Ep);
     pl->off_partial = take(sizeof(float) * pl->waves.partial_slots * tc::TM * pv16::PS);
+    pl->off_olong = take(sizeof(float) * pl->grid * pv16::NG * pv16::MAX_EB * tc::TM);
     pl->off_counter = take(sizeof(int) * pl->n_tiles);
     pl->total = o;
     return KMB_OK;
@@ -794,6 +822,7 @@ int tensor_pv16_product(const float* x, const float* y, const float* b, float* o
         P.binv = F(pl.off_binv);
         P.out = out;
         P.partial = F(pl.off_partial);
+        P.olong = F(pl.off_olong);
         P.tile_counter = counters;
         P.N = N;
         P.M = M;
@@ -812,6 +841,12 @@ int tensor_pv16_product(const float* x, const float* y, const float* b, float* o
         P.ksteps_last = pl.ksteps_last;
         P.stages = pl.stages;
         P.ep_rows = pl.Ep;
+        static const int flush_blocks = [] {   // tuning knob
+            const char* e = getenv("KMB_PV16_FLUSH_BLOCKS");
+            const int v = e ? atoi(e) : pv16::kFlushBlocks;
+            return v < 1 ? 1 : v;
+        }();
+        P.flush_blocks = flush_blocks;
         P.R = pl.waves.R;
         P.C = pl.waves.C;
         P.W = pl.waves.W;

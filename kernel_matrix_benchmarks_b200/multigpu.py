@@ -134,8 +134,8 @@ class DeviceGroup:
         return (path == "auto" and y0.shape[0] >= SYM_MIN_POINTS
                 and symmetric_applies(y0, y0, kernel, normalize_rows, density_estimation, E))
 
-    def product_sym(self, ys, bs, out0):
-        """Gaussian product with targets == sources: device i evaluates range i of the triangular unit list, the first
+    def product_sym(self, ys, bs, out0, kernel="gaussian"):
+        """Product with targets == sources: device i evaluates range i of the triangular unit list, the first
         device adds the partial vectors (peer reads) into ``out0`` (n, 1).  ``bs`` as in product_rows (None: density)."""
         lib = _lib.load()
         n, D = ys[0].shape
@@ -156,7 +156,7 @@ class DeviceGroup:
             sh.out = self.parts[i].data_ptr() if self.n > 1 else out0.data_ptr()
             sh.workspace, sh.workspace_bytes = ws.data_ptr(), ws.numel()
             sh.stream = self._stream(i)
-        _lib.check(lib.kmb_product_sym_multi_f32(shards, self.n, ctypes.c_void_p(out0.data_ptr()), n, D, _lib.KERNEL_IDS["gaussian"]))
+        _lib.check(lib.kmb_product_sym_multi_f32(shards, self.n, ctypes.c_void_p(out0.data_ptr()), n, D, _lib.KERNEL_IDS[kernel]))
         self.launches = int(lib.kmb_last_launch_count())
         return out0
 
@@ -180,7 +180,7 @@ class MultiDeviceSymmetricOps(CudaShardOps):
         if p_full.shape[1] != 1:
             raise NotImplementedError("the symmetric matvec takes one right-hand side")
         self._ap(1)
-        self.group.product_sym(self.ys, p_full, self.Ap)
+        self.group.product_sym(self.ys, p_full, self.Ap, kernel=self.kernel)
         self.launches += self.group.launches
         return self.Ap
 

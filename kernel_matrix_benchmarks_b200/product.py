@@ -50,8 +50,9 @@ last_path = None  # the path the last kernel_product call asked the library for 
 
 
 def symmetric_applies(x, y, kernel, normalize_rows=False, density_estimation=False, E=1):
-    """targets *are* the sources (same tensor), plain Gaussian product or density, D <= 3, E == 1."""
-    return (x.data_ptr() == y.data_ptr() and x.shape == y.shape and kernel == "gaussian" and not normalize_rows
+    """targets *are* the sources (same tensor), plain product or density of any kernel (all of bruteforce.py:18-22 are
+    functions of |x - y|, so K is symmetric), D <= 3, E == 1."""
+    return (x.data_ptr() == y.data_ptr() and x.shape == y.shape and kernel in _lib.KERNEL_IDS and not normalize_rows
             and E == 1 and x.shape[1] <= 3)
 
 
@@ -133,8 +134,8 @@ def kernel_product(x, y, b, *, kernel="gaussian", normalize_rows=False, density_
     return out
 
 
-def kernel_product_sym_part(y, b, part, n_parts, *, out=None, workspace=None):
-    """This part's share of the Gaussian product with targets == sources (kmb_product_sym_f32).
+def kernel_product_sym_part(y, b, part, n_parts, *, kernel="gaussian", out=None, workspace=None):
+    """This part's share of the product with targets == sources (kmb_product_sym_f32).
 
     Returns an (n, 1) tensor; the shares of all ``n_parts`` parts add up to K b (the caller
     all-reduces them when every part runs on its own GPU).  Asynchronous on the current stream.
@@ -156,7 +157,7 @@ def kernel_product_sym_part(y, b, part, n_parts, *, out=None, workspace=None):
         workspace = _default_ws.setdefault(y.device, Workspace())
     ws = workspace.get(need.value, y.device)
     with torch.cuda.device(y.device):
-        _lib.check(lib.kmb_product_sym_f32(_ptr(y), _ptr(b), _ptr(out), n, D, _lib.KERNEL_IDS["gaussian"], int(part),
+        _lib.check(lib.kmb_product_sym_f32(_ptr(y), _ptr(b), _ptr(out), n, D, _lib.KERNEL_IDS[kernel], int(part),
                                            int(n_parts), _ptr(ws), ws.numel(), _stream()))
     return out
 

