@@ -97,6 +97,18 @@ def _to_device(array, device, precision=np.float32, comm=None):
     return out
 
 
+def _to_host_f64(t):
+    """Device result -> fresh float64 host array (base.py:116 / :167): one copy into pinned memory, one widening pass."""
+    if t.dtype not in (torch.float32, torch.float64) or t.numel() == 0:
+        return np.ascontiguousarray(t.cpu().numpy(), dtype=np.float64)
+    stage = _staging(tuple(t.shape), np.float64 if t.dtype == torch.float64 else np.float32)
+    stage.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    out = np.empty(tuple(t.shape), dtype=np.float64)
+    _cast_into(out, stage.numpy())
+    return out
+
+
 _STAGING = {}
 
 
@@ -333,8 +345,8 @@ class B200Product(BaseProduct):
 
     def get_result(self):
         """Untimed device->host copy; float64 contiguous as base.py:116."""
-        self.res = self.res_device.cpu().numpy()
-        return np.ascontiguousarray(self.res, dtype=np.float64)
+        self.res = _to_host_f64(self.res_device.contiguous())
+        return self.res
 
     def get_additional(self):
         """Extra attrs stored with the result (runner.py:162 -> results.py:116-117)."""
@@ -544,8 +556,8 @@ class B200Solver(BaseSolver):
         self.query_ms = t.ms()
 
     def get_result(self):
-        self.res = self.x_full.cpu().numpy()
-        return np.ascontiguousarray(self.res, dtype=np.float64)
+        self.res = _to_host_f64(self.x_full.contiguous())
+        return self.res
 
     def get_additional(self):
         if self.info is None:

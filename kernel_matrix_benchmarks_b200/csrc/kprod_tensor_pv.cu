@@ -39,12 +39,18 @@ constexpr int TMEM_COLS = 512;
 constexpr int COL_S = 0, COL_PH = 128, COL_PL = 192, COL_O = 256;
 constexpr int MAX_EB = 64;             // signal columns per pass
 constexpr float kLazyRescale = 64.f;   // rescale O only when the row maximum grows by more than 2^64
+// The tensor cores add into the FP32 accumulator with truncation (see kprod_tensor_pv16.cu: 2.4e-4 relative after 12288
+// accumulating MMAs); this kernel makes 24 per 64-source block.  O therefore only collects kFlushBlocks blocks; then each
+// epilogue thread adds its chunks of O (round-to-nearest, L2 reductions it does not wait for) to a per-CTA FP32
+// accumulator in global memory and the next P.B starts from zero.
+constexpr int kFlushBlocks = 64;
 
 struct Params {
     const float* un;
     const float* vn;
     float* out;
     float* partial;
+    float* olong;              // grid x MAX_EB x TM: long accumulator of O, [column][row] (see kFlushBlocks)
     int* tile_counter;
     long long N, M, row_offset;
     int E, e0, eb;             // this pass covers signal columns e0 .. e0+eb-1; ebp = eb rounded up to 32
@@ -187,7 +193,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
         {
             uint32_t it = 0, n = 0, seg = 0;
             const uint32_t d_o = tmem_base + COL_O;
-            auto issue_pv = [&](uint32_t m, bool first_of_segment) {
+            auto issue_pv = [&](uint32_t m, bool from_zero) {   // from_zero: O was flushed (or the segment starts)
                 mbar_wait(p_ready, m & 1);
                 const int slot_h = it % ST;
                 mbar_wait(&full_bar[slot_h], (it / ST) & 1);
@@ -205,7 +211,7 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                         const uint64_t bh = umma_desc_sw128(sh + panel * HALF_SLOT, koff);
                         const uint64_t bl = umma_desc_sw128(sl + panel * HALF_SLOT, koff);
                         const uint32_t a_hi = tmem_base + COL_PH + k * UMMA_K, a_lo = tmem_base + COL_PL + k * UMMA_K;
-                        umma_tf32_ts(d_o, a_lo, bh, idesc_o, !(first_of_segment && k == 0));
+                        umma_tf32_ts(d_o, a_lo, bh, idesc_o, !(from_zero && k == 0));
                         umma_tf32_ts(d_o, a_hi, bl, idesc_o, 1);
                         umma_tf32_ts(d_o, a_hi, bh, idesc_o, 1);
                     }
@@ -220,12 +226,15 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
             for (int w = 0; w < P.W; ++w) {
             if (!wave_range(P, w, cta, wr)) continue;
             const long long u0 = wr.u0, u1 = wr.u1;
+            long long seg_u0 = u0;
             for (long long u = u0; u < u1; ++u, ++n) {
-                const bool first = (u == u0) || (u % nsb == 0);
+                bool first = (u == u0) || (u % nsb == 0);
                 if (first) {
                     mbar_wait(u_full, seg & 1);
                     ++seg;
+                    seg_u0 = u;
                 }
+                first = ((u - seg_u0) % kFlushBlocks == 0);   // O restarts from zero at every flush
                 const int a = n & 1;
                 mbar_wait(&acc_empty[a], ((n >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -305,6 +314,11 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
             const float un = row_ok ? __ldg(P.un + row) : 0.f;
             [[maybe_unused]] const long long jz = (P.row_offset + row) % (P.M + 1);
             float ksum = 0.f, ref = -INFINITY;   // ksum: this group's columns only
+            // long accumulator of this thread's 16-column chunks of O: zero, then only ever touched by this thread
+            float* olong = P.olong + static_cast<size_t>(blockIdx.x) * (MAX_EB * TM) + row_in_tile;
+            for (int c0 = cg * 16; c0 < P.ebp; c0 += NG * 16)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) __stcg(olong + (c0 + c) * TM, 0.f);
 
             for (int k = 0; k < cnt; ++k, ++n) {
                 const long long j0 = (sb0 + k) * TN;
@@ -353,6 +367,14 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                 }
                 KMB_T(4);
                 ensure_pv_done(n);   // PV(n-1) has read P and finished accumulating into O
+                if (k > 0 && k % kFlushBlocks == 0) {   // PV(n) starts O from zero: move what it holds to the long accumulator
+                    for (int c0 = cg * 16; c0 < P.ebp; c0 += NG * 16) {
+                        float o[16];
+                        tmem_ld_cols<16>(tmem_base + COL_O + c0 + lane_addr, o);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) atomicAdd(olong + (c0 + c) * TM, o[c]);   // RED: nothing to wait for
+                    }
+                }
                 KMB_T(5);
                 if constexpr (C::ONLINE_MAX) {
                     // lazy rescale: keep the reference exponent unless the row maximum outgrew it by 2^64
@@ -367,6 +389,9 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
 #pragma unroll
                             for (int c = 0; c < 16; ++c) o[c] *= sc;
                             tmem_st_cols<16>(tmem_base + COL_O + c0 + lane_addr, o);
+                            if (k >= kFlushBlocks && sc != 1.f)   // something was flushed already
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) __stcg(olong + (c0 + c) * TM, sc * __ldcg(olong + (c0 + c) * TM));
                         }
                         tmem_st_wait();
                         ksum *= sc;
@@ -417,6 +442,8 @@ kprod_tensor_pv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
             for (int c0 = cg * 16; c0 < P.ebp; c0 += NG * 16) {   // this group's 16-column chunks of O
                 float o[16];
                 tmem_ld_cols<16>(tmem_base + COL_O + c0 + lane_addr, o);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) o[c] += __ldcg(olong + (c0 + c) * TM);   // what earlier flushes moved out of O
                 if (complete) {
                     if (row_ok) {
 #pragma unroll
@@ -507,7 +534,7 @@ struct PvPlan {
     int Dp, Ep, kblocks, stages, grid_max, smem;
     long long n_tiles, nsb, Mp;
     tc::WavePlan waves;
-    size_t off_center, off_cpart, off_uh, off_ul, off_vh, off_vl, off_un, off_vn, off_sh, off_sl, off_partial, off_counter, total;
+    size_t off_center, off_cpart, off_uh, off_ul, off_vh, off_vl, off_un, off_vn, off_sh, off_sl, off_partial, off_olong, off_counter, total;
 };
 
 int plan_pv(int64_t N, int64_t M, int D, int E, PvPlan* pl) {
@@ -540,6 +567,7 @@ int plan_pv(int64_t N, int64_t M, int D, int E, PvPlan* pl) {
     pl->off_sl = take(sizeof(float) * pl->Ep * pl->Mp);
     tc::plan_waves(pl->n_tiles, pl->nsb, pl->grid_max, static_cast<size_t>(tc::TM) * pl->Dp * 8, &pl->waves);
     pl->off_partial = take(sizeof(float) * pl->waves.partial_slots * tc::TM * (pv::MAX_EB + 2));
+    pl->off_olong = take(sizeof(float) * pl->grid_max * pv::MAX_EB * tc::TM);
     pl->off_counter = take(sizeof(int) * pl->n_tiles);
     pl->total = o;
     return KMB_OK;
@@ -607,6 +635,7 @@ int tensor_pv_product(const float* x, const float* y, const float* b, float* out
         P.vn = F(pl.off_vn);
         P.out = out;
         P.partial = F(pl.off_partial);
+        P.olong = F(pl.off_olong);
         P.tile_counter = counters;
         P.N = N;
         P.M = M;

@@ -423,41 +423,58 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 mbar_wait(&acc_full[a], (n >> 1) & 1);
                 tc_fence_after();
                 KMB_T(1);
-                float2 t2[CPT / 2];   // S as pairs of sources, then t = -log2 k
-                tmem_ld_cols<CPT>(st_addr, reinterpret_cast<float(&)[CPT]>(t2));
-                KMB_T(2);
-
-                // t = -log2 of the kernel values (packed pairs) and their minimum over this thread's columns
-                float tmin = INFINITY;
-                if (j0 < P.M) {
-                    const float2 nss2 = make_float2(-sscale, -sscale), un2 = make_float2(un, un);
+                // One fused pass per block: S -> t = -log2 k -> P = 2^(-ref - t) with the reference exponent the row ALREADY has
+                // (it is lazy: it only moves when the block maximum outgrows it by 2^8), FP16 hi / lo, packed.  rsqrt / ex2
+                // (MUFU) and the packed FP32 work of different columns interleave instead of forming two phases in which the
+                // four warps of an SM sub-partition first all wait for the FMA pipe and then all for the MUFU pipe.  If the
+                // reference has to move (first block of a tile; afterwards almost never) the O_g are rescaled and the pass is
+                // repeated from the S columns, which are still in tensor memory.
+                uint32_t ph[CPT / 2], pl[CPT / 2];
+                float2 kacc;
+                bool again;
+                do {
+                    float2 t2[CPT / 2];   // S as pairs of sources
+                    tmem_ld_cols<CPT>(st_addr, reinterpret_cast<float(&)[CPT]>(t2));
+                    KMB_T(2);
+                    constexpr bool kRowTermOut = (KID == KMB_KERNEL_GAUSSIAN);   // t lacks the row's |u|^2
+                    // all -inf so far: every weight is 2^-inf = 0
+                    const float nref = (ref == -INFINITY) ? 0.f : (kRowTermOut ? -ref - un : -ref);
+                    const float2 nref2 = make_float2(nref, nref);
+                    float2 tmin2[2] = {make_float2(INFINITY, INFINITY), make_float2(INFINITY, INFINITY)};
+                    kacc = make_float2(0.f, 0.f);   // two-level sum of the weights (see kprod_direct.cuh)
+                    if (j0 < P.M) {
+                        const float2 nss2 = make_float2(-sscale, -sscale), un2 = make_float2(un, un);
 #pragma unroll
-                    for (int c = 0; c < CPT / 4; ++c) {
-                        const float4 vq = vnq[c];   // broadcast read of the warp's line
-                        // Gaussian: |u|^2 is the same for the whole row, so it is left out of t here and added to the
-                        // block minimum / subtracted with the reference exponent below (one FADD2 per four values less)
-                        const float2 wa = make_float2(vq.x, vq.y), wb = make_float2(vq.z, vq.w);
-                        const float2 ta = neg_log2_kernel2<KID>(t2[2 * c], nss2, KID == KMB_KERNEL_GAUSSIAN ? wa : add2(wa, un2));
-                        const float2 tb = neg_log2_kernel2<KID>(t2[2 * c + 1], nss2, KID == KMB_KERNEL_GAUSSIAN ? wb : add2(wb, un2));
-                        t2[2 * c] = ta;
-                        t2[2 * c + 1] = tb;
-                        tmin = fminf(fminf(tmin, ta.x), ta.y);
-                        tmin = fminf(fminf(tmin, tb.x), tb.y);
+                        for (int c = 0; c < CPT / 2; ++c) {
+                            const float4 vq = vnq[c >> 1];   // broadcast read of the warp's line
+                            // Gaussian: |u|^2 is the same for the whole row, so it is left out of t here and added to the
+                            // block minimum / subtracted with the reference exponent (one FADD2 per four values less)
+                            const float2 w = (c & 1) ? make_float2(vq.z, vq.w) : make_float2(vq.x, vq.y);
+                            const float2 t = neg_log2_kernel2<KID>(t2[c], nss2, KID == KMB_KERNEL_GAUSSIAN ? w : add2(w, un2));
+                            tmin2[c & 1] = make_float2(fminf(tmin2[c & 1].x, t.x), fminf(tmin2[c & 1].y, t.y));
+                            const float2 e = sub2(nref2, t);
+                            const float2 pw = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+                            kacc = add2(kacc, pw);
+                            // 11 significant bits: exact in FP16
+                            const float2 h = make_float2(__uint_as_float(__float_as_uint(pw.x) & 0xffffe000u),
+                                                         __uint_as_float(__float_as_uint(pw.y) & 0xffffe000u));
+                            const float2 l = sub2(pw, h);
+                            ph[c] = pack_half2(h.x, h.y);
+                            pl[c] = pack_half2(l.x, l.y);
+                        }
+                    } else {   // every source of this group is padding (warp-uniform): all weights are zero
+#pragma unroll
+                        for (int c = 0; c < CPT / 2; ++c) ph[c] = pl[c] = 0u;
                     }
-                } else {   // every source of this group is padding (warp-uniform): all weights are zero
-#pragma unroll
-                    for (int c = 0; c < CPT / 2; ++c) t2[c] = make_float2(INFINITY, INFINITY);
-                }
-                constexpr bool kRowTermOut = (KID == KMB_KERNEL_GAUSSIAN);   // t2 lacks the row's |u|^2
-                const float cm = kRowTermOut ? -(tmin + un) : -tmin;   // largest log2 k of the block
-                KMB_T(3);
-                // lazy rescale: keep the reference exponent unless the maximum outgrew it by 2^8
-                {
-                    bool need = false;
-                    if (ref == -INFINITY) ref = cm;   // nothing but zero weights so far
-                    else need = cm > ref + kLazyRescale;
-                    if (__any_sync(0xffffffffu, need)) {
-                        const float sc = need ? ex2_approx(ref - cm) : 1.f;
+                    const float tmin = fminf(fminf(tmin2[0].x, tmin2[0].y), fminf(tmin2[1].x, tmin2[1].y));
+                    const float cm = kRowTermOut ? -(tmin + un) : -tmin;   // largest log2 k of the block
+                    KMB_T(3);
+                    // lazy rescale: keep the reference exponent unless the maximum outgrew it by 2^8 (P <= 2^8 fits FP16;
+                    // a first block, ref == -inf, always adopts its maximum)
+                    const bool need = (ref == -INFINITY) ? (cm != -INFINITY) : (cm > ref + kLazyRescale);
+                    again = __any_sync(0xffffffffu, need);
+                    if (again) {
+                        const float sc = need ? ex2_approx(ref - cm) : 1.f;   // ref == -inf: 0 (nothing accumulated yet)
                         if (sb > ww.sb_lo) {   // O_g holds this tile's sums
                             wait_pv(n - 1);
                             for (int c0 = 0; c0 < P.ebp; c0 += 16) {
@@ -474,31 +491,12 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                         ksum *= sc;
                         if (need) ref = cm;
                     }
-                }
-                KMB_T(4);
-                // P = 2^(log2 k - ref) = 2^(-ref - t), FP16 hi / lo, two sources per TMEM column, over this thread's own S columns
-                {
-                    uint32_t ph[CPT / 2], pl[CPT / 2];
-                    float2 kacc = make_float2(0.f, 0.f);   // two-level sum of the weights (see kprod_direct.cuh)
-                    // all -inf so far: every weight is 2^-inf = 0
-                    const float nref = (ref == -INFINITY) ? 0.f : (kRowTermOut ? -ref - un : -ref);
-                    const float2 nref2 = make_float2(nref, nref);
-#pragma unroll
-                    for (int c = 0; c < CPT / 2; ++c) {
-                        const float2 e = sub2(nref2, t2[c]);
-                        const float2 pw = make_float2(ex2_approx(e.x), ex2_approx(e.y));
-                        kacc = add2(kacc, pw);
-                        // 11 significant bits: exact in FP16
-                        const float2 h = make_float2(__uint_as_float(__float_as_uint(pw.x) & 0xffffe000u),
-                                                     __uint_as_float(__float_as_uint(pw.y) & 0xffffe000u));
-                        const float2 l = sub2(pw, h);
-                        ph[c] = pack_half2(h.x, h.y);
-                        pl[c] = pack_half2(l.x, l.y);
-                    }
-                    tmem_st_32x16(st_addr, reinterpret_cast<const float*>(ph));
-                    tmem_st_32x16(st_addr + CPT / 2, reinterpret_cast<const float*>(pl));
-                    ksum += kacc.x + kacc.y;
-                }
+                    KMB_T(4);
+                } while (again);
+                // P over this thread's own S columns: FP16 hi / lo, two sources per TMEM column
+                tmem_st_32x16(st_addr, reinterpret_cast<const float*>(ph));
+                tmem_st_32x16(st_addr + CPT / 2, reinterpret_cast<const float*>(pl));
+                ksum += kacc.x + kacc.y;
                 KMB_T(5);
                 tmem_st_wait();
                 if (sb > ww.sb_lo && (sb - ww.sb_lo) % P.flush_blocks == 0) {   // P.B(n) starts the O_g from zero

@@ -164,3 +164,47 @@ def test_wave_schedule_covers_every_unit_once(n_tiles, nsb, grid, tile_bytes):
     assert (seen == 1).all()
     ideal = n_tiles * nsb / grid
     assert steps <= max(1.12 * ideal + 1, ideal + 2), (steps, ideal, plan)
+
+
+@pytest.mark.parametrize("n, ctas", [(1, 148), (4097, 1), (40000, 148), (100000, 148), (100000, 8 * 148), (300000, 2)])
+def test_symmetric_unit_list_covers_the_upper_block_triangle_once(n, ctas):
+    """kprod_sym.cuh: the strip-ordered unit list (kmb_debug_sym_unit, host logic only) enumerates every
+    (row tile, source block) pair on or above the block diagonal exactly once, strip by strip, tile by tile, block by
+    block, and the segment a unit reports contains it."""
+    import ctypes
+
+    from kernel_matrix_benchmarks_b200 import _lib
+
+    lib = _lib.load()
+
+    def unit(u):
+        o = (ctypes.c_int64 * 8)()
+        _lib.check(lib.kmb_debug_sym_unit(n, ctas, u, o))
+        return list(o)
+
+    total, n_strips, wb = unit(-1)[:3]
+    nsb, n_tiles = (n + 511) // 512, (n + 4095) // 4096
+    assert total == sum(nsb - 8 * t for t in range(n_tiles)) and wb % 8 == 0 and n_strips == -(-nsb // wb) <= 96
+    seen, prev = set(), None
+    for u in range(total):
+        _, _, _, strip, tile, block, begin, length = unit(u)
+        assert 8 * tile <= block < nsb and tile < n_tiles and strip == block // wb and begin <= u < begin + length
+        key = (strip, tile, block)
+        assert prev is None or key > prev
+        prev = key
+        seen.add((tile, block))
+    assert len(seen) == total
+
+
+def test_symmetric_strip_width_follows_the_cta_count():
+    """Wb ~ nsb / sqrt(2 G): a CTA's contiguous range is a roughly square patch of the pair matrix."""
+    import ctypes
+
+    from kernel_matrix_benchmarks_b200 import _lib
+
+    lib = _lib.load()
+    o = (ctypes.c_int64 * 8)()
+    _lib.check(lib.kmb_debug_sym_unit(1_000_000, 148, -1, o))
+    assert (o[1], o[2]) == (17, 120)
+    _lib.check(lib.kmb_debug_sym_unit(10_000_000, 8 * 148, -1, o))
+    assert o[1] <= 96 and 380 <= o[2] <= 420

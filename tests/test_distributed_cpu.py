@@ -117,7 +117,8 @@ def test_shard_bounds_cover_rows_exactly():
 # with float64 oracle arithmetic, so the N > 1 logic of CudaSymmetricOps is exercised on CPU.
 
 def sym_prefix(I, nsb, TB):
-    """units of tiles 0 .. I-1: sum_{t<I} (nsb - TB t)   (kprod_sym.cuh: sym_prefix)"""
+    """units of tiles 0 .. I-1: sum_{t<I} (nsb - TB t).  (A tile-major stand-in for the unit list: the CUDA kernel orders
+    the same units strip by strip -- kprod_sym.cuh, checked in test_abi_cpu.py -- which the host logic never sees.)"""
     return I * nsb - (TB * I * (I - 1)) // 2
 
 
@@ -277,3 +278,52 @@ def test_pcg_sharded_gloo(tmp_path):
                      torch.from_numpy(orc.regularised_matvec("absolute-exponential", pts, b, lam)).clone(), n, lam=lam,
                      rtol=1e-9, max_iter=500)
     assert int(parts[0]["it"]) * 2 <= plain.iterations
+
+
+# ---- symmetric mode with the preconditioner built from row shards and replicated, collective stop decision ----
+
+def _sym_pcg_worker(rank, world, port, n, lam, out_dir):
+    from kernel_matrix_benchmarks_b200.solver import NystromPreconditioner, ReplicatedComm, landmark_indices, pcg_solve
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.RandomState(21)
+        pts, b = rng.rand(n, 3), rng.randn(n, 1)
+        rhs = orc.regularised_matvec("gaussian", pts, b, lam)
+        lo, hi, _ = shard_bounds(n, rank, world)
+        comm = TorchDistComm()
+        tp = torch.from_numpy(pts)
+        pc = NystromPreconditioner(tp[lo:hi], tp[landmark_indices(n, 150)], "gaussian", lam, comm,
+                                   block_fn=_oracle_block("gaussian"), dtype=torch.float64).replicate(n)
+        assert pc.U.shape[0] == n and pc.comm.world == 1
+        ops = OracleSymmetricOps(pts, "gaussian", comm)
+        res = pcg_solve(ops, ReplicatedComm(comm), torch.from_numpy(rhs).clone(), n, pc, lam=lam, rtol=1e-9, max_iter=100)
+        np.savez(os.path.join(out_dir, f"spcg{rank}.npz"), x=res.x.numpy(), it=res.iterations, conv=res.converged, U=pc.U.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 333), (3, 200)])
+def test_symmetric_pcg_with_sharded_build_gloo(tmp_path, world, n):
+    """B200Solver(distributed=True), symmetric matvec: every rank builds 1 / world of the Nystrom factors, U is all-gathered,
+    the CG vectors are replicated and the ranks agree on when to stop (solver.ReplicatedComm.agree)."""
+    from kernel_matrix_benchmarks_b200.solver import NystromPreconditioner, landmark_indices
+
+    lam = 1.0
+    mp.spawn(_sym_pcg_worker, args=(world, _free_port(), n, lam, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.RandomState(21)
+    pts, b = rng.rand(n, 3), rng.randn(n, 1)
+    parts = [np.load(tmp_path / f"spcg{r}.npz") for r in range(world)]
+    assert all(bool(p["conv"]) for p in parts) and len({int(p["it"]) for p in parts}) == 1
+    for p in parts:
+        assert p["x"].shape == (n, 1) and orc.rel_l2(p["x"], b) <= 1e-6
+        assert np.array_equal(p["U"], parts[0]["U"]), "every rank must hold the same U"
+    # the replicated U spans the same space as a single-process build (columns may differ by sign / rotation within clusters)
+    tp = torch.from_numpy(pts)
+    one = NystromPreconditioner(tp, tp[landmark_indices(n, 150)], "gaussian", lam, block_fn=_oracle_block("gaussian"), dtype=torch.float64)
+    v = torch.from_numpy(rng.randn(n, 1))
+    many = NystromPreconditioner.__new__(NystromPreconditioner)
+    many.U, many.comm, many.eigenvalues = torch.from_numpy(parts[0]["U"]), LocalComm(), one.eigenvalues
+    many.set_shift(lam)
+    assert orc.rel_l2(many.apply(v).numpy(), one.apply(v).numpy()) <= 1e-6

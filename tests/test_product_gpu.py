@@ -17,8 +17,6 @@ pytestmark = pytest.mark.gpu
 TOL_DIRECT = 1e-5
 TOL_TENSOR = 1e-4
 PRODUCT_CASES = product_golden_names()
-TENSOR_PATH_BUILT = True  # both tensor paths (3xFP16 planes, 3xTF32 planes) are built; False would xfail the D > 16 goldens
-
 
 def run_plugin(kernel, y, x, b, *, same_points=False, normalize_rows=False, density=False, path="auto"):
     """The call sequence of runner.py:73-143."""
@@ -39,18 +37,7 @@ def run_plugin(kernel, y, x, b, *, same_points=False, normalize_rows=False, dens
     return out, extra
 
 
-def _golden_params():
-    out = []
-    for n in PRODUCT_CASES:
-        D = load_golden(n)["source_points"].shape[1]
-        marks = []
-        if D > 16 and not TENSOR_PATH_BUILT:
-            marks = [pytest.mark.xfail(reason="tcgen05 3xTF32 path not built yet", raises=NotImplementedError, strict=True)]
-        out.append(pytest.param(n, marks=marks))
-    return out
-
-
-@pytest.mark.parametrize("name", _golden_params())
+@pytest.mark.parametrize("name", PRODUCT_CASES)
 def test_golden_vectors(name):
     g = load_golden(name)
     D = g["source_points"].shape[1]
@@ -398,6 +385,25 @@ def test_config_c4_full_size_sampled():
         worst = np.max(np.linalg.norm(out[rows] - want, axis=1) / np.linalg.norm(want, axis=1))
         print(f"C4 full size {kernel}: sampled rel-L2 {err:.2e} (worst row {worst:.2e}) over {len(rows)} rows {extra}")
         assert err <= TOL_TENSOR and worst <= 5 * TOL_TENSOR
+
+
+@pytest.mark.parametrize("kernel, path, norm", [("inverse-distance", "auto", False), ("inverse-distance", "auto", True),
+                                                ("gaussian", "tensor_tf32", True), ("gaussian", "auto", False)])
+def test_wide_signal_tensor_kernels_over_many_source_blocks(kernel, path, norm):
+    """M = 262 144 sources against a few row tiles, D = 64, E = 16: the P.B accumulators of the E > 4 tensor kernels
+    (kprod_tensor_pv.cu for the inverse-distance kernel and the TF32 planes, kprod_tensor_pv16.cu otherwise) collect
+    thousands of source blocks per row tile.  The tensor cores truncate when they add into the FP32 accumulator, which
+    grew to 2.4e-4 relative at this M before the accumulators were flushed to FP32 sums every few dozen blocks."""
+    rng = np.random.RandomState(17)
+    m, n, d, e = 262_144, 384, 64, 16
+    r = (3.0 / d) ** 0.5
+    y, x, b = r * rng.rand(m, d), r * rng.rand(n, d), rng.randn(m, e)
+    out, extra = run_plugin(kernel, y, x, b, normalize_rows=norm, path=path)
+    rows = np.arange(0, n, 3)
+    want = c_oracle.kernel_product(kernel, y, x[rows], b, normalize_rows=norm)
+    err = orc.rel_l2(out[rows], want)
+    print(f"{kernel} path={path} norm={norm}: rel-L2 {err:.2e} {extra}")
+    assert err <= 0.5 * TOL_TENSOR
 
 
 def test_empty_row_shard_is_a_no_op():
