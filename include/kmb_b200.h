@@ -217,6 +217,11 @@ int kmb_kernel_block_f64(const double* x, const double* y, double* out, int64_t 
  * [n_source_blocks (b % C) / C, n_source_blocks (b % C + 1) / C). */
 int kmb_debug_plan_waves(int64_t n_tiles, int64_t n_source_blocks, int grid, size_t row_tile_bytes, int64_t* out7);
 
+/* The path KMB_PATH_AUTO stands for with this D, E and kernel (any other `path` is returned unchanged; -1 on bad arguments):
+ * D > 16 -> KMB_PATH_TENSOR_3XF16; D <= 16 -> KMB_PATH_DIRECT_F32, except wide signals (E >= 32) of the Gaussian /
+ * exponential kernels, whose K b is a dense contraction and runs on the tensor cores as well.  Host logic only. */
+int kmb_resolved_path(int D, int E, int kernel_id, int path);
+
 /* Diagnostics (host logic only, no GPU needed): where unit `u` of the strip-ordered unit list of the symmetric path
  * sits when n points are worked on by `total_ctas` CTAs over all parts (kprod_sym.cuh).
  * out8 = {total units, strips, strip width in source blocks, strip, row tile, source block, first unit of the

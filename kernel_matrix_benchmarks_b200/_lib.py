@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkmb_b200.so")
+# KMB_B200_LIB: another build of the same library (instrumented or A/B variants made by csrc/Makefile with EXTRA=...)
+LIB_PATH = os.environ.get("KMB_B200_LIB") or os.path.join(_HERE, "libkmb_b200.so")
 
 KMB_OK, KMB_ERR_INVALID, KMB_ERR_UNSUPPORTED, KMB_ERR_WORKSPACE, KMB_ERR_CUDA = range(5)
 
@@ -79,6 +80,7 @@ SIGNATURES = {
     "kmb_kernel_block_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     "kmb_debug_plan_waves": (c_int, [c_int64, c_int64, c_int, c_size_t, POINTER(c_int64)]),
     "kmb_debug_sym_unit": (c_int, [c_int64, c_int64, c_int64, POINTER(c_int64)]),
+    "kmb_resolved_path": (c_int, [c_int, c_int, c_int, c_int]),
     "kmb_set_profiling": (c_int, [c_int]),
     "kmb_last_main_kernel_ms": (c_int, [POINTER(c_float)]),
     "kmb_cg_scratch_bytes": (c_size_t, []),

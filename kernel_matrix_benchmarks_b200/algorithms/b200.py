@@ -284,7 +284,7 @@ class B200Product(BaseProduct):
             g.product_rows(self._xs, self._bounds, self._ys, self._bs, self.res_device, kernel=self.kernel,
                            normalize_rows=bool(self.normalize_rows), density_estimation=self.density_estimation, path=self.path,
                            prepared=g.prepared)
-            self.path_used = self.path
+            self.path_used = _product.resolved_path(y0.shape[1], E, self.kernel, self.path)
         self.launches = g.launches
 
     def query(self):
@@ -366,6 +366,9 @@ class B200Product(BaseProduct):
     def _form(self):
         if self.source_points.shape[1] > 16 or (self.normalize_rows and self.density_estimation) or self.dtype == np.float64:
             return "n/a"
+        E = 1 if self.density_estimation else self.source_signal.shape[1]
+        if self.path_used != "direct_sym" and _product.resolved_path(self.source_points.shape[1], E, self.kernel, self.path).startswith("tensor"):
+            return "n/a"   # wide signal: the tensor-core kernel ran (no direct-path statistics in the workspace)
         from ..product import direct_stats
 
         return direct_stats(self._group.workspaces[0] if self._multi() else self.workspace)["form"]

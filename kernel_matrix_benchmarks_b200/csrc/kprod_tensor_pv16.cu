@@ -57,6 +57,14 @@ constexpr int PS = MAX_EB + 2;         // partial record: O row, sum of weights,
 // does not wait for) to a per-(CTA, group) FP32 accumulator in global memory and the next P.B starts from zero.
 // Measured at C4 (M = 262144): flush every 2048 blocks (= never) 2.4e-4, every 32 blocks 3.6e-6 at +6 % time (the L2
 // reductions of 148 CTAs arrive together).
+// Build-time variants, A/B-tested on one box with tools/pv16_ab.sh (make EXTRA="-DKMB_PV16_...=..."):
+#ifndef KMB_PV16_FUSED
+#define KMB_PV16_FUSED 0     // 1: one fused pass per block instead of two phases (t, then P)
+#endif
+#ifndef KMB_PV16_SKEW_NS
+#define KMB_PV16_SKEW_NS 0   // > 0: column group g starts every row tile g * KMB_PV16_SKEW_NS ns late, so that the four epilogue
+                             // warps of an SM sub-partition (one per group) are not all between their MUFU phases at once
+#endif
 constexpr int kFlushBlocks = 128;      // default of Params::flush_blocks: 768 accumulating MMAs per flush, ~1.5e-5
 
 struct Params {
@@ -407,6 +415,9 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     if (wave_work(P, w2, cta, wn)) sb_next_tile = wn.sb_lo;
             }
 
+#if KMB_PV16_SKEW_NS > 0
+            if (cg > 0) __nanosleep(cg * KMB_PV16_SKEW_NS);
+#endif
             for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++n) {
                 const long long j0 = static_cast<long long>(sb) * TNS + col0;
                 const int a = n & 1;
@@ -423,6 +434,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 mbar_wait(&acc_full[a], (n >> 1) & 1);
                 tc_fence_after();
                 KMB_T(1);
+#if KMB_PV16_FUSED
                 // One fused pass per block: S -> t = -log2 k -> P = 2^(-ref - t) with the reference exponent the row ALREADY has
                 // (it is lazy: it only moves when the block maximum outgrows it by 2^8), FP16 hi / lo, packed.  rsqrt / ex2
                 // (MUFU) and the packed FP32 work of different columns interleave instead of forming two phases in which the
@@ -497,6 +509,84 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 tmem_st_32x16(st_addr, reinterpret_cast<const float*>(ph));
                 tmem_st_32x16(st_addr + CPT / 2, reinterpret_cast<const float*>(pl));
                 ksum += kacc.x + kacc.y;
+#else   // two phases: all t = -log2 k of the block, then (reference settled) all P
+                float2 t2[CPT / 2];   // S as pairs of sources, then t = -log2 k
+                tmem_ld_cols<CPT>(st_addr, reinterpret_cast<float(&)[CPT]>(t2));
+                KMB_T(2);
+
+                // t = -log2 of the kernel values (packed pairs) and their minimum over this thread's columns
+                float tmin = INFINITY;
+                if (j0 < P.M) {
+                    const float2 nss2 = make_float2(-sscale, -sscale), un2 = make_float2(un, un);
+#pragma unroll
+                    for (int c = 0; c < CPT / 4; ++c) {
+                        const float4 vq = vnq[c];   // broadcast read of the warp's line
+                        // Gaussian: |u|^2 is the same for the whole row, so it is left out of t here and added to the
+                        // block minimum / subtracted with the reference exponent below (one FADD2 per four values less)
+                        const float2 wa = make_float2(vq.x, vq.y), wb = make_float2(vq.z, vq.w);
+                        const float2 ta = neg_log2_kernel2<KID>(t2[2 * c], nss2, KID == KMB_KERNEL_GAUSSIAN ? wa : add2(wa, un2));
+                        const float2 tb = neg_log2_kernel2<KID>(t2[2 * c + 1], nss2, KID == KMB_KERNEL_GAUSSIAN ? wb : add2(wb, un2));
+                        t2[2 * c] = ta;
+                        t2[2 * c + 1] = tb;
+                        tmin = fminf(fminf(tmin, ta.x), ta.y);
+                        tmin = fminf(fminf(tmin, tb.x), tb.y);
+                    }
+                } else {   // every source of this group is padding (warp-uniform): all weights are zero
+#pragma unroll
+                    for (int c = 0; c < CPT / 2; ++c) t2[c] = make_float2(INFINITY, INFINITY);
+                }
+                constexpr bool kRowTermOut = (KID == KMB_KERNEL_GAUSSIAN);   // t2 lacks the row's |u|^2
+                const float cm = kRowTermOut ? -(tmin + un) : -tmin;   // largest log2 k of the block
+                KMB_T(3);
+                // lazy rescale: keep the reference exponent unless the maximum outgrew it by 2^8
+                {
+                    bool need = false;
+                    if (ref == -INFINITY) ref = cm;   // nothing but zero weights so far
+                    else need = cm > ref + kLazyRescale;
+                    if (__any_sync(0xffffffffu, need)) {
+                        const float sc = need ? ex2_approx(ref - cm) : 1.f;
+                        if (sb > ww.sb_lo) {   // O_g holds this tile's sums
+                            wait_pv(n - 1);
+                            for (int c0 = 0; c0 < P.ebp; c0 += 16) {
+                                float o[16];
+                                tmem_ld_cols<16>(o_mine + c0, o);
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) o[c] *= sc;
+                                tmem_st_cols<16>(o_mine + c0, o);
+                            }
+                            tmem_st_wait();
+                            if (sb - ww.sb_lo >= P.flush_blocks && sc != 1.f)   // something was flushed already
+                                for (int c = 0; c < P.ebp; ++c) __stcg(olong + c * TM, sc * __ldcg(olong + c * TM));
+                        }
+                        ksum *= sc;
+                        if (need) ref = cm;
+                    }
+                }
+                KMB_T(4);
+                // P = 2^(log2 k - ref) = 2^(-ref - t), FP16 hi / lo, two sources per TMEM column, over this thread's own S columns
+                {
+                    uint32_t ph[CPT / 2], pl[CPT / 2];
+                    float2 kacc = make_float2(0.f, 0.f);   // two-level sum of the weights (see kprod_direct.cuh)
+                    // all -inf so far: every weight is 2^-inf = 0
+                    const float nref = (ref == -INFINITY) ? 0.f : (kRowTermOut ? -ref - un : -ref);
+                    const float2 nref2 = make_float2(nref, nref);
+#pragma unroll
+                    for (int c = 0; c < CPT / 2; ++c) {
+                        const float2 e = sub2(nref2, t2[c]);
+                        const float2 pw = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+                        kacc = add2(kacc, pw);
+                        // 11 significant bits: exact in FP16
+                        const float2 h = make_float2(__uint_as_float(__float_as_uint(pw.x) & 0xffffe000u),
+                                                     __uint_as_float(__float_as_uint(pw.y) & 0xffffe000u));
+                        const float2 l = sub2(pw, h);
+                        ph[c] = pack_half2(h.x, h.y);
+                        pl[c] = pack_half2(l.x, l.y);
+                    }
+                    tmem_st_32x16(st_addr, reinterpret_cast<const float*>(ph));
+                    tmem_st_32x16(st_addr + CPT / 2, reinterpret_cast<const float*>(pl));
+                    ksum += kacc.x + kacc.y;
+                }
+#endif
                 KMB_T(5);
                 tmem_st_wait();
                 if (sb > ww.sb_lo && (sb - ww.sb_lo) % P.flush_blocks == 0) {   // P.B(n) starts the O_g from zero

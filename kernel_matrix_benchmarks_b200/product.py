@@ -46,7 +46,7 @@ _default_ws = {}
 SYM_MIN_POINTS = 32768
 
 
-last_path = None  # the path the last kernel_product call asked the library for ("auto" resolved to "direct_sym" or left to C)
+last_path = None  # the path the last kernel_product call took ("auto" resolved: direct_sym here, otherwise kmb_resolved_path)
 
 
 def symmetric_applies(x, y, kernel, normalize_rows=False, density_estimation=False, E=1):
@@ -63,6 +63,15 @@ def workspace_bytes(N, M, D, E, *, kernel="gaussian", normalize_rows=False, dens
     _lib.check(_lib.load().kmb_product_workspace_bytes(int(N), int(M), int(D), int(E), _lib.KERNEL_IDS[kernel], flags,
                                                        _lib.PATH_IDS[path], ctypes.byref(need)))
     return int(need.value)
+
+
+def resolved_path(D, E, kernel="gaussian", path="auto"):
+    """The name of the path ``path`` stands for with this D, E and kernel (kmb_resolved_path; "auto" -> what the C library picks)."""
+    pid = int(_lib.load().kmb_resolved_path(int(D), int(E), _lib.KERNEL_IDS[kernel], _lib.PATH_IDS[path]))
+    names = {v: k for k, v in _lib.PATH_IDS.items() if k != "tensor"}
+    if pid not in names:
+        raise ValueError(f"bad arguments D={D} E={E} kernel={kernel} path={path}")
+    return names[pid]
 
 
 def prepare_points(x, y, *, kernel="gaussian", path="auto", workspace=None, min_bytes=0):
@@ -119,7 +128,7 @@ def kernel_product(x, y, b, *, kernel="gaussian", normalize_rows=False, density_
     if path == "auto" and N >= SYM_MIN_POINTS and symmetric_applies(x, y, kernel, normalize_rows, density_estimation, E):
         path = "direct_sym"  # same_points: each kernel value serves its row and its column (kprod_sym.cuh)
     global last_path
-    last_path = path
+    last_path = path if path == "direct_sym" else resolved_path(D, E, kernel, path)   # what "auto" stood for
     kid, pid = _lib.KERNEL_IDS[kernel], _lib.PATH_IDS[path]
     need = ctypes.c_size_t(0)
     _lib.check(lib.kmb_product_workspace_bytes(N, M, D, E, kid, flags, pid, ctypes.byref(need)))

@@ -208,3 +208,17 @@ def test_symmetric_strip_width_follows_the_cta_count():
     assert (o[1], o[2]) == (17, 120)
     _lib.check(lib.kmb_debug_sym_unit(10_000_000, 8 * 148, -1, o))
     assert o[1] <= 96 and 380 <= o[2] <= 420
+
+
+def test_auto_path_resolution():
+    """KMB_PATH_AUTO: tensor path for D > 16 and for wide signals (E >= 32) of the kernels the FP16-plane P.B kernel covers;
+    the direct FP32 kernel otherwise; explicit paths are returned unchanged (kmb_resolved_path, host logic only)."""
+    from kernel_matrix_benchmarks_b200 import _lib
+    from kernel_matrix_benchmarks_b200.product import resolved_path
+
+    assert resolved_path(3, 1) == "direct" and resolved_path(16, 31) == "direct"
+    assert resolved_path(17, 1) == "tensor_f16" and resolved_path(784, 1) == "tensor_f16"
+    assert resolved_path(3, 64) == "tensor_f16" and resolved_path(3, 64, "absolute-exponential") == "tensor_f16"
+    assert resolved_path(3, 64, "inverse-distance") == "direct"   # the P.B kernel with FP16 planes has no inverse-distance form
+    assert resolved_path(3, 64, path="direct") == "direct" and resolved_path(64, 64, path="tensor_tf32") == "tensor_tf32"
+    assert _lib.load().kmb_resolved_path(0, 1, 0, 0) == -1

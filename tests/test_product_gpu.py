@@ -400,10 +400,28 @@ def test_wide_signal_tensor_kernels_over_many_source_blocks(kernel, path, norm):
     y, x, b = r * rng.rand(m, d), r * rng.rand(n, d), rng.randn(m, e)
     out, extra = run_plugin(kernel, y, x, b, normalize_rows=norm, path=path)
     rows = np.arange(0, n, 3)
-    want = c_oracle.kernel_product(kernel, y, x[rows], b, normalize_rows=norm)
+    want = c_oracle.kernel_product(kernel, y, x, b, normalize_rows=norm, rows=rows)   # global row indices: inverse-distance zeroing
     err = orc.rel_l2(out[rows], want)
     print(f"{kernel} path={path} norm={norm}: rel-L2 {err:.2e} {extra}")
     assert err <= 0.5 * TOL_TENSOR
+
+
+@pytest.mark.parametrize("kernel", ["gaussian", "absolute-exponential"])
+def test_wide_signal_with_small_d_takes_the_tensor_kernel(kernel):
+    """D <= 16 with E >= 32 under path="auto": K b is a dense contraction, so the P.B kernel (tcgen05, FP16 planes) runs
+    instead of ceil(E / 16) passes of the direct kernel (6x faster at D = 3, E = 64); path="direct" keeps the FP32 kernel."""
+    rng = np.random.RandomState(23)
+    y, x, b = rng.rand(3000, 3), rng.rand(700, 3), rng.randn(3000, 64)
+    for norm in (False, True):
+        want = c_oracle.kernel_product(kernel, y, x, b, normalize_rows=norm)
+        out, extra = run_plugin(kernel, y, x, b, normalize_rows=norm)
+        assert extra["path_used"] == "tensor_f16" and extra["form"] == "n/a", extra
+        assert orc.rel_l2(out, want) <= TOL_TENSOR
+        out, extra = run_plugin(kernel, y, x, b, normalize_rows=norm, path="direct")
+        assert extra["path_used"] == "direct"
+        assert orc.rel_l2(out, want) <= TOL_DIRECT
+    out, extra = run_plugin(kernel, y, x, b[:, :16].copy())
+    assert extra["path_used"] == "direct"
 
 
 def test_empty_row_shard_is_a_no_op():

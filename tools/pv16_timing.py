@@ -2,7 +2,8 @@
 import os, sys, numpy as np, torch
 sys.path.insert(0, '.')
 from kernel_matrix_benchmarks_b200 import _lib
-_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), 'libkmb_b200_timing.so')
+if not os.environ.get('KMB_B200_LIB'):
+    _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), 'libkmb_b200_timing.so')
 from kernel_matrix_benchmarks_b200 import product
 rng = np.random.RandomState(0)
 D, E = 64, 64
