@@ -99,9 +99,9 @@ def read_peaks():
 
 def measured_traffic(n, world, sym):
     """dram__bytes_read.sum + dram__bytes_write.sum of the main kernel from the committed ncu capture
-    (profiles/r1_traffic_*.json); only valid for the workload it was captured on."""
+    (profiles/r*_traffic_*.json); only valid for the workload it was captured on."""
     try:
-        name = "r1_traffic_sym_kernel.json" if sym else "r1_traffic_main_kernel.json"
+        name = "r2_traffic_sym_kernel.json" if sym else "r1_traffic_main_kernel.json"
         with open(os.path.join(REPO, "profiles", name)) as f:
             t = json.load(f)
         if t["N"] == n and world == 1:

@@ -19,7 +19,7 @@ template <class C>
 void run(const char* name, long long N, const float* y, const float* b, float* out, int sms, double ref_checksum) {
     const long long nsb = (N + C::SB - 1) / C::SB, N_pad = nsb * C::SB;
     const long long n_tiles = (N + C::TILE_ROWS - 1) / C::TILE_ROWS;
-    float2* rec; DirectStats* stats; float* box; float *rowsum, *rowpart, *colpart;
+    float2* rec; DirectStats* stats; float* box; float *rowseg, *rowpart, *colpart;
     CK(cudaMalloc(&rec, N_pad * C::RECV * 16));
     CK(cudaMalloc(&stats, sizeof(DirectStats))); CK(cudaMemset(stats, 0, sizeof(DirectStats)));
     CK(cudaMalloc(&box, sizeof(float) * STATS_MAX_BLOCKS * 32));
@@ -27,19 +27,22 @@ void run(const char* name, long long N, const float* y, const float* b, float* o
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kprod_sym_kernel<C>, C::THREADS, C::SMEM_BYTES));
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kprod_sym_kernel<C>));
-    const long long units = sym_prefix<C::TB>(n_tiles, nsb);
     long long grid = (long long)sms * per_sm;
+    SymGeom geom;
+    sym_build_geom<C::TB>(n_tiles, nsb, grid, &geom);
+    const long long units = geom.strip_prefix[geom.n_strips];
     if (grid > units) grid = units;
-    CK(cudaMalloc(&rowsum, n_tiles * C::TILE_ROWS * 4));
+    CK(cudaMalloc(&rowseg, (size_t)geom.seg_prefix[geom.n_strips] * C::TILE_ROWS * 4));
     CK(cudaMalloc(&rowpart, grid * 2 * C::TILE_ROWS * 4));
-    CK(cudaMalloc(&colpart, (size_t)n_tiles * N_pad * 4));
+    CK(cudaMalloc(&colpart, (size_t)(grid + geom.n_strips) * geom.Wb * C::SB * 4));
     const float scale = 1.2011224087864498f;
     direct_stats_kernel<<<64, STATS_THREADS>>>(y, N, y, N, 3, box, stats, 1);
     PackLayout L{N_pad, 0, C::RECV * 2};
     pack_sources_kernel<<<(unsigned)((N_pad + 255) / 256), 256>>>(y, b, rec, stats, N, 3, 1, C::DP, 1, L, L, 0, scale);
     SymParams P{};
-    P.stats = stats; P.rec = (const float4*)rec; P.rowsum = rowsum; P.rowpart = rowpart; P.colpart = colpart; P.out = out;
-    P.N = N; P.N_pad = N_pad; P.unit_begin = 0; P.unit_end = units; P.n_tiles = (int)n_tiles; P.nsb = (int)nsb; P.grid = (int)grid;
+    P.stats = stats; P.rec = (const float4*)rec; P.rowseg = rowseg; P.rowpart = rowpart; P.colpart = colpart; P.out = out;
+    P.N = N; P.M = N; P.unit_begin = 0; P.unit_end = units; P.piece_floats = (long long)geom.Wb * C::SB; P.grid = (int)grid;
+    P.seg_base = 0; P.strip_base = 0; P.g = geom;
     cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
     for (int i = 0; i < 2; ++i) kprod_sym_kernel<C><<<(int)grid, C::THREADS, C::SMEM_BYTES>>>(P);
     CK(cudaDeviceSynchronize());
@@ -57,7 +60,7 @@ void run(const char* name, long long N, const float* y, const float* b, float* o
     const double kev = (double)units * C::TILE_ROWS * C::SB / (ms * 1e-3);
     printf("%-28s regs=%3d ctas/sm=%d grid=%4lld smem=%6d  main %8.3f ms + combine %6.3f ms  %7.1f Gpairs/s  %.2f k-evals/clk/SM@1965  checksum=%.6e (ref %.6e)\n",
            name, fa.numRegs, per_sm, grid, C::SMEM_BYTES, ms, ms_c, gp, kev / (sms * 1.965e9), cs, ref_checksum);
-    cudaFree(rec); cudaFree(rowsum); cudaFree(rowpart); cudaFree(colpart); cudaFree(stats); cudaFree(box);
+    cudaFree(rec); cudaFree(rowseg); cudaFree(rowpart); cudaFree(colpart); cudaFree(stats); cudaFree(box);
 }
 
 int main(int argc, char** argv) {
@@ -73,16 +76,13 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(b, hb.data(), N * 4, cudaMemcpyHostToDevice));
     printf("N=%lld on %s (%d SMs)\n", N, p.name, p.multiProcessorCount);
     const int sms = p.multiProcessorCount;
-    //   DP POLY MINB CH CONSUMERS R STAGES
+    //   DP KID FORM POLY MINB CH CONSUMERS R STAGES   (product form of the Gaussian kernel: KID 0, FORM 1)
 #define RUN(...) run<SymCfg<__VA_ARGS__>>(#__VA_ARGS__, N, y, b, out, sms, 0.0)
-    RUN(3, 0, 2, 8, 512, 4, 4);
-    RUN(3, 0, 2, 16, 512, 4, 4);
-    RUN(3, 0, 1, 16, 512, 8, 4);
-    RUN(3, 0, 1, 8, 512, 8, 4);
-    RUN(3, 0, 2, 16, 256, 8, 4);
-    RUN(3, 0, 2, 16, 256, 6, 4);
-    RUN(3, 0, 3, 16, 256, 4, 3);
-    RUN(3, 32, 2, 16, 512, 4, 4);
-    RUN(3, 32, 1, 16, 512, 8, 4);
+    RUN(3, 0, 1, 0, 2, 8, 512, 4, 4);
+    RUN(3, 0, 1, 0, 2, 16, 512, 4, 4);
+    RUN(3, 0, 1, 0, 1, 16, 512, 8, 4);
+    RUN(3, 0, 1, 0, 1, 8, 512, 8, 4);
+    RUN(3, 0, 1, 32, 2, 16, 512, 4, 4);
+    RUN(3, 0, 1, 32, 1, 16, 512, 8, 4);
     return 0;
 }
