@@ -28,6 +28,9 @@ no collective.  Rank 0 prints ONE JSON line.
             (kind "port") only when that tree is absent
   parity    sampled target rows of the TIMED output (and of the e2e result) against the float64 C oracle
             (oracle/kprod_ref.c -- the checker, never the thing measured), at every N: rel_l2, rows, tol
+  --workload solve
+            config C5 (the kernel solve) as the line's own metric (ms per solve, lower is better) with iterations, ms per
+            iteration, fit() time and the collective -- for 1/2/4/8-GPU sweeps of the solve
   configs   the other BASELINE.json configs on the same line (skip with --no-configs): C1 (N=M=10^4), C3 (D=784,
             tensor path), C4 (D=E=64 attention, tensor path), C5 (CG solve, N=10^6) through the plugin API, each
             with ms, its roofline (SURVEY.md section 8d formulas) and oracle parity on sampled rows; under
@@ -67,6 +70,8 @@ def parse_args():
     ap.add_argument("--no-configs", action="store_true", help="skip the C1/C3/C4/C5 block")
     ap.add_argument("--configs", default="c1,c3,c4,c5", help="which of c1,c3,c4,c5 to run beside the headline")
     ap.add_argument("--parity-rows", type=int, default=256, help="sampled rows checked against the C oracle")
+    ap.add_argument("--workload", default="product", choices=["product", "solve"],
+                    help="product: the headline C2 product (default); solve: BASELINE config C5, (K + I) b = a at N = 10^6, as the line's own metric")
     return ap.parse_args()
 
 
@@ -543,10 +548,53 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
+def run_solve_workload(args):
+    """--workload solve: config C5 (Gaussian solve (K + I) b = a, N = M = 10^6, preconditioned CG through B200Solver) as the
+    line's metric, so that a 1/2/4/8-GPU sweep reports the solve like the product: time of query() (device, max over ranks),
+    iterations, ms per iteration, fit() time, the collective, oracle-scored residual.  One step = one solve."""
+    import torch
+    import torch.distributed as dist
+
+    from bench_configs import run_solver   # tools/bench_configs.py
+
+    rank, world, local_rank = (int(os.environ.get(k, "0" if k != "WORLD_SIZE" else "1")) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    peaks, _ = read_peaks()
+    c5 = run_solver("C5: gaussian solve (K + I) b = a, N=M=10^6, D=3, preconditioned CG", args.n, local_rank=local_rank, rank=rank,
+                    world=world, parity_rows=min(args.parity_rows, 128), peaks=peaks)
+    if rank == 0:
+        clocks = sampler.stop()
+        n = args.n
+        print(json.dumps({
+            "metric": "gaussian_kernel_solve_ms", "value": c5["ms"], "unit": "ms", "n_gpus": world, "steps": 1, "warmup": 1,
+            "ms_per_step": c5["ms"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": c5["workload"], "N": n, "M": n, "D": 3, "E": 1, "lam": c5["lam"], "rtol": c5["rtol"],
+                       "matvec": c5["matvec"], "preconditioner": c5["preconditioner"], "collective": c5["collective"],
+                       "l2": "the 32 MB of records per matvec are L2-resident by design; nothing is flushed inside a solve"},
+            "clocks": clocks, "iterations": c5["iterations"], "ms_per_iteration": c5["ms_per_iteration"], "fit_ms": c5["fit_ms"],
+            "first_fit_ms": c5["first_fit_ms"], "converged": c5["converged"],
+            "e2e": {"value": c5["e2e_ms"], "unit": "ms", "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 4 * n,
+                    "api": "B200Solver.prepare_query/query/get_result, host float64 in/out"},
+            "gpu_launches": c5["gpu_launches"], "roofline": c5["roofline"], "parity": c5["parity"],
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "solve":
+        run_solve_workload(args)
     else:
         run_b200_arm(args)
 

@@ -160,8 +160,15 @@ def run_solver(name, n, *, lam=1.0, rtol=1e-6, local_rank=0, rank=0, world=1, pa
         queries.append((1e3 * (time.perf_counter() - t0), algo.query_ms))
     x = algo.get_result()
     extra = algo.get_additional()
+    # end to end through the plugin: host float64 right-hand side in (cast + H2D), solve, host float64 solution out
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    algo.prepare_query(target_signal=rhs)
+    algo.query()
+    algo.get_result()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
     algo.done()
-    fit_first, fit_ms, q_first, q_ms = _max_over_ranks([fits[0], fits[1], queries[0][1], queries[1][1]], dev, world)
+    fit_first, fit_ms, q_first, q_ms, e2e_ms = _max_over_ranks([fits[0], fits[1], queries[0][1], queries[1][1], e2e_ms], dev, world)
     if rank != 0:
         return None
     it = max(1, int(extra["cg_iterations"]))
@@ -180,7 +187,7 @@ def run_solver(name, n, *, lam=1.0, rtol=1e-6, local_rank=0, rank=0, world=1, pa
     achieved = pairs_per_gpu_per_iteration / (ms_it * 1e-3) / 1e9
     return {
         "workload": name, "kernel": "gaussian", "N": n, "M": n, "D": 3, "E": 1, "lam": lam, "rtol": rtol, "n_gpus": world,
-        "ms": q_ms, "first_query_ms": q_first, "fit_ms": fit_ms, "first_fit_ms": fit_first,
+        "ms": q_ms, "first_query_ms": q_first, "fit_ms": fit_ms, "first_fit_ms": fit_first, "e2e_ms": e2e_ms,
         "iterations": it, "ms_per_iteration": ms_it, "converged": bool(extra["cg_converged"]),
         "rel_residual_recurrence": float(extra["cg_rel_residual"]), "matvec": extra["matvec"], "preconditioner": extra["preconditioner"],
         "collective": ("none (1 GPU)" if world == 1 else

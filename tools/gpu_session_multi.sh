@@ -9,6 +9,7 @@ mkdir -p $O
 nvidia-smi -L | head -8
 timeout 600 python -m pytest tests/test_multigpu_gpu.py -m gpu -q > $O/r2_gputest_multi_${G}gpu.log 2>&1; echo "multigpu pytest rc=$?"; tail -4 $O/r2_gputest_multi_${G}gpu.log
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $G --steps 5 --warmup 3 > $O/r2_bench_${G}gpu.json 2> $O/r2_bench_${G}gpu.err; echo "bench rc=$?"
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $G --workload solve > $O/r2_bench_solve_${G}gpu.json 2> $O/r2_bench_solve_${G}gpu.err; echo "solve rc=$?"; cut -c1-600 $O/r2_bench_solve_${G}gpu.json
 python - <<PY
 import json
 try:
