@@ -64,6 +64,10 @@ constexpr int PS = MAX_EB + 2;         // partial record: O row, sum of weights,
 #ifndef KMB_PV16_SETS
 #define KMB_PV16_SETS 0      // 1: the 16 epilogue warps form two sets of eight that work on ALTERNATE source blocks (see the epilogue)
 #endif
+#ifndef KMB_PV16_VN_LDG
+#define KMB_PV16_VN_LDG 0    // 1: |v|^2 of a block straight from global memory (eight uniform LDG.128 per thread, L1 broadcast) instead of
+                             // one coalesced load parked in a shared-memory line: STS / LDS share the MIO queue with the MUFU instructions
+#endif
 #ifndef KMB_PV16_SKEW_NS
 #define KMB_PV16_SKEW_NS 0   // > 0: column group g starts every row tile g * KMB_PV16_SKEW_NS ns late, so that the four epilogue
                              // warps of an SM sub-partition (one per group) are not all between their MUFU phases at once
@@ -630,6 +634,9 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 const long long j0 = static_cast<long long>(sb) * TNS + col0;
                 const int a = n & 1;
                 const uint32_t st_addr = tmem_base + COL_S + a * TNS + col0 + lane_addr;
+#if KMB_PV16_VN_LDG
+                const float4* vnq = reinterpret_cast<const float4*>(P.vn + j0);   // 128-byte aligned; padded to whole blocks
+#else
                 float* line = my_line + (n & 1) * 32;
                 line[lane] = vn_next;
                 {
@@ -638,6 +645,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 }
                 __syncwarp();
                 const float4* vnq = reinterpret_cast<const float4*>(line);
+#endif
                 KMB_T(0);
                 mbar_wait(&acc_full[a], (n >> 1) & 1);
                 tc_fence_after();
@@ -728,7 +736,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     const float2 nss2 = make_float2(-sscale, -sscale), un2 = make_float2(un, un);
 #pragma unroll
                     for (int c = 0; c < CPT / 4; ++c) {
-                        const float4 vq = vnq[c];   // broadcast read of the warp's line
+                        const float4 vq = KMB_PV16_VN_LDG ? __ldg(vnq + c) : vnq[c];   // broadcast read (L1 / the warp's line)
                         // Gaussian: |u|^2 is the same for the whole row, so it is left out of t here and added to the
                         // block minimum / subtracted with the reference exponent below (one FADD2 per four values less)
                         const float2 wa = make_float2(vq.x, vq.y), wb = make_float2(vq.z, vq.w);
