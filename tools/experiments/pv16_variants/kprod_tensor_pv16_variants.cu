@@ -57,6 +57,21 @@ constexpr int PS = MAX_EB + 2;         // partial record: O row, sum of weights,
 // does not wait for) to a per-(CTA, group) FP32 accumulator in global memory and the next P.B starts from zero.
 // Measured at C4 (M = 262144): flush every 2048 blocks (= never) 2.4e-4, every 32 blocks 3.6e-6 at +6 % time (the L2
 // reductions of 148 CTAs arrive together).
+// Build-time variants, A/B-tested on one box with tools/pv16_ab.sh (make EXTRA="-DKMB_PV16_...=..."):
+#ifndef KMB_PV16_FUSED
+#define KMB_PV16_FUSED 0     // 1: one fused pass per block instead of two phases (t, then P)
+#endif
+#ifndef KMB_PV16_SETS
+#define KMB_PV16_SETS 0      // 1: the 16 epilogue warps form two sets of eight that work on ALTERNATE source blocks (see the epilogue)
+#endif
+#ifndef KMB_PV16_VN_LDG
+#define KMB_PV16_VN_LDG 0    // 1: |v|^2 of a block straight from global memory (eight uniform LDG.128 per thread, L1 broadcast) instead of
+                             // one coalesced load parked in a shared-memory line: STS / LDS share the MIO queue with the MUFU instructions
+#endif
+#ifndef KMB_PV16_SKEW_NS
+#define KMB_PV16_SKEW_NS 0   // > 0: column group g starts every row tile g * KMB_PV16_SKEW_NS ns late, so that the four epilogue
+                             // warps of an SM sub-partition (one per group) are not all between their MUFU phases at once
+#endif
 constexpr int kFlushBlocks = 128;      // default of Params::flush_blocks: 768 accumulating MMAs per flush, ~1.5e-5
 
 struct Params {
@@ -123,6 +138,11 @@ __device__ __forceinline__ float2 neg_log2_kernel2(float2 s_raw, float2 nsscale,
     }
 }
 
+// 2^d for an integer-valued d <= 0 (exact; 0 below the normal range, which is also what d = -inf gives)
+__device__ __forceinline__ float pow2_int(float d) {
+    return d > -126.f ? __int_as_float((127 + static_cast<int>(d)) << 23) : 0.f;
+}
+
 // PAIR: two CTAs of a cluster (cta_group::2) work on two adjacent row tiles and the same source blocks: every MMA is
 // 256 rows tall (half as many instructions per row tile -- the issuing warp is what bounds the single-CTA kernel),
 // each CTA streams half of every v block (64 sources) and half of every signal block (32 signal columns), the leader
@@ -138,7 +158,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
     unsigned char* u_region = smem;                                   // kblocks x [A hi 16 KB | A lo 16 KB]
     unsigned char* ring = u_region + P.kblocks * 2 * A_TILE_BYTES;    // stages x 32 KB
     float* vline = reinterpret_cast<float*>(ring + P.stages * SLOT);    // EPI_WARPS x 2 x 32: per-warp |v|^2 lines
-    float* refbuf = vline + EPI_WARPS * 2 * 32;                                // NG x TM: per-group reference exponents
+    float* refbuf = vline + EPI_WARPS * 2 * 64;                                // NG x TM: per-group reference exponents
     float* ksbuf = refbuf + NG * TM;                                           // NG x TM: per-group sums of weights
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ksbuf + NG * TM);
     uint64_t* empty_bar = full_bar + P.stages;
@@ -158,7 +178,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
 
     if (tid == 0) {
         for (int s = 0; s < ST; ++s) { mbar_init(&full_bar[s], NCTA); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&p_ready[a], NCTA * EPI_WARPS); mbar_init(&pv_done[a], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&p_ready[a], NCTA * (KMB_PV16_SETS ? EPI_WARPS / 2 : EPI_WARPS)); mbar_init(&pv_done[a], 1); }
         mbar_init(u_full, NCTA);
         mbar_init(u_free, 1);
         fence_mbar_init();
@@ -286,8 +306,14 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     const uint64_t bh = umma_desc_sw128(sg + panel * PANEL, koff);
                     const uint64_t bl = umma_desc_sw128(sg + (2 + panel) * PANEL, koff);
                     const uint32_t a_hi = p_base + g * CPT + (k & 1) * 8, a_lo = a_hi + CPT / 2;
+#if KMB_PV16_SETS
+                    // stream = set (m & 1) + 2 * column half (k / 4): both 32-column chunks of a half go to one accumulator
+                    const uint32_t d_g = d_o + ((m & 1) + 2 * (k >> 2)) * MAX_EB;
+                    mma_ts(d_g, a_lo, bh, idesc_o, !(from_zero && (k & 3) == 0));
+#else
                     const uint32_t d_g = d_o + g * MAX_EB;
                     mma_ts(d_g, a_lo, bh, idesc_o, !(from_zero && (k & 1) == 0));
+#endif
                     mma_ts(d_g, a_hi, bl, idesc_o, 1);
                     mma_ts(d_g, a_hi, bh, idesc_o, 1);
                 }
@@ -302,10 +328,21 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
             if (!wave_work(P, w, cta, ww)) continue;
             mbar_wait(u_full, seg & 1);
             ++seg;
+#if KMB_PV16_SETS
+            int until_flush2[2] = {0, 0};   // per set: its own blocks until its streams are flushed again
+            const int flush_own = max(1, P.flush_blocks / 2);
+#else
             int until_flush = 0;   // blocks until the epilogue flushes the O_g again (a countdown: no division in the loop)
+#endif
             for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++n) {
+#if KMB_PV16_SETS
+                int& until_flush = until_flush2[n & 1];
+                const bool first = (until_flush == 0);
+                until_flush = first ? flush_own - 1 : until_flush - 1;
+#else
                 const bool first = (until_flush == 0);
                 until_flush = first ? P.flush_blocks - 1 : until_flush - 1;
+#endif
                 const int a = n & 1;   // stage a held P(n-2): PV(n-2) was issued in the previous iteration
                 const uint32_t d_s = tmem_base + COL_S + a * TNS;
                 for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
@@ -356,7 +393,16 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
         const int et = tid - 64;
         const int lane_group = warp & 3;             // TMEM lane quarter this warp may touch
         const int cg = (warp - 2) >> 2;              // column group = online-softmax stream (own reference, sum, O_g)
+#if KMB_PV16_SETS
+        // Two sets of eight warps work on ALTERNATE source blocks: stream cg belongs to set cg & 1 (blocks whose global
+        // index n has n & 1 == set, i.e. S / P stage `set`) and covers columns [64 half, 64 half + 64) of them, half = cg >> 1,
+        // in two passes of 32.  The four warps of an SM sub-partition (same TMEM lane quarter) are then two from each set,
+        // half a block period apart: while one pair waits for its S tile, loads it, stores P or arrives, the other pair keeps
+        // the MUFU pipe busy -- with all 16 warps on the same block those ~900 cycles per block leave it idle.
+        const int set = cg & 1, half = cg >> 1;
+#else
         const int col0 = cg * CPT;                   // first S column of this thread
+#endif
         const int row_in_tile = lane_group * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(lane_group * 32) << 16;
         const uint32_t o_mine = tmem_base + COL_O + cg * MAX_EB + lane_addr;   // this group's accumulator
@@ -375,9 +421,15 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
 
         // |v|^2 of this group's 32 sources: lane l fetches source l of the NEXT block (one coalesced load, a block
         // ahead of its use), parks it in the warp's shared-memory line and every lane reads the line back as float4s
+#if KMB_PV16_SETS
+        float* my_line = vline + (warp - 2) * 2 * 64;   // 64 sources per own block, double buffered
+        float vn_a = 0.f, vn_b = 0.f;                   // prefetched |v|^2 of the next own block (sources lane, 32 + lane)
+        uint32_t pref_n = 0xffffffffu, own = 0, n_base = 0;   // block they belong to; own blocks so far; first block of the tile
+#else
         float* my_line = vline + (warp - 2) * 2 * 32;
         float vn_next = 0.f;
         bool primed = false;
+#endif
         WaveWork ww;
         for (int w = 0; w < P.W; ++w) {
             if (!wave_work(P, w, cta, ww)) continue;
@@ -397,6 +449,170 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     for (int c = 0; c < 16; ++c) atomicAdd(olong + (c0 + c) * TM, o[c]);   // RED: nothing to wait for
                 }
             };
+#if KMB_PV16_SETS
+            const int cnt = ww.sb_hi - ww.sb_lo;
+            int next_lo = -1, next_cnt = 0;   // the next wave this CTA works in (prefetch across the tile boundary)
+            {
+                WaveWork wn;
+                for (int w2 = w + 1; w2 < P.W && next_lo < 0; ++w2)
+                    if (wave_work(P, w2, cta, wn)) { next_lo = wn.sb_lo; next_cnt = wn.sb_hi - wn.sb_lo; }
+            }
+            const int flush_own = max(1, P.flush_blocks / 2);
+            int until_flush = flush_own;   // own blocks until this thread moves its O_g row to the long accumulator
+            bool flushed = false, any = false;   // a flush has happened in this tile; the stream has had a block in this tile
+            uint32_t m_last = 0;                 // its last block
+            for (int i = ((n_base & 1u) == static_cast<uint32_t>(set)) ? 0 : 1; i < cnt; i += 2) {
+                const int sb = ww.sb_lo + i;
+                const uint32_t n = n_base + i;   // n & 1 == set
+                const long long jb = static_cast<long long>(sb) * TNS + 64 * half;
+                float* line = my_line + (own & 1) * 64;
+                ++own;
+                if (pref_n != n) {   // nothing prefetched for this block (first block of the kernel, or a tile of one block)
+                    vn_a = __ldg(P.vn + jb + lane);   // padded to whole blocks with 3.4e38
+                    vn_b = __ldg(P.vn + jb + 32 + lane);
+                }
+                line[lane] = vn_a;
+                line[32 + lane] = vn_b;
+                {
+                    int sbn = -1;
+                    uint32_t nn = 0;
+                    if (i + 2 < cnt) { sbn = sb + 2; nn = n + 2; }
+                    else if (next_lo >= 0) {
+                        const uint32_t nb = n_base + cnt;
+                        const int i2 = ((nb & 1u) == static_cast<uint32_t>(set)) ? 0 : 1;
+                        if (i2 < next_cnt) { sbn = next_lo + i2; nn = nb + i2; }
+                    }
+                    pref_n = 0xffffffffu;
+                    if (sbn >= 0) {
+                        const long long jn = static_cast<long long>(sbn) * TNS + 64 * half;
+                        vn_a = __ldg(P.vn + jn + lane);
+                        vn_b = __ldg(P.vn + jn + 32 + lane);
+                        pref_n = nn;
+                    }
+                }
+                __syncwarp();
+                KMB_T(0);
+                mbar_wait(&acc_full[set], (n >> 1) & 1);
+                tc_fence_after();
+                KMB_T(1);
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int col0 = 64 * half + 32 * pass;
+                    const long long j0 = static_cast<long long>(sb) * TNS + col0;
+                    const uint32_t st_addr = tmem_base + COL_S + set * TNS + col0 + lane_addr;
+                    const float4* vnq = reinterpret_cast<const float4*>(line + 32 * pass);
+                    float2 t2[CPT / 2];   // S as pairs of sources, then t = -log2 k
+                    tmem_ld_cols<CPT>(st_addr, reinterpret_cast<float(&)[CPT]>(t2));
+                    KMB_T(2);
+                    // t = -log2 of the kernel values (packed pairs) and their minimum over this thread's columns
+                    float tmin = INFINITY;
+                    if (j0 < P.M) {
+                        const float2 nss2 = make_float2(-sscale, -sscale), un2 = make_float2(un, un);
+#pragma unroll
+                        for (int c = 0; c < CPT / 4; ++c) {
+                            const float4 vq = vnq[c];   // broadcast read of the warp's line
+                            const float2 wa = make_float2(vq.x, vq.y), wb = make_float2(vq.z, vq.w);
+                            const float2 ta = neg_log2_kernel2<KID>(t2[2 * c], nss2, KID == KMB_KERNEL_GAUSSIAN ? wa : add2(wa, un2));
+                            const float2 tb = neg_log2_kernel2<KID>(t2[2 * c + 1], nss2, KID == KMB_KERNEL_GAUSSIAN ? wb : add2(wb, un2));
+                            t2[2 * c] = ta;
+                            t2[2 * c + 1] = tb;
+                            tmin = fminf(fminf(tmin, ta.x), ta.y);
+                            tmin = fminf(fminf(tmin, tb.x), tb.y);
+                        }
+                    } else {   // every source of this chunk is padding (warp-uniform): all weights are zero
+#pragma unroll
+                        for (int c = 0; c < CPT / 2; ++c) t2[c] = make_float2(INFINITY, INFINITY);
+                    }
+                    constexpr bool kRowTermOut = (KID == KMB_KERNEL_GAUSSIAN);   // t2 lacks the row's |u|^2
+                    const float cm = kRowTermOut ? -(tmin + un) : -tmin;   // largest log2 k of the chunk
+                    KMB_T(3);
+                    // lazy rescale with INTEGER reference exponents: every rescale factor is an exact power of two, so the
+                    // P of pass 0 that is already in tensor memory can follow a reference that moves in pass 1 without error
+                    {
+                        bool need = false;
+                        if (ref == -INFINITY) ref = (cm == -INFINITY) ? cm : ceilf(cm);   // nothing but zero weights so far
+                        else need = cm > ref + kLazyRescale;
+                        if (__any_sync(0xffffffffu, need)) {
+                            const float ref_new = need ? ceilf(cm) : ref;
+                            const float sc = need ? pow2_int(ref - ref_new) : 1.f;
+                            if (any) {   // O_g holds this tile's sums
+                                wait_pv(m_last);
+                                for (int c0 = 0; c0 < P.ebp; c0 += 16) {
+                                    float o[16];
+                                    tmem_ld_cols<16>(o_mine + c0, o);
+#pragma unroll
+                                    for (int c = 0; c < 16; ++c) o[c] *= sc;
+                                    tmem_st_cols<16>(o_mine + c0, o);
+                                }
+                                if (flushed && sc != 1.f)   // something was flushed already
+                                    for (int c = 0; c < P.ebp; ++c) __stcg(olong + c * TM, sc * __ldcg(olong + c * TM));
+                            }
+                            if (pass == 1) {   // the P of pass 0 (16 hi + 16 lo columns of packed halves) waits for the same P.B
+                                float pq[CPT];
+                                tmem_ld_cols<CPT>(st_addr - CPT, pq);
+                                const __half2 sc2 = __float2half2_rn(sc);
+#pragma unroll
+                                for (int c = 0; c < CPT; ++c) {
+                                    __half2 h = *reinterpret_cast<__half2*>(&pq[c]);
+                                    h = __hmul2(h, sc2);
+                                    pq[c] = *reinterpret_cast<float*>(&h);
+                                }
+                                tmem_st_cols<CPT>(st_addr - CPT, pq);
+                            }
+                            tmem_st_wait();
+                            ksum *= sc;
+                            ref = ref_new;
+                        }
+                    }
+                    KMB_T(4);
+                    // P = 2^(log2 k - ref) = 2^(-ref - t), FP16 hi / lo, two sources per TMEM column, over this thread's own S columns
+                    {
+                        uint32_t ph[CPT / 2], pl[CPT / 2];
+                        float2 kacc = make_float2(0.f, 0.f);   // two-level sum of the weights (see kprod_direct.cuh)
+                        const float nref = (ref == -INFINITY) ? 0.f : (kRowTermOut ? -ref - un : -ref);
+                        const float2 nref2 = make_float2(nref, nref);
+#pragma unroll
+                        for (int c = 0; c < CPT / 2; ++c) {
+                            const float2 e = sub2(nref2, t2[c]);
+                            const float2 pw = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+                            kacc = add2(kacc, pw);
+                            const float2 h = make_float2(__uint_as_float(__float_as_uint(pw.x) & 0xffffe000u),
+                                                         __uint_as_float(__float_as_uint(pw.y) & 0xffffe000u));
+                            const float2 l = sub2(pw, h);
+                            ph[c] = pack_half2(h.x, h.y);
+                            pl[c] = pack_half2(l.x, l.y);
+                        }
+                        tmem_st_32x16(st_addr, reinterpret_cast<const float*>(ph));
+                        tmem_st_32x16(st_addr + CPT / 2, reinterpret_cast<const float*>(pl));
+                        ksum += kacc.x + kacc.y;
+                    }
+                    KMB_T(5);
+                }
+                tmem_st_wait();
+                if (until_flush == 0) {   // P.B(n) starts this stream's O_g from zero
+                    wait_pv(m_last);
+                    flush_o();
+                    until_flush = flush_own;
+                    flushed = true;
+                }
+                --until_flush;
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (PAIR && rank != 0) pair::mbar_arrive_cluster(pair::map_to_cta(&p_ready[set], 0));
+                    else mbar_arrive(&p_ready[set]);
+                }
+                any = true;
+                m_last = n;
+                KMB_T(6);
+            }
+#ifdef KMB_PV16_TIMING
+            if (blockIdx.x == 0 && et == 0) {
+                for (int i = 0; i < 7; ++i) P.out[i] = static_cast<float>(tacc[i]) / max(1u, own);
+                P.out[7] = static_cast<float>(own);
+            }
+#endif
+#else
             if (!primed) {
                 vn_next = __ldg(P.vn + static_cast<long long>(ww.sb_lo) * TNS + col0 + lane);   // padded to whole blocks with 3.4e38
                 primed = true;
@@ -409,12 +625,18 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     if (wave_work(P, w2, cta, wn)) sb_next_tile = wn.sb_lo;
             }
 
+#if KMB_PV16_SKEW_NS > 0
+            if (cg > 0) __nanosleep(cg * KMB_PV16_SKEW_NS);
+#endif
             int until_flush = P.flush_blocks;   // blocks until this thread moves its O_g row to the long accumulator
             bool flushed = false;               // ... which has happened at least once in this tile
             for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++n) {
                 const long long j0 = static_cast<long long>(sb) * TNS + col0;
                 const int a = n & 1;
                 const uint32_t st_addr = tmem_base + COL_S + a * TNS + col0 + lane_addr;
+#if KMB_PV16_VN_LDG
+                const float4* vnq = reinterpret_cast<const float4*>(P.vn + j0);   // 128-byte aligned; padded to whole blocks
+#else
                 float* line = my_line + (n & 1) * 32;
                 line[lane] = vn_next;
                 {
@@ -423,10 +645,87 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 }
                 __syncwarp();
                 const float4* vnq = reinterpret_cast<const float4*>(line);
+#endif
                 KMB_T(0);
                 mbar_wait(&acc_full[a], (n >> 1) & 1);
                 tc_fence_after();
                 KMB_T(1);
+#if KMB_PV16_FUSED
+                // One fused pass per block: S -> t = -log2 k -> P = 2^(-ref - t) with the reference exponent the row ALREADY has
+                // (it is lazy: it only moves when the block maximum outgrows it by 2^8), FP16 hi / lo, packed.  rsqrt / ex2
+                // (MUFU) and the packed FP32 work of different columns interleave instead of forming two phases in which the
+                // four warps of an SM sub-partition first all wait for the FMA pipe and then all for the MUFU pipe.  If the
+                // reference has to move (first block of a tile; afterwards almost never) the O_g are rescaled and the pass is
+                // repeated from the S columns, which are still in tensor memory.
+                uint32_t ph[CPT / 2], pl[CPT / 2];
+                float2 kacc;
+                bool again;
+                do {
+                    float2 t2[CPT / 2];   // S as pairs of sources
+                    tmem_ld_cols<CPT>(st_addr, reinterpret_cast<float(&)[CPT]>(t2));
+                    KMB_T(2);
+                    constexpr bool kRowTermOut = (KID == KMB_KERNEL_GAUSSIAN);   // t lacks the row's |u|^2
+                    // all -inf so far: every weight is 2^-inf = 0
+                    const float nref = (ref == -INFINITY) ? 0.f : (kRowTermOut ? -ref - un : -ref);
+                    const float2 nref2 = make_float2(nref, nref);
+                    float2 tmin2[2] = {make_float2(INFINITY, INFINITY), make_float2(INFINITY, INFINITY)};
+                    kacc = make_float2(0.f, 0.f);   // two-level sum of the weights (see kprod_direct.cuh)
+                    if (j0 < P.M) {
+                        const float2 nss2 = make_float2(-sscale, -sscale), un2 = make_float2(un, un);
+#pragma unroll
+                        for (int c = 0; c < CPT / 2; ++c) {
+                            const float4 vq = vnq[c >> 1];   // broadcast read of the warp's line
+                            // Gaussian: |u|^2 is the same for the whole row, so it is left out of t here and added to the
+                            // block minimum / subtracted with the reference exponent (one FADD2 per four values less)
+                            const float2 w = (c & 1) ? make_float2(vq.z, vq.w) : make_float2(vq.x, vq.y);
+                            const float2 t = neg_log2_kernel2<KID>(t2[c], nss2, KID == KMB_KERNEL_GAUSSIAN ? w : add2(w, un2));
+                            tmin2[c & 1] = make_float2(fminf(tmin2[c & 1].x, t.x), fminf(tmin2[c & 1].y, t.y));
+                            const float2 e = sub2(nref2, t);
+                            const float2 pw = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+                            kacc = add2(kacc, pw);
+                            // 11 significant bits: exact in FP16
+                            const float2 h = make_float2(__uint_as_float(__float_as_uint(pw.x) & 0xffffe000u),
+                                                         __uint_as_float(__float_as_uint(pw.y) & 0xffffe000u));
+                            const float2 l = sub2(pw, h);
+                            ph[c] = pack_half2(h.x, h.y);
+                            pl[c] = pack_half2(l.x, l.y);
+                        }
+                    } else {   // every source of this group is padding (warp-uniform): all weights are zero
+#pragma unroll
+                        for (int c = 0; c < CPT / 2; ++c) ph[c] = pl[c] = 0u;
+                    }
+                    const float tmin = fminf(fminf(tmin2[0].x, tmin2[0].y), fminf(tmin2[1].x, tmin2[1].y));
+                    const float cm = kRowTermOut ? -(tmin + un) : -tmin;   // largest log2 k of the block
+                    KMB_T(3);
+                    // lazy rescale: keep the reference exponent unless the maximum outgrew it by 2^8 (P <= 2^8 fits FP16;
+                    // a first block, ref == -inf, always adopts its maximum)
+                    const bool need = (ref == -INFINITY) ? (cm != -INFINITY) : (cm > ref + kLazyRescale);
+                    again = __any_sync(0xffffffffu, need);
+                    if (again) {
+                        const float sc = need ? ex2_approx(ref - cm) : 1.f;   // ref == -inf: 0 (nothing accumulated yet)
+                        if (sb > ww.sb_lo) {   // O_g holds this tile's sums
+                            wait_pv(n - 1);
+                            for (int c0 = 0; c0 < P.ebp; c0 += 16) {
+                                float o[16];
+                                tmem_ld_cols<16>(o_mine + c0, o);
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) o[c] *= sc;
+                                tmem_st_cols<16>(o_mine + c0, o);
+                            }
+                            tmem_st_wait();
+                            if (flushed && sc != 1.f)   // something was flushed already
+                                for (int c = 0; c < P.ebp; ++c) __stcg(olong + c * TM, sc * __ldcg(olong + c * TM));
+                        }
+                        ksum *= sc;
+                        if (need) ref = cm;
+                    }
+                    KMB_T(4);
+                } while (again);
+                // P over this thread's own S columns: FP16 hi / lo, two sources per TMEM column
+                tmem_st_32x16(st_addr, reinterpret_cast<const float*>(ph));
+                tmem_st_32x16(st_addr + CPT / 2, reinterpret_cast<const float*>(pl));
+                ksum += kacc.x + kacc.y;
+#else   // two phases: all t = -log2 k of the block, then (reference settled) all P
                 float2 t2[CPT / 2];   // S as pairs of sources, then t = -log2 k
                 tmem_ld_cols<CPT>(st_addr, reinterpret_cast<float(&)[CPT]>(t2));
                 KMB_T(2);
@@ -437,7 +736,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     const float2 nss2 = make_float2(-sscale, -sscale), un2 = make_float2(un, un);
 #pragma unroll
                     for (int c = 0; c < CPT / 4; ++c) {
-                        const float4 vq = vnq[c];   // broadcast read of the warp's line
+                        const float4 vq = KMB_PV16_VN_LDG ? __ldg(vnq + c) : vnq[c];   // broadcast read (L1 / the warp's line)
                         // Gaussian: |u|^2 is the same for the whole row, so it is left out of t here and added to the
                         // block minimum / subtracted with the reference exponent below (one FADD2 per four values less)
                         const float2 wa = make_float2(vq.x, vq.y), wb = make_float2(vq.z, vq.w);
@@ -503,6 +802,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     tmem_st_32x16(st_addr + CPT / 2, reinterpret_cast<const float*>(pl));
                     ksum += kacc.x + kacc.y;
                 }
+#endif
                 KMB_T(5);
                 tmem_st_wait();
                 if (until_flush == 0) {   // P.B(n) starts the O_g from zero
@@ -527,12 +827,21 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
             }
 #endif
 
+#endif
 
             // ------------------------------ row tile done: merge the four streams ------------------------------
             refbuf[cg * TM + row_in_tile] = ref;
             ksbuf[cg * TM + row_in_tile] = ksum;
+#if KMB_PV16_SETS
+            if (any) {   // (a stream without a block in this tile has nothing in its O_g: its long accumulator stays zero)
+                wait_pv(m_last);
+                flush_o();
+            }
+            n_base += cnt;
+#else
             wait_pv(n - 1);   // the tile's last PV
             flush_o();        // the long accumulators now hold the whole tile
+#endif
             __threadfence();
             named_bar_sync(2, EPI_THREADS);
             float rmax = -INFINITY, wg[NG], ktot = 0.f;
@@ -722,7 +1031,7 @@ int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
     pl->pair = pair_enabled && pl->n_tiles >= 2 && sms >= 2;
     pl->grid = pl->pair ? sms / 2 * 2 : sms;
     const int slot = pl->pair ? pv16::SLOT_BYTES / 2 : pv16::SLOT_BYTES;
-    const int fixed = 1024 + pl->kblocks * 2 * pv16::A_TILE_BYTES + pv16::EPI_WARPS * 2 * 32 * 4 + 2 * pv16::NG * tc::TM * 4 + 512;
+    const int fixed = 1024 + pl->kblocks * 2 * pv16::A_TILE_BYTES + pv16::EPI_WARPS * 2 * 64 * 4 + 2 * pv16::NG * tc::TM * 4 + 512;
     pl->stages = std::min(pl->pair ? 10 : 6, (smem_max - fixed) / slot);
     if (pl->stages < 3) return set_error(KMB_ERR_UNSUPPORTED, "not enough shared memory for D=%d", D);
     pl->smem = fixed + pl->stages * slot;
