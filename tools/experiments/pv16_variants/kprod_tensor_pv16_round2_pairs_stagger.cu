@@ -40,34 +40,45 @@ constexpr int SLOT_BYTES = 32768;      // ring slot: v block of one K block (hi 
                                        // (CTA pairs: each CTA holds half of either, 16 KB slots)
 constexpr int A_TILE_BYTES = TM * 128; // 16 KB: 128 rows of one 128-byte K block
 constexpr int PANEL_BYTES = 64 * 128;  // signal: 64 signal columns x 64 sources (one swizzle atom wide)
-// Shape of the epilogue (build-time; rounds 1 and 2 began with NG = 4, SST = 2, two phases per block):
+// Shape of the epilogue (build-time; the round-1 / round-2 kernel was NG = 4, SST = 2):
 //   NG  column groups = online-softmax streams (4 warps each, one per TMEM lane quarter), own accumulator O_g each
 //   SST S / P stages in tensor memory
 // 512 TMEM columns = SST * 128 (S / P) + NG * 64 (O_g).  With two stages the epilogue of block n + 2 cannot start before
-// P(n) of the SLOWEST group + P.B(n) + S(n + 2); with three the tensor side is always a block ahead.  What was measured on
-// the way (16 warps in pairs sharing a group, the groups skewed or staggered by a barrier, parts of the kernel removed,
-// SM clock inside the kernel): tools/experiments/README.md, profiles/r2_pv16_*.
+// P(n) of the SLOWEST group + P.B(n) + S(n + 2): the groups march in lock step and every latency of a block (tcgen05.ld,
+// the reference test, tcgen05.st + wait, the barrier round trip) is paid by all warps of an SM sub-partition at once.
+// Three stages leave a whole block of slack, so the two groups can run half a block apart (Params::skew_ns) and one
+// fills the MUFU / issue slots while the other waits.
+#ifndef KMB_PV16_X
+#define KMB_PV16_X 0   // experiment switches (timing only, results are wrong): see tools/experiments/README.md
+#endif
 #ifndef KMB_PV16_NG
 #define KMB_PV16_NG 2
 #endif
 #ifndef KMB_PV16_SST
 #define KMB_PV16_SST 3
 #endif
-#ifndef KMB_PV16_FUSED
-#define KMB_PV16_FUSED 1
+#ifndef KMB_PV16_WPG
+#define KMB_PV16_WPG 2
 #endif
-constexpr int NG = KMB_PV16_NG;        // epilogue column groups (4 warps each)
+constexpr int NG = KMB_PV16_NG;        // epilogue column groups = online-softmax streams (own reference, own O_g)
 constexpr int SST = KMB_PV16_SST;      // S / P stages
-constexpr int kFused = KMB_PV16_FUSED;   // one pass per block with the row's current reference: 0 never, 1 Gaussian, 2 both kernels
-constexpr int CPT = TNS / NG;          // S columns per epilogue thread
-constexpr int EPI_WARPS = 4 * NG;
+// Warps per (column group, TMEM lane quarter).  With 2 the group's columns are split between two warps that agree on
+// the block maximum through shared memory and a 64-thread named barrier once per block (same reference, same decisions,
+// one O_g): four epilogue warps per SM sub-partition for the MUFU / fixed-latency stalls to hide behind, with two
+// groups' worth of tensor memory.  Measured (tools/ubench_epilogue.cu): the P phase's instruction mix reaches 68 % of the
+// MUFU rate with two warps per sub-partition, 87 % with four.
+constexpr int WPG = KMB_PV16_WPG;
+constexpr int GW = TNS / NG;           // S columns of a group
+constexpr int CPT = GW / WPG;          // S columns per epilogue thread
+constexpr int EPI_WARPS = 4 * NG * WPG;
 constexpr int EPI_THREADS = 32 * EPI_WARPS;
 constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_EB = 64;             // signal columns per pass
 constexpr int COL_S = 0, COL_O = SST * TNS;
 static_assert(COL_O + NG * MAX_EB <= TMEM_COLS, "S / P stages and the O_g must fit 512 tensor-memory columns");
-static_assert(CPT % 32 == 0 && SST >= 2 && SST <= 4, "epilogue shape");
+static_assert(CPT % 32 == 0 && SST >= 2 && SST <= 4 && (WPG == 1 || WPG == 2), "epilogue shape");
+constexpr int PAIR_BAR0 = 3;           // named barriers 3 .. 3 + 4 NG - 1: the warp pair of (lane quarter, group)
 constexpr float kLazyRescale = 8.f;    // rescale O only when the row maximum outgrew the reference by 2^8
 constexpr int PS = MAX_EB + 2;         // partial record: O row, sum of weights, reference exponent
 // The tensor cores add into the FP32 accumulator with truncation, not round-to-nearest: every accumulating MMA shrinks
@@ -77,7 +88,9 @@ constexpr int PS = MAX_EB + 2;         // partial record: O row, sum of weights,
 // does not wait for) to a per-(CTA, group) FP32 accumulator in global memory and the next P.B starts from zero.
 // Measured at C4 (M = 262144): flush every 2048 blocks (= never) 2.4e-4, every 32 blocks 3.6e-6 at +6 % time (the L2
 // reductions of 148 CTAs arrive together).
-constexpr int kFlushBlocks = 256 / NG;   // default of Params::flush_blocks: 768 accumulating MMAs per O_g and flush, ~1.5e-5
+constexpr int kSkewNs = 0;             // default of Params::skew_ns
+constexpr int kStagger = 1;            // default of Params::stagger
+constexpr int kFlushBlocks = 128;      // default of Params::flush_blocks: 768 accumulating MMAs per flush, ~1.5e-5
 
 struct Params {
     const float* un;
@@ -91,6 +104,8 @@ struct Params {
     long long N, M;
     int E, e0, eb, ebp;        // this pass covers signal columns e0 .. e0+eb-1; ebp = eb rounded up to 32
     int n_tiles, nsb, kblocks, ksteps_last, stages, ep_rows, flush_blocks;
+    int skew_ns;               // column group g enters every row tile g * skew_ns late (see SST above)
+    int stagger;               // group 1 runs half a block behind group 0 (barrier per block)
     int R, C, W, R_last, C_last, slots_per_wave;
 };
 
@@ -144,6 +159,11 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 template <int KID>
 __device__ __forceinline__ float2 neg_log2_kernel2(float2 s_raw, float2 nsscale, float2 w) {
@@ -175,15 +195,17 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
     unsigned char* ring = u_region + P.kblocks * 2 * A_TILE_BYTES;    // stages x 32 KB
     float* vline = reinterpret_cast<float*>(ring + P.stages * SLOT);    // EPI_WARPS x 2 x CPT: per-warp |v|^2 lines
     float* refbuf = vline + EPI_WARPS * 2 * CPT;                               // NG x TM: per-group reference exponents
-    float* ksbuf = refbuf + NG * TM;                                           // NG x TM: per-group sums of weights
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ksbuf + NG * TM);
+    float* ksbuf = refbuf + NG * TM;                                           // NG x WPG x TM: per-warp sums of weights
+    float* cmx = ksbuf + NG * WPG * TM;                                        // 2 x NG x WPG x TM: block maxima of the warp pairs
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(cmx + 2 * NG * WPG * TM);
     uint64_t* empty_bar = full_bar + P.stages;
     uint64_t* acc_full = empty_bar + P.stages;     // [SST] S(n) complete in stage n % SST
     uint64_t* p_ready = acc_full + SST;            // [SST] P(n) stored in stage n % SST
     uint64_t* pv_done = p_ready + SST;             // [SST] PV(n) complete
     uint64_t* u_full = pv_done + SST;
     uint64_t* u_free = u_full + 1;
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(u_free + 1);
+    uint64_t* stg_bar = u_free + 1;                // [4 lane quarters][SST] group g - 1 is past the log2 k phase of block n
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(stg_bar + 4 * SST);
     int* s_flag = reinterpret_cast<int*>(tmem_base_smem + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -197,6 +219,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
         for (int a = 0; a < SST; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&p_ready[a], NCTA * EPI_WARPS); mbar_init(&pv_done[a], 1); }
         mbar_init(u_full, NCTA);
         mbar_init(u_free, 1);
+        for (int a = 0; a < 4 * SST; ++a) mbar_init(&stg_bar[a], WPG);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -329,16 +352,18 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
             const uint32_t p_base = tmem_base + COL_S + a * TNS;
             if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < TNS / 16; ++k) {   // 16 sources per instruction; column group g = k / (CPT / 16)
-                    constexpr int KPG = CPT / 16;      // instructions (of each of the three terms) per group
+                for (int k = 0; k < TNS / 16; ++k) {   // 16 sources per instruction; column group g = k / (GW / 16)
+                    constexpr int KPG = GW / 16;       // instructions (of each of the three terms) per group
                     const int g = k / KPG, kk = k % KPG, panel = k >> 2, koff = (k & 3) * 32;
                     const uint64_t bh = umma_desc_sw128(sg + panel * PANEL, koff);
                     const uint64_t bl = umma_desc_sw128(sg + (2 + panel) * PANEL, koff);
-                    const uint32_t a_hi = p_base + g * CPT + kk * 8, a_lo = a_hi + CPT / 2;
+                    const uint32_t a_hi = p_base + g * GW + kk * 8, a_lo = a_hi + GW / 2;
                     const uint32_t d_g = d_o + g * MAX_EB;
+#if !(KMB_PV16_X & 8)
                     mma_ts(d_g, a_lo, bh, idesc_o, !(from_zero && kk == 0));
                     mma_ts(d_g, a_hi, bl, idesc_o, 1);
                     mma_ts(d_g, a_hi, bh, idesc_o, 1);
+#endif
                 }
                 commit(&empty_bar[slot]);
                 commit(&pv_done[a]);
@@ -375,9 +400,11 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                                 const uint64_t al = umma_desc_sw128(at + A_TILE_BYTES, k * 32);
                                 const uint64_t bh = umma_desc_sw128(bt, k * 32);
                                 const uint64_t bl = umma_desc_sw128(bt + SLOT / 2, k * 32);
+#if !(KMB_PV16_X & 16)
                                 mma_ss(d_s, al, bh, idesc_s, (kb | k) != 0);
                                 mma_ss(d_s, ah, bl, idesc_s, 1);
                                 mma_ss(d_s, ah, bh, idesc_s, 1);
+#endif
                             }
                         }
                         commit(&empty_bar[slot]);
@@ -407,8 +434,14 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
         // -------------------------------------- epilogue --------------------------------------
         const int et = tid - 64;
         const int lane_group = warp & 3;             // TMEM lane quarter this warp may touch
-        const int cg = (warp - 2) >> 2;              // column group = online-softmax stream (own reference, sum, O_g)
-        const int col0 = cg * CPT;                   // first S column of this thread
+        const int widx = (warp - 2) >> 2;            // 0 .. NG WPG - 1
+        const int cg = widx / WPG;                   // column group = online-softmax stream (own reference, sum, O_g)
+        const int par = widx % WPG;                  // which of the group's WPG warps of this lane quarter
+        const int col0 = cg * GW + par * CPT;        // first S column of this thread
+        const int pair_bar = PAIR_BAR0 + lane_group * NG + cg;
+        // block maxima of the pair: [block parity][group][warp of the pair][row]
+        const uint32_t cmx_mine = smem_u32(cmx + (cg * WPG + par) * TM + lane_group * 32 + lane);
+        const uint32_t cmx_other = smem_u32(cmx + (cg * WPG + (par ^ (WPG - 1))) * TM + lane_group * 32 + lane);
         const int row_in_tile = lane_group * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(lane_group * 32) << 16;
         const uint32_t o_mine = tmem_base + COL_O + cg * MAX_EB + lane_addr;   // this group's accumulator
@@ -450,7 +483,8 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
             float ksum = 0.f, ref = -INFINITY;   // this group's stream
             // long accumulator of this thread's O_g row: zero, then only ever touched by this thread until the merge
             float* olong = P.olong + (static_cast<size_t>(blockIdx.x) * NG + cg) * (MAX_EB * TM) + row_in_tile;
-            for (int c = 0; c < P.ebp; ++c) __stcg(olong + c * TM, 0.f);
+            if (par == 0)
+                for (int c = 0; c < P.ebp; ++c) __stcg(olong + c * TM, 0.f);
             auto flush_o = [&]() {   // olong += O_g (after the last P.B into it has completed)
                 for (int c0 = 0; c0 < P.ebp; c0 += 16) {
                     float o[16];
@@ -463,6 +497,8 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 fetch_vn(ww.sb_lo);
                 primed = true;
             }
+            if (P.skew_ns > 0 && cg > 0) __nanosleep(static_cast<unsigned>(cg * P.skew_ns));
+            if (P.skew_ns < 0 && cg < NG - 1) __nanosleep(static_cast<unsigned>((NG - 1 - cg) * -P.skew_ns));   // the other way round
             // first block of the next wave this CTA works in (for the prefetch across the tile boundary)
             int sb_next_tile = -1;
             {
@@ -474,6 +510,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
             int until_flush = P.flush_blocks;   // blocks until this thread moves its O_g row to the long accumulator
             bool flushed = false;               // ... which has happened at least once in this tile
             for (int sb = ww.sb_lo; sb < ww.sb_hi; ++sb, ++n) {
+                const long long j0 = static_cast<long long>(sb) * TNS + col0;
                 const int a = n % SST;
                 const uint32_t st_addr = tmem_base + COL_S + a * TNS + col0 + lane_addr;
                 const uint32_t line = my_line_addr + (n & 1) * (CPT * 4);
@@ -484,7 +521,16 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     if (sbn >= 0) fetch_vn(sbn);
                 }
                 __syncwarp();
+                // Stagger (P.stagger): group 1 starts block n when group 0 has finished the block's log2 k phase, so that on
+                // every SM sub-partition one pair of warps is in a MUFU phase while the other loads, stores and signals.
+                // One barrier per S stage: group 0 cannot be a whole ring ahead (S(n + SST) needs P(n) of both groups).
+                if (P.stagger && cg == 1) mbar_wait(&stg_bar[lane_group * SST + a], (n / SST) & 1);
                 KMB_T(0);
+#ifdef KMB_PV16_TIMING
+                // lag between the column groups: clock of warps 2 (group 0) and 2 + 4 WPG (group 1) at blocks 8, 100 and 400
+                if (blockIdx.x == 0 && lane == 0 && lane_group == 2 && par == 0 && (n == 1544 || n == 1636 || n == 1736))
+                    P.out[64 + 16 + (n == 1544 ? 0 : n == 1636 ? 2 : 4) + cg] = static_cast<float>(clock64() - t_start);
+#endif
                 mbar_wait(&acc_full[a], (n / SST) & 1);
                 tc_fence_after();
                 KMB_T(1);
@@ -492,64 +538,19 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 tmem_ld_cols<CPT>(st_addr, reinterpret_cast<float(&)[CPT]>(t2));
                 KMB_T(2);
 
-                // Padded sources need no branch: their |v|^2 is 3.39e38, so their exponent is -3.39e38 or -inf and their
-                // weight an exact zero whatever the reference is.
-                constexpr bool kRowTermOut = (KID == KMB_KERNEL_GAUSSIAN);   // the Gaussian t leaves the row's |u|^2 out
-                const float2 nss2 = make_float2(-sscale, -sscale), un2 = make_float2(un, un);
-                uint32_t ph[CPT / 2], pl[CPT / 2];       // P = 2^(log2 k - ref): FP16 hi / lo, two sources per TMEM column
-                float2 kacc = make_float2(0.f, 0.f);     // two-level sum of the weights (see kprod_direct.cuh)
-                auto weight = [&](int c, float2 e) {     // exponent -> weight -> planes (2 MUFU.EX2 + 7 instructions)
-                    const float2 pw = make_float2(ex2_approx(e.x), ex2_approx(e.y));
-                    kacc = add2(kacc, pw);
-                    // 11 significant bits: exact in FP16
-                    const float2 h = make_float2(__uint_as_float(__float_as_uint(pw.x) & 0xffffe000u),
-                                                 __uint_as_float(__float_as_uint(pw.y) & 0xffffe000u));
-                    const float2 l = sub2(pw, h);
-                    ph[c] = pack_half2(h.x, h.y);
-                    pl[c] = pack_half2(l.x, l.y);
-                };
-                bool done = false;
-                if constexpr (kFused == 2 || (kFused == 1 && KID == KMB_KERNEL_GAUSSIAN)) {
-                    // One pass with the reference the row already has: S -> exponent -> weight, the largest exponent on the
-                    // side.  The lazy reference moves in a handful of blocks per row tile; only then (or while a row has
-                    // no reference yet) is the block redone in two phases below, from S, which is still in tensor memory.
-                    // Gaussian kernel: the two phases leave the MUFU pipe idle through the whole log2 k phase (C4 shape:
-                    // 45.1 -> 42.7 ms).  Exponential kernel: sqrt -> exponent -> ex2 in one chain is no faster than the two
-                    // MUFU-bound phases (52.3 against 51.4 ms), so it keeps them (profiles/r2_pv16_fused_ab.jsonl).
-                    if (__all_sync(0xffffffffu, ref != -INFINITY)) {
-                        const float nref = kRowTermOut ? -ref - un : -ref;
-                        const float2 nref2 = make_float2(nref, nref), ss2 = make_float2(sscale, sscale);
-                        const float2 nts2 = make_float2(-t_scale<KID>(), -t_scale<KID>());
-                        float emax = -INFINITY, emax_b = -INFINITY;   // two chains
-#pragma unroll
-                        for (int c = 0; c < CPT / 4; ++c) {
-                            const float4 vq = lds128(line + c * 16);   // broadcast read of the warp's line
-                            const float2 wa = make_float2(vq.x, vq.y), wb = make_float2(vq.z, vq.w);
-                            float2 ea, eb;
-                            if constexpr (KID == KMB_KERNEL_GAUSSIAN) {
-                                ea = fma2(t2[2 * c], ss2, sub2(nref2, wa));
-                                eb = fma2(t2[2 * c + 1], ss2, sub2(nref2, wb));
-                            } else {
-                                ea = fma2(neg_log2_kernel2<KID>(t2[2 * c], nss2, add2(wa, un2)), nts2, nref2);
-                                eb = fma2(neg_log2_kernel2<KID>(t2[2 * c + 1], nss2, add2(wb, un2)), nts2, nref2);
-                            }
-                            emax = fmaxf(fmaxf(emax, ea.x), ea.y);
-                            emax_b = fmaxf(fmaxf(emax_b, eb.x), eb.y);
-                            weight(2 * c, ea);
-                            weight(2 * c + 1, eb);
-                        }
-                        const bool need = fmaxf(emax, emax_b) > kLazyRescale;
-                        done = !__any_sync(0xffffffffu, need);
-                        if (!done) {
-                            tmem_ld_cols<CPT>(st_addr, reinterpret_cast<float(&)[CPT]>(t2));
-                            kacc = make_float2(0.f, 0.f);
-                        }
-                    }
-                }
-                KMB_T(3);
-                if (!done) {
-                    // t = -log2 of the kernel values (packed pairs) and their minimum over this thread's columns
-                    float tmin = INFINITY, tmin_b = INFINITY;   // two chains
+                // t = -log2 of the kernel values (packed pairs) and their minimum over this thread's columns
+                float tmin = INFINITY, tmin_b = INFINITY;   // two chains
+#if (KMB_PV16_X & 1)
+                tmin = 1.f;
+                if (false) {
+#elif (KMB_PV16_X & 32)
+                const bool x_idle = (cg == 1);   // experiment: group 1 skips the arithmetic
+                if (x_idle) tmin = 1.f;
+                if (j0 < P.M && !x_idle) {
+#else
+                if (j0 < P.M) {
+#endif
+                    const float2 nss2 = make_float2(-sscale, -sscale), un2 = make_float2(un, un);
 #pragma unroll
                     for (int c = 0; c < CPT / 4; ++c) {
                         const float4 vq = lds128(line + c * 16);   // broadcast read of the warp's line
@@ -564,14 +565,37 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                         tmin_b = fminf(fminf(tmin_b, tb.x), tb.y);
                     }
                     tmin = fminf(tmin, tmin_b);
-                    const float cm = kRowTermOut ? -(tmin + un) : -tmin * t_scale<KID>();   // largest log2 k of the block
-                    // lazy rescale: keep the reference exponent unless the maximum outgrew it by 2^8
+                }
+#if !(KMB_PV16_X & 1)
+                else {   // every source of this group is padding (warp-uniform): all weights are zero
+#pragma unroll
+                    for (int c = 0; c < CPT / 2; ++c) t2[c] = make_float2(INFINITY, INFINITY);
+                }
+#endif
+                constexpr bool kRowTermOut = (KID == KMB_KERNEL_GAUSSIAN);   // t2 lacks the row's |u|^2
+                float cm = kRowTermOut ? -(tmin + un) : -tmin * t_scale<KID>();   // largest log2 k of the block
+                if constexpr (WPG == 2) {
+                    // the pair's maximum: both warps then take the same decisions on the same reference.  The barrier also
+                    // orders this warp's S loads before the partner's P stores into the same columns (P hi of both warps
+                    // goes to the first half of the group's columns, P lo to the second).
+                    const uint32_t off = (n & 1) * (NG * WPG * TM * 4);
+                    sts32(cmx_mine + off, cm);
+                    named_bar_sync(pair_bar, 64);
+                    cm = fmaxf(cm, lds32(cmx_other + off));
+                }
+                if (P.stagger && cg == 0) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&stg_bar[lane_group * SST + a]);
+                }
+                KMB_T(3);
+                // lazy rescale: keep the reference exponent unless the maximum outgrew it by 2^8
+                {
                     bool need = false;
                     if (ref == -INFINITY) ref = cm;   // nothing but zero weights so far
                     else need = cm > ref + kLazyRescale;
                     if (__any_sync(0xffffffffu, need)) {
                         const float sc = need ? ex2_approx(ref - cm) : 1.f;
-                        if (sb > ww.sb_lo) {   // O_g holds this tile's sums
+                        if (sb > ww.sb_lo && par == 0) {   // O_g holds this tile's sums
                             wait_pv(n - 1);
                             for (int c0 = 0; c0 < P.ebp; c0 += 16) {
                                 float o[16];
@@ -587,27 +611,53 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                         ksum *= sc;
                         if (need) ref = cm;
                     }
+                }
+                KMB_T(4);
+                // P = 2^(log2 k - ref) = 2^(-ref - t), FP16 hi / lo, two sources per TMEM column, over this thread's own S columns
+                {
+                    uint32_t ph[CPT / 2], pl[CPT / 2];
+                    float2 kacc = make_float2(0.f, 0.f);   // two-level sum of the weights (see kprod_direct.cuh)
                     // all -inf so far: every weight is 2^-inf = 0
                     const float nref = (ref == -INFINITY) ? 0.f : (kRowTermOut ? -ref - un : -ref);
                     const float2 nref2 = make_float2(nref, nref);
 #pragma unroll
-                    for (int c = 0; c < CPT / 2; ++c)
-                        weight(c, (KID == KMB_KERNEL_GAUSSIAN) ? sub2(nref2, t2[c])
-                                                                : fma2(t2[c], make_float2(-t_scale<KID>(), -t_scale<KID>()), nref2));
-                }
-                KMB_T(4);
-                {
-                    // the group's P over the thread's own S columns: hi planes in the first half, lo planes in the second
-                    const uint32_t p_addr = tmem_base + COL_S + a * TNS + col0 + lane_addr;
+                    for (int c = 0; c < CPT / 2; ++c) {
+                        const float2 e = (KID == KMB_KERNEL_GAUSSIAN) ? sub2(nref2, t2[c])
+                                                                      : fma2(t2[c], make_float2(-t_scale<KID>(), -t_scale<KID>()), nref2);
+#if (KMB_PV16_X & 2)
+                        const float2 pw = e;
+#elif (KMB_PV16_X & 32)
+                        float2 pw = e;
+                        if (!x_idle) pw = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+#else
+                        const float2 pw = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+#endif
+                        kacc = add2(kacc, pw);
+                        // 11 significant bits: exact in FP16
+                        const float2 h = make_float2(__uint_as_float(__float_as_uint(pw.x) & 0xffffe000u),
+                                                     __uint_as_float(__float_as_uint(pw.y) & 0xffffe000u));
+                        const float2 l = sub2(pw, h);
+#if (KMB_PV16_X & 4)
+                        ph[c] = __float_as_uint(pw.x);
+                        pl[c] = __float_as_uint(pw.y);
+#else
+                        ph[c] = pack_half2(h.x, h.y);
+                        pl[c] = pack_half2(l.x, l.y);
+#endif
+                    }
+                    // the group's P: hi planes of its GW sources in the first GW / 2 columns, lo planes in the second
+                    const uint32_t p_addr = tmem_base + COL_S + a * TNS + cg * GW + par * (CPT / 2) + lane_addr;
                     tmem_st_cols<CPT / 2>(p_addr, reinterpret_cast<const float(&)[CPT / 2]>(ph));
-                    tmem_st_cols<CPT / 2>(p_addr + CPT / 2, reinterpret_cast<const float(&)[CPT / 2]>(pl));
+                    tmem_st_cols<CPT / 2>(p_addr + GW / 2, reinterpret_cast<const float(&)[CPT / 2]>(pl));
                     ksum += kacc.x + kacc.y;
                 }
                 KMB_T(5);
                 tmem_st_wait();
                 if (until_flush == 0) {   // P.B(n) starts the O_g from zero
-                    wait_pv(n - 1);
-                    flush_o();
+                    if (par == 0) {
+                        wait_pv(n - 1);
+                        flush_o();
+                    }
                     until_flush = P.flush_blocks;
                     flushed = true;
                 }
@@ -633,10 +683,12 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
 
 
             // ------------------------------ row tile done: merge the four streams ------------------------------
-            refbuf[cg * TM + row_in_tile] = ref;
-            ksbuf[cg * TM + row_in_tile] = ksum;
-            wait_pv(n - 1);   // the tile's last PV
-            flush_o();        // the long accumulators now hold the whole tile
+            refbuf[cg * TM + row_in_tile] = ref;   // the same in every warp of the group
+            ksbuf[widx * TM + row_in_tile] = ksum;
+            if (par == 0) {
+                wait_pv(n - 1);   // the tile's last PV
+                flush_o();        // the long accumulators now hold the whole tile
+            }
             __threadfence();
             named_bar_sync(2, EPI_THREADS);
             float rmax = -INFINITY, wg[NG], ktot = 0.f;
@@ -646,7 +698,9 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
             for (int g = 0; g < NG; ++g) {
                 const float rg = refbuf[g * TM + row_in_tile];
                 wg[g] = (rg == -INFINITY) ? 0.f : ex2_approx(rg - rmax);
-                ktot = fmaf(wg[g], ksbuf[g * TM + row_in_tile], ktot);   // fixed order
+                float kg = ksbuf[g * WPG * TM + row_in_tile];
+                if constexpr (WPG == 2) kg += ksbuf[(g * WPG + 1) * TM + row_in_tile];
+                ktot = fmaf(wg[g], kg, ktot);   // fixed order
             }
             const bool complete = (ww.Cw == 1);
             const bool ghost = tile >= P.n_tiles;   // pairs: an odd number of row tiles leaves the last peer without one
@@ -655,7 +709,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
             float* mine = P.partial + (slot0 + static_cast<size_t>(ww.c) * NCTA) * (TM * PS);
             // plain product: undo the reference exponent (2^ref may underflow exactly where FP32 K b would)
             const float row_scale = NORM ? 1.f / ktot : ((rmax == -INFINITY) ? 0.f : ex2_approx(rmax));
-            for (int c0 = cg * 16; c0 < P.ebp; c0 += NG * 16) {   // this thread merges 16-column chunks c0 of all O_g
+            for (int c0 = widx * 16; c0 < P.ebp; c0 += NG * WPG * 16) {   // this thread merges 16-column chunks c0 of all O_g
                 float o[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) o[c] = 0.f;
@@ -679,7 +733,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
             }
             tc_fence_before();
             if (!complete && !ghost) {
-                if (cg == 0) {
+                if (widx == 0) {
                     mine[MAX_EB * TM + row_in_tile] = ktot;
                     mine[(MAX_EB + 1) * TM + row_in_tile] = rmax;
                 }
@@ -699,7 +753,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     float mx = -INFINITY;
                     for (int c = 0; c < ww.Cw; ++c)
                         mx = fmaxf(mx, __ldcg(P.partial + (slot0 + static_cast<size_t>(c) * NCTA) * (TM * PS) + (MAX_EB + 1) * TM + row_in_tile));
-                    for (int e = cg; e < P.eb; e += NG) {   // the groups share the signal columns of the row
+                    for (int e = widx; e < P.eb; e += NG * WPG) {   // the warps of a lane quarter share the signal columns of the row
                         float sum = 0.f, l = 0.f;
                         for (int c = 0; c < ww.Cw; ++c) {
                             const float* ps = P.partial + (slot0 + static_cast<size_t>(c) * NCTA) * (TM * PS);
@@ -826,7 +880,7 @@ int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
     pl->pair = pair_enabled && pl->n_tiles >= 2 && sms >= 2;
     pl->grid = pl->pair ? sms / 2 * 2 : sms;
     const int slot = pl->pair ? pv16::SLOT_BYTES / 2 : pv16::SLOT_BYTES;
-    const int fixed = 1024 + pl->kblocks * 2 * pv16::A_TILE_BYTES + pv16::EPI_WARPS * 2 * pv16::CPT * 4 + 2 * pv16::NG * tc::TM * 4 + 512;
+    const int fixed = 1024 + pl->kblocks * 2 * pv16::A_TILE_BYTES + pv16::EPI_WARPS * 2 * pv16::CPT * 4 + (1 + 3 * pv16::WPG) * pv16::NG * tc::TM * 4 + 512;
     pl->stages = std::min(pl->pair ? 10 : 6, (smem_max - fixed) / slot);
     if (pl->stages < 3) return set_error(KMB_ERR_UNSUPPORTED, "not enough shared memory for D=%d", D);
     pl->smem = fixed + pl->stages * slot;
@@ -959,6 +1013,17 @@ int tensor_pv16_product(const float* x, const float* y, const float* b, float* o
             return v < 1 ? 1 : v;
         }();
         P.flush_blocks = flush_blocks;
+        static const int skew_ns = [] {   // tuning knob
+            const char* e = getenv("KMB_PV16_SKEW_NS");
+            const int v = e ? atoi(e) : pv16::kSkewNs;
+            return v;
+        }();
+        P.skew_ns = skew_ns;
+        static const int stagger = [] {   // tuning knob
+            const char* e = getenv("KMB_PV16_STAGGER");
+            return e ? atoi(e) : pv16::kStagger;
+        }();
+        P.stagger = (pv16::NG == 2) ? stagger : 0;
         P.R = pl.waves.R;
         P.C = pl.waves.C;
         P.W = pl.waves.W;

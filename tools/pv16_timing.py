@@ -11,10 +11,10 @@ N = M = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 r = (3.0 / D) ** 0.5
 x = torch.tensor(r * rng.rand(N, D), dtype=torch.float32, device='cuda'); y = torch.tensor(r * rng.rand(M, D), dtype=torch.float32, device='cuda')
 b = torch.tensor(rng.randn(M, E), dtype=torch.float32, device='cuda')
-names = ['loop top', 'wait S', 'LDTM', 'log2 k', 'rescale', 'P', 'st+arrive', 'blocks', 'MMA: other', 'wait P', 'wait signal', 'MMA: issue', 'wait V']
+names = ['loop top', 'wait S', 'LDTM', 'log2 k', 'rescale', 'P', 'st+arrive', 'blocks', 'MMA: other', 'wait P', 'wait signal', 'MMA: issue', 'wait V', 'cycles/block', 'MHz']
 for kernel in ('gaussian', 'absolute-exponential'):
     for rep in range(2):
         out = product.kernel_product(x, y, b, kernel=kernel, normalize_rows=True)
     torch.cuda.synchronize()
-    v = out[0, :13].cpu().numpy()
+    v = out[0, :15].cpu().numpy()
     print(kernel, ' '.join(f'{n}={a:.0f}' for n, a in zip(names, v)), 'epilogue total', v[:7].sum())
