@@ -6,21 +6,23 @@
 //
 //   S = 2 u.v^T   128 rows x 128 sources per block; tcgen05.mma kind::f16, three-term split
 //                 (lo.hi + hi.lo + hi.hi), A = u tile (hi, lo) resident in shared memory for the whole row
-//                 tile, B = v blocks streamed by TMA, FP32 accumulator in TMEM (two stages)
-//   P = k(S)      16 epilogue warps = 4 column groups x 4 TMEM lane quarters.  Group g owns columns [32g, 32g+32)
+//                 tile, B = v blocks streamed by TMA, FP32 accumulator in TMEM (SST = 3 stages)
+//   P = k(S)      8 epilogue warps = NG = 2 column groups x 4 TMEM lane quarters.  Group g owns columns [64g, 64g+64)
 //                 of every S block and runs its OWN online-softmax stream over those sources: tcgen05.ld S, log2
 //                 of the kernel, a running reference exponent per (row, group) (lazy rescale of the group's O
 //                 when the maximum outgrows it by 2^8, so P <= 2^8 fits FP16 and rows whose kernel values all
 //                 underflow FP32 still normalise), P = 2^(log2 k - ref) split into FP16 hi + lo, packed two per
 //                 32-bit column and stored IN PLACE over the thread's own S columns (tcgen05.st).  No
-//                 block-level synchronisation between epilogue warps inside a row tile.
+//                 block-level synchronisation between epilogue warps inside a row tile.  Gaussian kernel: one fused
+//                 pass per block with the reference the row already has (kFused); the two phases only when it moves.
 //   O_g += P_g.B  tcgen05.mma with A = P from TMEM (hi, lo), B = transposed signal block (FP16 hi, lo, scaled per
 //                 signal column by a power of two) from shared memory; one accumulator O_g (128 x E) per column
-//                 group, kept in TMEM for the whole row tile; the four are merged (weights 2^(ref_g - ref)) when
+//                 group, kept in TMEM for the whole row tile; the NG of them are merged (weights 2^(ref_g - ref)) when
 //                 the row tile ends -- every thread can read all four because TMEM lanes are rows.
 //
-// TMEM columns: S/P stage 0 [0,128) | S/P stage 1 [128,256) | O_0 .. O_3 at 256 + 64 g.
-// S(n+2) overwrites stage n & 1 after PV(n) has been issued (tensor-pipe order), so P is double buffered for free.
+// TMEM columns: S/P stages at 128 a, a < SST | O_g at 128 SST + 64 g  (3 x 128 + 2 x 64 = 512).
+// S(n + SST) overwrites stage n % SST after PV(n) has been issued (tensor-pipe order): the issue order is
+// S(0) .. S(SST-1), PV(0), S(SST), PV(1), ..., so the tensor side runs SST - 1 blocks ahead of the epilogue.
 // Work split: the wave schedule of kprod_tensor.cu -- every CTA of a wave walks the SAME source blocks at the same
 // time (all of them when there are at least as many row tiles as CTAs), so v and b blocks come from L2.
 #include <algorithm>
@@ -632,7 +634,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
 #endif
 
 
-            // ------------------------------ row tile done: merge the four streams ------------------------------
+            // ------------------------------ row tile done: merge the streams of the column groups ------------------------------
             refbuf[cg * TM + row_in_tile] = ref;
             ksbuf[cg * TM + row_in_tile] = ksum;
             wait_pv(n - 1);   // the tile's last PV
