@@ -452,23 +452,32 @@ def run_b200_arm(args):
     if not args.no_e2e:
         xs_host = ds.source_points[lo:hi]
 
+        phases = {}   # host seconds per plugin call, summed over the timed steps (this rank)
+
+        def timed(name, fn, **kw):
+            t = time.perf_counter()
+            out = fn(**kw)
+            phases[name] = phases.get(name, 0.0) + time.perf_counter() - t
+            return out
+
         def e2e_step():
-            algo = B200Product(kernel="gaussian", dimension=3, normalize_rows=False, precision="float32", path=args.path,
-                               device=local_rank, distributed=(sym and world > 1))
+            algo = timed("construct", B200Product, kernel="gaussian", dimension=3, normalize_rows=False, precision="float32",
+                         path=args.path, device=local_rank, distributed=(sym and world > 1))
             if world == 1 or sym:
-                algo.prepare_data(source_points=ds.source_points, target_points=ds.source_points, same_points=True)
+                timed("prepare_data", algo.prepare_data, source_points=ds.source_points, target_points=ds.source_points, same_points=True)
             else:
-                algo.prepare_data(source_points=ds.source_points, target_points=xs_host, same_points=False)
-            algo.fit()
-            algo.prepare_query(source_signal=ds.source_signal)
-            algo.query()
-            res = algo.get_result()
-            algo.done()
+                timed("prepare_data", algo.prepare_data, source_points=ds.source_points, target_points=xs_host, same_points=False)
+            timed("fit", algo.fit)
+            timed("prepare_query", algo.prepare_query, source_signal=ds.source_signal)
+            timed("query", algo.query)
+            res = timed("get_result", algo.get_result)
+            timed("done", algo.done)
             return res
 
         for _ in range(max(1, min(2, args.warmup))):
             e2e_step()
         barrier()
+        phases.clear()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             res = e2e_step()
@@ -485,6 +494,7 @@ def run_b200_arm(args):
             "h2d_bytes_per_step": int(4 * (n_x + M * 3 + M * 1)),
             "d2h_bytes_per_step": int(4 * n_out),
             "api": "B200Product.prepare_data/fit/prepare_query/query/get_result, host float64 in/out",
+            "host_ms_per_call": {k: round(1e3 * v / args.steps, 3) for k, v in phases.items()},   # rank 0's clock
         }
         assert res.shape == (n_out, 1)
         if rank == 0:
