@@ -481,6 +481,45 @@ def test_tensor_pv_lazy_rescale(kernel, path):
     assert orc.rel_l2(out, want) <= 5e-4  # |u||v| ~ 1e4 here: the 3xTF32 cancellation error of d^2 is ~1e-2
 
 
+@pytest.mark.parametrize("norm", [False, True])
+@pytest.mark.parametrize("kernel", ["gaussian", "absolute-exponential"])
+def test_tensor_pv16_reference_moves_block_after_block(kernel, norm):
+    """Sources sorted from far to near in small steps: the lazy reference of every row moves in many of the 128-source
+    blocks of a row tile, so the fused pass of kprod_tensor_pv16 (exponent with the reference the row already has) is
+    redone in two phases again and again, with accumulators to rescale and long accumulators already flushed
+    (M > 64 blocks).  E = 64, D = 64: the shape of config C4."""
+    rng = np.random.RandomState(11)
+    D, E, M, N = 64, 64, 128 * 150 + 37, 300
+    step = np.linspace(6.0 if kernel == "gaussian" else 40.0, 0.0, M)[:, None] / np.sqrt(D)   # distance to the targets shrinks
+    y = 0.15 * rng.rand(M, D) + step
+    x = 0.15 * rng.rand(N, D)
+    b = rng.randn(M, E)
+    out, extra = run_plugin(kernel, y, x, b, normalize_rows=norm, path="tensor")
+    assert extra["path_used"] == "tensor_f16"
+    want = orc.kernel_product(kernel, y, x, b, normalize_rows=norm)
+    assert np.isfinite(out).all()
+    # exponential kernel: the sources span 40 length units, |u||v| ~ 300 in log2 units, and the cancellation error of the
+    # three-term d^2 (2^-22 |u||v|) goes through a square root at the near sources -- as in test_tensor_pv_lazy_rescale
+    assert orc.rel_l2(out, want) <= (TOL_TENSOR if kernel == "gaussian" else 5e-4)
+
+
+@pytest.mark.parametrize("M", [1, 63, 64, 65, 127, 129, 200])
+@pytest.mark.parametrize("kernel", ["gaussian", "absolute-exponential"])
+def test_tensor_pv16_padded_sources_weigh_nothing(kernel, M):
+    """Blocks that are partly or (for one column group) wholly padding: padded sources carry |v|^2 = 3.39e38 and must come
+    out as exact zero weights without a branch, whatever the row's reference exponent is (also when a group never sees a
+    real source: M <= 64)."""
+    rng = np.random.RandomState(M)
+    D, E, N = 64, 40, 260
+    r = (3.0 / D) ** 0.5
+    y, x, b = r * rng.rand(M, D), r * rng.rand(N, D), rng.randn(M, E)
+    for norm in (False, True):
+        out, _ = run_plugin(kernel, y, x, b, normalize_rows=norm, path="tensor")
+        want = orc.kernel_product(kernel, y, x, b, normalize_rows=norm)
+        assert np.isfinite(out).all()
+        assert orc.rel_l2(out, want) <= TOL_TENSOR
+
+
 # ---- symmetric (same_points) Gaussian product: kprod_sym --------------------------------------------
 
 def _sym_case(n, D, radius=1.0, kernel="gaussian", round_inputs=False):
