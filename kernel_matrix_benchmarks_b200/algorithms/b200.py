@@ -42,7 +42,7 @@ def _check_precision(precision, who, allowed=(np.float32,)):
 
 
 _CAST_THREADS = 4            # host threads of one cast (numpy releases the GIL inside copyto)
-_CAST_MIN_BYTES = 4 << 20    # below this a single pass is faster than handing out slices
+_CAST_MIN_BYTES = 2 << 20    # below this a single pass is faster than handing out slices (C2: the 4 MB result and signal are above it)
 _cast_pool = None
 
 
