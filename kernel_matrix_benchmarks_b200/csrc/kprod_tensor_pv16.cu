@@ -4,7 +4,8 @@
 // tools/ubench_umma.cu: a 128 x 64 x 8 SS MMA takes 60 cycles for 32 cycles of math, a 128 x 128 x 16 one 75 for
 // 64, and kind::f16 does twice the work of kind::tf32 per instruction.
 //
-//   S = 2 u.v^T   128 rows x 128 sources per block; tcgen05.mma kind::f16, three-term split
+//   S = 2 u.v^T   (exponential kernel: 2 u.v - |u|^2 - |v|^2, the squared norms as one more BF16 K step -- extra_k)
+//                 128 rows x 128 sources per block; tcgen05.mma kind::f16, three-term split
 //                 (lo.hi + hi.lo + hi.hi), A = u tile (hi, lo) resident in shared memory for the whole row
 //                 tile, B = v blocks streamed by TMA, FP32 accumulator in TMEM (SST = 3 stages)
 //   P = k(S)      8 epilogue warps = NG = 2 column groups x 4 TMEM lane quarters.  Group g owns columns [64g, 64g+64)
@@ -28,6 +29,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "tensor_common.cuh"
@@ -58,9 +60,19 @@ constexpr int PANEL_BYTES = 64 * 128;  // signal: 64 signal columns x 64 sources
 #ifndef KMB_PV16_FUSED
 #define KMB_PV16_FUSED 1
 #endif
+#ifndef KMB_PV16_EXTRAK
+#define KMB_PV16_EXTRAK 1
+#endif
 constexpr int NG = KMB_PV16_NG;        // epilogue column groups (4 warps each)
 constexpr int SST = KMB_PV16_SST;      // S / P stages
 constexpr int kFused = KMB_PV16_FUSED;   // one pass per block with the row's current reference: 0 never, 1 Gaussian, 2 both kernels
+// |u|^2 + |v|^2 through the tensor cores: one more K step (BF16: FP32's exponent range) whose operands are three BF16 pieces of
+// -2^2p |u_i|^2 against ones and ones against three pieces of -2^2p |v_j|^2, so that the accumulator holds (2 u.v - |u|^2 - |v|^2) / sscale
+// = -d2 / sscale and the epilogue needs neither the shared-memory line of |v|^2 nor a packed add per pair.  0 never, 1 exponential
+// kernel, 2 both kernels.
+constexpr int kExtraK = KMB_PV16_EXTRAK;
+template <int KID>
+__host__ __device__ constexpr bool extra_k() { return kExtraK == 2 || (kExtraK == 1 && KID == KMB_KERNEL_ABSOLUTE_EXPONENTIAL); }
 constexpr int CPT = TNS / NG;          // S columns per epilogue thread
 constexpr int EPI_WARPS = 4 * NG;
 constexpr int EPI_THREADS = 32 * EPI_WARPS;
@@ -168,13 +180,15 @@ __device__ __forceinline__ float2 neg_log2_kernel2(float2 s_raw, float2 nsscale,
 template <int KID, bool NORM, bool PAIR>
 __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUtensorMap& map_al, const CUtensorMap& map_bh,
                                           const CUtensorMap& map_bl, const CUtensorMap& map_sh, const CUtensorMap& map_sl,
-                                          const Params& P) {
+                                          const CUtensorMap& map_ue, const CUtensorMap& map_ve, const Params& P) {
+    constexpr bool XK = extra_k<KID>();                            // the squared norms come out of the tensor cores
     constexpr int SLOT = PAIR ? SLOT_BYTES / 2 : SLOT_BYTES;       // V: hi | lo halves of the slot
     constexpr int PANEL = PAIR ? PANEL_BYTES / 2 : PANEL_BYTES;    // signal: 4 panels (hi 0, hi 1, lo 0, lo 1)
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    unsigned char* u_region = smem;                                   // kblocks x [A hi 16 KB | A lo 16 KB]
-    unsigned char* ring = u_region + P.kblocks * 2 * A_TILE_BYTES;    // stages x 32 KB
+    unsigned char* u_region = smem;                                   // kblocks x [A hi 16 KB | A lo 16 KB] (+ the norm tile)
+    unsigned char* u_extra = u_region + P.kblocks * 2 * A_TILE_BYTES; // XK: 128 rows x [3 pieces of -2^2p |u|^2, 1, 1, 1, 0 ..] (BF16)
+    unsigned char* ring = u_extra + (XK ? A_TILE_BYTES : 0);          // stages x 32 KB
     float* vline = reinterpret_cast<float*>(ring + P.stages * SLOT);    // EPI_WARPS x 2 x CPT: per-warp |v|^2 lines
     float* refbuf = vline + EPI_WARPS * 2 * CPT;                               // NG x TM: per-group reference exponents
     float* ksbuf = refbuf + NG * TM;                                           // NG x TM: per-group sums of weights
@@ -263,11 +277,12 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
             mbar_wait(u_free, (seg & 1) ^ 1);
             const int my_row0 = (PAIR ? ww.tile * 2 + static_cast<int>(rank) : ww.tile) * TM;
             if (elect_one()) {
-                arm_full(u_full, P.kblocks * 2 * A_TILE_BYTES);
+                arm_full(u_full, (P.kblocks * 2 + (XK ? 1 : 0)) * A_TILE_BYTES);
                 for (int kb = 0; kb < P.kblocks; ++kb) {
                     load2d(u_region + (kb * 2 + 0) * A_TILE_BYTES, &map_ah, kb * 64, my_row0, u_full);
                     load2d(u_region + (kb * 2 + 1) * A_TILE_BYTES, &map_al, kb * 64, my_row0, u_full);
                 }
+                if constexpr (XK) load2d(u_extra, &map_ue, 0, my_row0, u_full);
             }
             __syncwarp();
             ++seg;
@@ -280,6 +295,16 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                         arm_full(&full_bar[slot], SLOT);
                         load2d(dst, &map_bh, kb * 64, src0, &full_bar[slot]);
                         load2d(dst + SLOT / 2, &map_bl, kb * 64, src0, &full_bar[slot]);
+                    }
+                    __syncwarp();
+                    ring_next();
+                }
+                if constexpr (XK) {   // the block's norm tile: its own ring slot (half of it used)
+                    mbar_wait(&empty_bar[slot], ring_phase ^ 1u);
+                    const int src0 = sb * TNS + (PAIR ? static_cast<int>(rank) * (TNS / 2) : 0);
+                    if (elect_one()) {
+                        arm_full(&full_bar[slot], SLOT / 2);
+                        load2d(ring + slot * SLOT, &map_ve, 0, src0, &full_bar[slot]);
                     }
                     __syncwarp();
                     ring_next();
@@ -387,6 +412,17 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     __syncwarp();
                     ring_next();
                 }
+                if constexpr (XK) {   // S -= (|u|^2 + |v|^2) / sscale: one BF16 MMA, K = 16
+                    mbar_wait(&full_bar[slot], ring_phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        constexpr uint32_t bf16_ab = (1u << 7) | (1u << 10);   // A and B formats: BF16
+                        mma_ss(d_s, umma_desc_sw128(u_extra, 0), umma_desc_sw128(ring + slot * SLOT, 0), idesc_s | bf16_ab, 1);
+                        commit(&empty_bar[slot]);
+                    }
+                    __syncwarp();
+                    ring_next();
+                }
                 const bool last_of_tile = (sb + 1 == ww.sb_hi);
                 if (elect_one()) {
                     commit(&acc_full[a]);
@@ -461,7 +497,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     for (int c = 0; c < 16; ++c) atomicAdd(olong + (c0 + c) * TM, o[c]);   // RED: nothing to wait for
                 }
             };
-            if (!primed) {
+            if (!XK && !primed) {
                 fetch_vn(ww.sb_lo);
                 primed = true;
             }
@@ -479,13 +515,13 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 const int a = n % SST;
                 const uint32_t st_addr = tmem_base + COL_S + a * TNS + col0 + lane_addr;
                 const uint32_t line = my_line_addr + (n & 1) * (CPT * 4);
+                if constexpr (!XK) {
 #pragma unroll
-                for (int q = 0; q < VQ; ++q) sts32(line + (q * 32 + lane) * 4, vn_next[q]);
-                {
+                    for (int q = 0; q < VQ; ++q) sts32(line + (q * 32 + lane) * 4, vn_next[q]);
                     const int sbn = (sb + 1 < ww.sb_hi) ? sb + 1 : sb_next_tile;
                     if (sbn >= 0) fetch_vn(sbn);
+                    __syncwarp();
                 }
-                __syncwarp();
                 KMB_T(0);
                 mbar_wait(&acc_full[a], (n / SST) & 1);
                 tc_fence_after();
@@ -496,8 +532,18 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
 
                 // Padded sources need no branch: their |v|^2 is 3.39e38, so their exponent is -3.39e38 or -inf and their
                 // weight an exact zero whatever the reference is.
-                constexpr bool kRowTermOut = (KID == KMB_KERNEL_GAUSSIAN);   // the Gaussian t leaves the row's |u|^2 out
+                constexpr bool kRowTermOut = (KID == KMB_KERNEL_GAUSSIAN) && !XK;   // the Gaussian t leaves the row's |u|^2 out
                 const float2 nss2 = make_float2(-sscale, -sscale), un2 = make_float2(un, un);
+                // XK: the accumulator is -d2 / sscale.  Gaussian: t = -sscale S.  Exponential: |S| - S = 2 max(d2, 0) / sscale in one
+                // packed add, T = its MUFU.SQRT, t = sqrt(sscale / 2) T -- the factor leaves with the FFMA2 that forms the exponent.
+                const float xk_tscale = (KID == KMB_KERNEL_GAUSSIAN) ? 1.f : sqrtf(0.5f * sscale);
+                auto xk_t = [&](float2 sv) -> float2 {
+                    if constexpr (KID == KMB_KERNEL_GAUSSIAN) return mul2(sv, nss2);
+                    else {
+                        const float2 r = add2(make_float2(fabsf(sv.x), fabsf(sv.y)), make_float2(-sv.x, -sv.y));
+                        return make_float2(sqrt_mufu(r.x), sqrt_mufu(r.y));
+                    }
+                };
                 uint32_t ph[CPT / 2], pl[CPT / 2];       // P = 2^(log2 k - ref): FP16 hi / lo, two sources per TMEM column
                 float2 kacc = make_float2(0.f, 0.f);     // two-level sum of the weights (see kprod_direct.cuh)
                 auto weight = [&](int c, float2 e) {     // exponent -> weight -> planes (2 MUFU.EX2 + 7 instructions)
@@ -521,14 +567,23 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     if (__all_sync(0xffffffffu, ref != -INFINITY)) {
                         const float nref = kRowTermOut ? -ref - un : -ref;
                         const float2 nref2 = make_float2(nref, nref), ss2 = make_float2(sscale, sscale);
-                        const float2 nts2 = make_float2(-t_scale<KID>(), -t_scale<KID>());
+                        const float2 nts2 = XK ? make_float2(-xk_tscale, -xk_tscale) : make_float2(-t_scale<KID>(), -t_scale<KID>());
                         float emax = -INFINITY, emax_b = -INFINITY;   // two chains
 #pragma unroll
                         for (int c = 0; c < CPT / 4; ++c) {
-                            const float4 vq = lds128(line + c * 16);   // broadcast read of the warp's line
+                            float4 vq = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if constexpr (!XK) vq = lds128(line + c * 16);   // broadcast read of the warp's line
                             const float2 wa = make_float2(vq.x, vq.y), wb = make_float2(vq.z, vq.w);
                             float2 ea, eb;
-                            if constexpr (KID == KMB_KERNEL_GAUSSIAN) {
+                            if constexpr (XK) {
+                                if constexpr (KID == KMB_KERNEL_GAUSSIAN) {
+                                    ea = fma2(t2[2 * c], ss2, nref2);
+                                    eb = fma2(t2[2 * c + 1], ss2, nref2);
+                                } else {
+                                    ea = fma2(xk_t(t2[2 * c]), nts2, nref2);
+                                    eb = fma2(xk_t(t2[2 * c + 1]), nts2, nref2);
+                                }
+                            } else if constexpr (KID == KMB_KERNEL_GAUSSIAN) {
                                 ea = fma2(t2[2 * c], ss2, sub2(nref2, wa));
                                 eb = fma2(t2[2 * c + 1], ss2, sub2(nref2, wb));
                             } else {
@@ -554,19 +609,26 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     float tmin = INFINITY, tmin_b = INFINITY;   // two chains
 #pragma unroll
                     for (int c = 0; c < CPT / 4; ++c) {
-                        const float4 vq = lds128(line + c * 16);   // broadcast read of the warp's line
-                        // Gaussian: |u|^2 is the same for the whole row, so it is left out of t here and added to the
-                        // block minimum / subtracted with the reference exponent below (one FADD2 per four values less)
-                        const float2 wa = make_float2(vq.x, vq.y), wb = make_float2(vq.z, vq.w);
-                        const float2 ta = neg_log2_kernel2<KID>(t2[2 * c], nss2, KID == KMB_KERNEL_GAUSSIAN ? wa : add2(wa, un2));
-                        const float2 tb = neg_log2_kernel2<KID>(t2[2 * c + 1], nss2, KID == KMB_KERNEL_GAUSSIAN ? wb : add2(wb, un2));
+                        float2 ta, tb;
+                        if constexpr (XK) {
+                            ta = xk_t(t2[2 * c]);
+                            tb = xk_t(t2[2 * c + 1]);
+                        } else {
+                            const float4 vq = lds128(line + c * 16);   // broadcast read of the warp's line
+                            // Gaussian: |u|^2 is the same for the whole row, so it is left out of t here and added to the
+                            // block minimum / subtracted with the reference exponent below (one FADD2 per four values less)
+                            const float2 wa = make_float2(vq.x, vq.y), wb = make_float2(vq.z, vq.w);
+                            ta = neg_log2_kernel2<KID>(t2[2 * c], nss2, KID == KMB_KERNEL_GAUSSIAN ? wa : add2(wa, un2));
+                            tb = neg_log2_kernel2<KID>(t2[2 * c + 1], nss2, KID == KMB_KERNEL_GAUSSIAN ? wb : add2(wb, un2));
+                        }
                         t2[2 * c] = ta;
                         t2[2 * c + 1] = tb;
                         tmin = fminf(fminf(tmin, ta.x), ta.y);
                         tmin_b = fminf(fminf(tmin_b, tb.x), tb.y);
                     }
                     tmin = fminf(tmin, tmin_b);
-                    const float cm = kRowTermOut ? -(tmin + un) : -tmin * t_scale<KID>();   // largest log2 k of the block
+                    const float tsc = XK ? xk_tscale : t_scale<KID>();                 // t = tsc T
+                    const float cm = kRowTermOut ? -(tmin + un) : -tmin * tsc;         // largest log2 k of the block
                     // lazy rescale: keep the reference exponent unless the maximum outgrew it by 2^8
                     bool need = false;
                     if (ref == -INFINITY) ref = cm;   // nothing but zero weights so far
@@ -594,8 +656,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     const float2 nref2 = make_float2(nref, nref);
 #pragma unroll
                     for (int c = 0; c < CPT / 2; ++c)
-                        weight(c, (KID == KMB_KERNEL_GAUSSIAN) ? sub2(nref2, t2[c])
-                                                                : fma2(t2[c], make_float2(-t_scale<KID>(), -t_scale<KID>()), nref2));
+                        weight(c, (KID == KMB_KERNEL_GAUSSIAN) ? sub2(nref2, t2[c]) : fma2(t2[c], make_float2(-tsc, -tsc), nref2));
                 }
                 KMB_T(4);
                 {
@@ -734,16 +795,16 @@ __global__ void __launch_bounds__(THREADS, 1)
 kprod_tensor_pv16_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                          const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                          const __grid_constant__ CUtensorMap map_sh, const __grid_constant__ CUtensorMap map_sl,
-                         const Params P) {
-    pv16_body<KID, NORM, false>(map_ah, map_al, map_bh, map_bl, map_sh, map_sl, P);
+                         const __grid_constant__ CUtensorMap map_ue, const __grid_constant__ CUtensorMap map_ve, const Params P) {
+    pv16_body<KID, NORM, false>(map_ah, map_al, map_bh, map_bl, map_sh, map_sl, map_ue, map_ve, P);
 }
 template <int KID, bool NORM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 kprod_tensor_pv16_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                               const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                               const __grid_constant__ CUtensorMap map_sh, const __grid_constant__ CUtensorMap map_sl,
-                              const Params P) {
-    pv16_body<KID, NORM, true>(map_ah, map_al, map_bh, map_bl, map_sh, map_sl, P);
+                              const __grid_constant__ CUtensorMap map_ue, const __grid_constant__ CUtensorMap map_ve, const Params P) {
+    pv16_body<KID, NORM, true>(map_ah, map_al, map_bh, map_bl, map_sh, map_sl, map_ue, map_ve, P);
 }
 
 // ---- signal planes -----------------------------------------------------------------------------------
@@ -794,6 +855,36 @@ static __global__ void transpose_split_signal_f16_kernel(const float* __restrict
     lo[at] = __float2half_rn(v - __half2float(h));
 }
 
+// Norm tiles of the extra K step (extra_k): rows of 64 BF16 (one 128-byte swizzle atom wide, 16 columns used).
+//   ue[i] = [a0 a1 a2 1 1 1 0 ..]   a0 + a1 + a2 = -|u_i|^2 / sscale  (three BF16 pieces: 24 significant bits)
+//   ve[j] = [1 1 1 b0 b1 b2 0 ..]   b0 + b1 + b2 = -|v_j|^2 / sscale;  padded sources (j >= M): b0 = -3e38, so that their
+//                                   accumulator is -3e38 and their weight an exact zero (their v rows are zero-filled by TMA)
+static __global__ void __launch_bounds__(256) norm_tiles_kernel(const float* __restrict__ un, const float* __restrict__ vn,
+                                                                const float* __restrict__ sscale, long long N, long long M, long long Mp,
+                                                                __nv_bfloat16* __restrict__ ue, __nv_bfloat16* __restrict__ ve) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= N + Mp) return;
+    const bool is_u = i < N;
+    const long long j = is_u ? i : i - N;
+    const float inv = 1.f / __ldg(sscale + 1);   // 2^2p: exact
+    float val = is_u ? -un[j] * inv : (j < M ? -vn[j] * inv : -3.0e38f);
+    __nv_bfloat16 pc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        pc[k] = __float2bfloat16_rn(val);
+        val -= __bfloat162float(pc[k]);
+    }
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+    __nv_bfloat16* row = (is_u ? ue : ve) + j * 64;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+        __nv_bfloat16 v = zero;
+        if (c < 3) v = is_u ? pc[c] : one;
+        else if (c < 6) v = is_u ? one : pc[c - 3];
+        row[c] = v;
+    }
+}
+
 }  // namespace pv16
 
 namespace {
@@ -806,7 +897,7 @@ struct Pv16Plan {
     long long n_tiles, nsb, Mp;
     tc::WavePlan waves;
     size_t off_center, off_stats, off_sscale, off_uh, off_ul, off_vh, off_vl, off_un, off_vn, off_sh, off_sl, off_bmax, off_bscale,
-        off_binv, off_partial, off_olong, off_counter, total;
+        off_binv, off_partial, off_olong, off_counter, off_ue, off_ve, total;
 };
 
 int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
@@ -828,7 +919,7 @@ int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
     pl->pair = pair_enabled && pl->n_tiles >= 2 && sms >= 2;
     pl->grid = pl->pair ? sms / 2 * 2 : sms;
     const int slot = pl->pair ? pv16::SLOT_BYTES / 2 : pv16::SLOT_BYTES;
-    const int fixed = 1024 + pl->kblocks * 2 * pv16::A_TILE_BYTES + pv16::EPI_WARPS * 2 * pv16::CPT * 4 + 2 * pv16::NG * tc::TM * 4 + 512;
+    const int fixed = 1024 + (pl->kblocks * 2 + (pv16::kExtraK ? 1 : 0)) * pv16::A_TILE_BYTES + pv16::EPI_WARPS * 2 * pv16::CPT * 4 + 2 * pv16::NG * tc::TM * 4 + 512;
     pl->stages = std::min(pl->pair ? 10 : 6, (smem_max - fixed) / slot);
     if (pl->stages < 3) return set_error(KMB_ERR_UNSUPPORTED, "not enough shared memory for D=%d", D);
     pl->smem = fixed + pl->stages * slot;
@@ -854,6 +945,8 @@ int plan_pv16(int64_t N, int64_t M, int D, int E, Pv16Plan* pl) {
     pl->off_partial = take(sizeof(float) * pl->waves.partial_slots * tc::TM * pv16::PS);
     pl->off_olong = take(sizeof(float) * pl->grid * pv16::NG * pv16::MAX_EB * tc::TM);
     pl->off_counter = take(sizeof(int) * pl->n_tiles);
+    pl->off_ue = take(pv16::kExtraK ? static_cast<size_t>(N) * 128 : 0);     // norm tiles of the extra K step: 64 BF16 per row
+    pl->off_ve = take(pv16::kExtraK ? static_cast<size_t>(pl->Mp) * 128 : 0);
     pl->total = o;
     return KMB_OK;
 }
@@ -863,11 +956,11 @@ int launch_pv16(const CUtensorMap* m, const pv16::Params& P, int grid, int smem,
     if (pair) {
         auto fn = pv16::kprod_tensor_pv16_pair_kernel<KID, NORM>;
         if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(fn), smem)) return rc;
-        fn<<<grid, pv16::THREADS, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
+        fn<<<grid, pv16::THREADS, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], P);
     } else {
         auto fn = pv16::kprod_tensor_pv16_kernel<KID, NORM>;
         if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(fn), smem)) return rc;
-        fn<<<grid, pv16::THREADS, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
+        fn<<<grid, pv16::THREADS, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], P);
     }
     KMB_CUDA_CHECK(cudaGetLastError());
     return KMB_OK;
@@ -920,12 +1013,26 @@ int tensor_pv16_product(const float* x, const float* y, const float* b, float* o
         KMB_CUDA_CHECK(cudaGetLastError());
         count_launch(3);
     }
-    CUtensorMap maps[6];
+    CUtensorMap maps[8];
     if (int rc = tc::make_tensor_map_f16(&maps[0], uh, N, pl.Dp, tc::TM)) return rc;
     if (int rc = tc::make_tensor_map_f16(&maps[1], ul, N, pl.Dp, tc::TM)) return rc;
     // CTA pairs: each CTA loads 64 of a block's 128 sources and half of the pass's signal columns
     if (int rc = tc::make_tensor_map_f16(&maps[2], vh, M, pl.Dp, pl.pair ? pv16::TNS / 2 : pv16::TNS)) return rc;
     if (int rc = tc::make_tensor_map_f16(&maps[3], vl, M, pl.Dp, pl.pair ? pv16::TNS / 2 : pv16::TNS)) return rc;
+    const bool xk = (kid == KMB_KERNEL_GAUSSIAN) ? pv16::extra_k<KMB_KERNEL_GAUSSIAN>() : pv16::extra_k<KMB_KERNEL_ABSOLUTE_EXPONENTIAL>();
+    if (xk) {   // |u|^2, |v|^2 as operands of one more K step (16-bit elements: the FP16 map serves BF16 rows as well)
+        const long long rows = N + pl.Mp;
+        pv16::norm_tiles_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, stream>>>(
+            F(pl.off_un), F(pl.off_vn), F(pl.off_sscale), N, M, pl.Mp, reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ue),
+            reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ve));
+        KMB_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+        if (int rc = tc::make_tensor_map_f16(&maps[6], ws + pl.off_ue, N, 64, tc::TM)) return rc;
+        if (int rc = tc::make_tensor_map_f16(&maps[7], ws + pl.off_ve, pl.Mp, 64, pl.pair ? pv16::TNS / 2 : pv16::TNS)) return rc;
+    } else {
+        maps[6] = maps[0];
+        maps[7] = maps[2];
+    }
 
     const int n_passes = pl.Ep / pv16::MAX_EB;
     for (int pass = 0; pass < n_passes; ++pass) {
