@@ -58,7 +58,7 @@ constexpr int PANEL_BYTES = 64 * 128;  // signal: 64 signal columns x 64 sources
 #define KMB_PV16_SST 3
 #endif
 #ifndef KMB_PV16_FUSED
-#define KMB_PV16_FUSED 1
+#define KMB_PV16_FUSED 2
 #endif
 #ifndef KMB_PV16_EXTRAK
 #define KMB_PV16_EXTRAK 1
@@ -562,8 +562,10 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     // side.  The lazy reference moves in a handful of blocks per row tile; only then (or while a row has
                     // no reference yet) is the block redone in two phases below, from S, which is still in tensor memory.
                     // Gaussian kernel: the two phases leave the MUFU pipe idle through the whole log2 k phase (C4 shape:
-                    // 45.1 -> 42.7 ms).  Exponential kernel: sqrt -> exponent -> ex2 in one chain is no faster than the two
-                    // MUFU-bound phases (52.3 against 51.4 ms), so it keeps them (profiles/r2_pv16_fused_ab.jsonl).
+                    // 45.1 -> 42.7 ms).  Exponential kernel: sqrt -> exponent -> ex2 in one chain was slower than the two
+                    // MUFU-bound phases while the chain began with the |v|^2 line (52.3 against 51.4 ms); with the norms out of
+                    // the tensor cores (extra_k) it is level to slightly ahead (49.8 against 50.2 ms) and used for both
+                    // (profiles/r2_pv16_fused_ab.jsonl, r2_pv16_extra_k_ab.jsonl).
                     if (__all_sync(0xffffffffu, ref != -INFINITY)) {
                         const float nref = kRowTermOut ? -ref - un : -ref;
                         const float2 nref2 = make_float2(nref, nref), ss2 = make_float2(sscale, sscale);
