@@ -90,8 +90,9 @@ constexpr int PS = MAX_EB + 2;         // partial record: O row, sum of weights,
 // So O_g only collects kFlushBlocks source blocks; then the epilogue adds it (round-to-nearest, L2 reductions the thread
 // does not wait for) to a per-(CTA, group) FP32 accumulator in global memory and the next P.B starts from zero.
 // Measured at C4 (M = 262144): flush every 2048 blocks (= never) 2.4e-4, every 32 blocks 3.6e-6 at +6 % time (the L2
-// reductions of 148 CTAs arrive together).
-constexpr int kFlushBlocks = 256 / NG;   // default of Params::flush_blocks: 768 accumulating MMAs per O_g and flush, ~1.5e-5
+// reductions of 148 CTAs arrive together).  With NG = 2 a group makes 12 accumulating MMAs per block: every 128 blocks
+// (1536 MMAs) 3.0e-5, every 64 blocks 1.4e-5 at +0.3 % (exponential) / +1.5 % (Gaussian) -- profiles/r2_pv16_variants_ab.jsonl.
+constexpr int kFlushBlocks = 128;        // default of Params::flush_blocks
 
 struct Params {
     const float* un;
