@@ -41,7 +41,16 @@ def _check_precision(precision, who, allowed=(np.float32,)):
     return dt
 
 
-_CAST_THREADS = 4            # host threads of one cast (numpy releases the GIL inside copyto)
+def _cast_threads():
+    """Host threads of one cast (numpy releases the GIL inside copyto): 4, fewer when several ranks share the host's cores
+    (torchrun's LOCAL_WORLD_SIZE) -- eight ranks with four threads each on sixteen cores only get in each other's way."""
+    import os
+
+    local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(1, min(4, (os.cpu_count() or 4) // local))
+
+
+_CAST_THREADS = _cast_threads()
 _CAST_MIN_BYTES = 2 << 20    # below this a single pass is faster than handing out slices (C2: the 4 MB result and signal are above it)
 _cast_pool = None
 
