@@ -60,6 +60,9 @@ constexpr int PANEL_BYTES = 64 * 128;  // signal: 64 signal columns x 64 sources
 #ifndef KMB_PV16_FUSED
 #define KMB_PV16_FUSED 2
 #endif
+#ifndef KMB_PV16_FHSPLIT
+#define KMB_PV16_FHSPLIT 1
+#endif
 #ifndef KMB_PV16_EXTRAK
 #define KMB_PV16_EXTRAK 1
 #endif
@@ -70,6 +73,10 @@ constexpr int kFused = KMB_PV16_FUSED;   // one pass per block with the row's cu
 // -2^2p |u_i|^2 against ones and ones against three pieces of -2^2p |v_j|^2, so that the accumulator holds (2 u.v - |u|^2 - |v|^2) / sscale
 // = -d2 / sscale and the epilogue needs neither the shared-memory line of |v|^2 nor a packed add per pair.  0 never, 1 exponential
 // kernel, 2 both kernels.
+// hi / lo split of a weight: 1 = hi by one F2FP (round to nearest), -lo = hi - w by the mixed-precision FHADD of sm_100a (f16 + f32),
+// the lo plane stored negated and the P_lo.B_hi MMA negating its A operand (instruction descriptor bit 13): 4 instructions per two
+// weights; 0 = mask + packed subtract + two F2FP: 5.
+constexpr bool kFhSplit = KMB_PV16_FHSPLIT != 0;
 constexpr int kExtraK = KMB_PV16_EXTRAK;
 template <int KID>
 __host__ __device__ constexpr bool extra_k() { return kExtraK == 2 || (kExtraK == 1 && KID == KMB_KERNEL_ABSOLUTE_EXPONENTIAL); }
@@ -364,7 +371,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                     const uint64_t bl = umma_desc_sw128(sg + (2 + panel) * PANEL, koff);
                     const uint32_t a_hi = p_base + g * CPT + kk * 8, a_lo = a_hi + CPT / 2;
                     const uint32_t d_g = d_o + g * MAX_EB;
-                    mma_ts(d_g, a_lo, bh, idesc_o, !(from_zero && kk == 0));
+                    mma_ts(d_g, a_lo, bh, idesc_o | (kFhSplit ? (1u << 13) : 0u), !(from_zero && kk == 0));   // (-) P_lo . B_hi
                     mma_ts(d_g, a_hi, bl, idesc_o, 1);
                     mma_ts(d_g, a_hi, bh, idesc_o, 1);
                 }
@@ -550,12 +557,22 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 auto weight = [&](int c, float2 e) {     // exponent -> weight -> planes (2 MUFU.EX2 + 7 instructions)
                     const float2 pw = make_float2(ex2_approx(e.x), ex2_approx(e.y));
                     kacc = add2(kacc, pw);
-                    // 11 significant bits: exact in FP16
-                    const float2 h = make_float2(__uint_as_float(__float_as_uint(pw.x) & 0xffffe000u),
-                                                 __uint_as_float(__float_as_uint(pw.y) & 0xffffe000u));
-                    const float2 l = sub2(pw, h);
-                    ph[c] = pack_half2(h.x, h.y);
-                    pl[c] = pack_half2(l.x, l.y);
+                    if constexpr (kFhSplit) {
+                        const uint32_t hi2 = pack_half2(pw.x, pw.y);
+                        float nlx, nly;   // hi - w: exact in FP32 (hi is within 2^-11 of w)
+                        asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\nsub.rn.f32.f16 %0, l, %3;\nsub.rn.f32.f16 %1, h, %4;\n}"
+                            : "=f"(nlx), "=f"(nly)
+                            : "r"(hi2), "f"(pw.x), "f"(pw.y));
+                        ph[c] = hi2;
+                        pl[c] = pack_half2(nlx, nly);   // -lo
+                    } else {
+                        // 11 significant bits: exact in FP16
+                        const float2 h = make_float2(__uint_as_float(__float_as_uint(pw.x) & 0xffffe000u),
+                                                     __uint_as_float(__float_as_uint(pw.y) & 0xffffe000u));
+                        const float2 l = sub2(pw, h);
+                        ph[c] = pack_half2(h.x, h.y);
+                        pl[c] = pack_half2(l.x, l.y);
+                    }
                 };
                 bool done = false;
                 if constexpr (kFused == 2 || (kFused == 1 && KID == KMB_KERNEL_GAUSSIAN)) {
