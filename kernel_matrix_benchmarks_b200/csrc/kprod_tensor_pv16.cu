@@ -556,7 +556,7 @@ __device__ __forceinline__ void pv16_body(const CUtensorMap& map_ah, const CUten
                 float2 kacc = make_float2(0.f, 0.f);     // two-level sum of the weights (see kprod_direct.cuh)
                 auto weight = [&](int c, float2 e) {     // exponent -> weight -> planes (2 MUFU.EX2 + 7 instructions)
                     const float2 pw = make_float2(ex2_approx(e.x), ex2_approx(e.y));
-                    kacc = add2(kacc, pw);
+                    if constexpr (NORM) kacc = add2(kacc, pw);   // the plain product never divides by the sum of the weights
                     if constexpr (kFhSplit) {
                         const uint32_t hi2 = pack_half2(pw.x, pw.y);
                         float nlx, nly;   // hi - w: exact in FP32 (hi is within 2^-11 of w)
