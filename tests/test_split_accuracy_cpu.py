@@ -113,3 +113,71 @@ def test_per_group_lazy_online_softmax_merges_exactly():
     w = np.exp2(ref - rmax[None, :])
     got = (w[:, :, None] * O).sum(0) / (w * ks).sum(0)[:, None]
     assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
+# ---- the squared norms as one more (BF16) K step of the S contraction, and the F2FP + FHADD split of the weights ------
+# (kprod_tensor_pv16.cu: norm_tiles_kernel, the `weight` step of the epilogue) restated in NumPy
+
+def to_bf16(x):
+    """__float2bfloat16_rn: round to nearest even on the 16 dropped bits (finite inputs)."""
+    u = np.float32(x).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def norm_pieces(val):
+    """Three BF16 pieces of val, each the rounding of what is left (norm_tiles_kernel)."""
+    val = np.float32(val)
+    pieces = []
+    for _ in range(3):
+        p = to_bf16(val)
+        pieces.append(p)
+        val = np.float32(val - p)
+    return pieces
+
+
+def test_three_bf16_pieces_carry_a_squared_norm_to_fp32_precision():
+    rng = np.random.RandomState(3)
+    # -|u|^2 / sscale for data scaled into [2^13, 2^14) per coordinate, D = 1 ... 128; and tiny / zero norms
+    val = -np.float32(np.concatenate([rng.rand(20000) * 128 * 2.0 ** 28, rng.rand(2000) * 1e-3, [0.0, 1.0, 2.0 ** 34]]))
+    p0, p1, p2 = norm_pieces(val)
+    back = p0.astype(np.float64) + p1.astype(np.float64) + p2.astype(np.float64)
+    nz = val != 0
+    assert np.abs(back[nz] - val[nz].astype(np.float64)).max() <= 0   # 8 + 8 + 8 significant bits: the FP32 value exactly
+    assert (back[~nz] == 0).all()
+    # what the tensor cores add up for one (row, source): the ones columns pick the pieces of both norms, in FP32
+    un, vn = val[:1000].astype(np.float64), val[1000:2000].astype(np.float64)
+    a, b = norm_pieces(val[:1000]), norm_pieces(val[1000:2000])
+    acc = sum(x.astype(np.float64) for x in a) + sum(x.astype(np.float64) for x in b)
+    assert np.abs(acc - (un + vn)).max() == 0
+
+
+def test_padded_sources_get_a_finite_marker_that_no_norm_can_offset():
+    p0, p1, p2 = norm_pieces(np.float32(-3.0e38))
+    back = float(p0) + float(p1) + float(p2)
+    assert np.isfinite([p0, p1, p2]).all() and back < -2.9e38
+    # the largest -|u|^2 / sscale a row can carry (128 coordinates below 2^14) does not move it, nor does sscale below 1 make it a NaN
+    assert np.isfinite(np.float32(back) + np.float32(-128 * 2.0 ** 28))
+    for sscale in (2.0 ** -40, 1.0, 2.0 ** 40):
+        d2 = -np.float32(sscale) * np.float32(back)          # what the epilogue turns the accumulator into
+        assert d2 > 1e20 and not np.isnan(d2)                 # weight 2^-d2 (Gaussian) or 2^-sqrt(.) (exponential): an exact zero
+
+
+def test_f2fp_fhadd_split_of_a_weight_keeps_22_bits():
+    """hi = fp16_rn(w); -lo = fp16_rn(hi - w), the difference exact in FP32 (FHADD); the MMA negates the lo plane."""
+    rng = np.random.RandomState(5)
+    w = np.float32(2.0 ** rng.uniform(-3.0, 8.0, 200000))    # weights 2^(log2 k - ref) <= 2^8 whose lo part is a normal FP16
+    hi = w.astype(np.float16)
+    nl = (hi.astype(np.float32) - w).astype(np.float32)       # exact: |hi - w| <= 2^-11 w, both on w's FP32 grid
+    assert (nl.astype(np.float64) == hi.astype(np.float64) - w.astype(np.float64)).all()
+    neg_lo = nl.astype(np.float16)
+    back = hi.astype(np.float64) - neg_lo.astype(np.float64)
+    assert (np.abs(back - w.astype(np.float64)) / w).max() <= 2.0 ** -22
+    # smaller weights: the lo part (then hi as well) falls into FP16's subnormals and the planes lose bits, but the absolute
+    # error stays at half a subnormal step, 2^-25 -- of a row whose largest weight is at least 1 (the lazy reference)
+    small = np.float32(2.0 ** rng.uniform(-40.0, -3.0, 100000))
+    h2 = small.astype(np.float16)
+    d2 = (h2.astype(np.float32) - small).astype(np.float32)
+    assert (d2.astype(np.float64) == h2.astype(np.float64) - small.astype(np.float64)).all()
+    l2 = d2.astype(np.float16)
+    assert np.abs(h2.astype(np.float64) - l2.astype(np.float64) - small).max() <= 2.0 ** -25
