@@ -387,7 +387,7 @@ class B200Product(BaseProduct):
         return super().get_memory_usage() + torch.cuda.memory_allocated(self.device) / 1024
 
     def done(self):
-        for k in ("source_points", "target_points", "source_signal", "res_device", "_prepared", "_group", "_ys", "_xs", "_bs"):
+        for k in ("source_points", "target_points", "source_signal", "res_device", "res", "_prepared", "_group", "_ys", "_xs", "_bs"):
             self.__dict__.pop(k, None)
         self._group = None
         self.workspace = Workspace()
@@ -609,7 +609,7 @@ class B200Solver(BaseSolver):
         return super().get_memory_usage() + torch.cuda.memory_allocated(self.device) / 1024
 
     def done(self):
-        for k in ("source_points", "target_signal", "ops", "_ops", "_precond", "x_full", "_group", "_ys"):
+        for k in ("source_points", "target_signal", "ops", "_ops", "_precond", "x_full", "res", "_group", "_ys"):
             self.__dict__.pop(k, None)
         self._group = None
 
