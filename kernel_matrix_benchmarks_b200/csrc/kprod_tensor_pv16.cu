@@ -894,15 +894,19 @@ static __global__ void __launch_bounds__(256) norm_tiles_kernel(const float* __r
         pc[k] = __float2bfloat16_rn(val);
         val -= __bfloat162float(pc[k]);
     }
-    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
-    __nv_bfloat16* row = (is_u ? ue : ve) + j * 64;
+    // one 16-byte store of the six live columns (+ two zeros), seven of zeros: rows are 128 bytes
+    const unsigned short one = 0x3f80;   // BF16 1.0
+    unsigned short h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int c = 0; c < 64; ++c) {
-        __nv_bfloat16 v = zero;
-        if (c < 3) v = is_u ? pc[c] : one;
-        else if (c < 6) v = is_u ? one : pc[c - 3];
-        row[c] = v;
+    for (int k = 0; k < 3; ++k) {
+        h[k] = is_u ? __bfloat16_as_ushort(pc[k]) : one;
+        h[3 + k] = is_u ? one : __bfloat16_as_ushort(pc[k]);
     }
+    uint4* row = reinterpret_cast<uint4*>((is_u ? ue : ve) + j * 64);
+    row[0] = make_uint4(h[0] | (static_cast<unsigned>(h[1]) << 16), h[2] | (static_cast<unsigned>(h[3]) << 16),
+                        h[4] | (static_cast<unsigned>(h[5]) << 16), 0u);
+#pragma unroll
+    for (int c = 1; c < 8; ++c) row[c] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 }  // namespace pv16
